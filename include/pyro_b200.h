@@ -1,0 +1,283 @@
+/*
+ * pyro_b200.h -- C ABI of the B200-native numerics library behind Pyro's two hot paths
+ * (Trace_ELBO SVI step, NUTS/HMC leapfrog).
+ *
+ * Every entry point replaces one piece of arithmetic that reference Pyro (pyro-ppl/pyro 1.9.1)
+ * executes as a chain of ATen launches.  The reference-side binding is a ctypes stub
+ * (see INTEGRATION.md); there are no torch types in any signature.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers owned by the caller.  The library never allocates,
+ *     frees or retains them beyond the call.  `stream` is a cudaStream_t passed as void*.
+ *   - Every function returns B2_OK (0) or a negative B2_ERR_* code; nothing throws or aborts.
+ *     Numerical failures are data (NaN / -inf in outputs), exactly like the reference, where a
+ *     NaN energy means "reject" (pyro/infer/mcmc/nuts.py:209-214).
+ *   - Functions are re-entrant and stream ordered, do not synchronise, and are CUDA-graph
+ *     capturable.  Reductions use a fixed order (no floating-point atomics): results are
+ *     bit-stable from run to run for a given shape.
+ *   - Tensors are described by b2_tensor: a common broadcast shape and per-operand element
+ *     strides (0 = broadcast along that dim), so Pyro's ExpandedDistribution / MaskedDistribution /
+ *     Independent views (pyro/distributions/torch_distribution.py:163-232,302-374,399-488)
+ *     never need a copy.
+ */
+#ifndef PYRO_B200_H_
+#define PYRO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_MAX_DIMS 8
+
+/* ---- error codes ------------------------------------------------------------------------ */
+#define B2_OK 0
+#define B2_ERR_BAD_DTYPE (-1)
+#define B2_ERR_BAD_SHAPE (-2)
+#define B2_ERR_BAD_FAMILY (-3)
+#define B2_ERR_NULL (-4)
+#define B2_ERR_WORKSPACE (-5)
+#define B2_ERR_UNSUPPORTED_REDUCTION (-6) /* gradient output broadcast pattern not fused; caller
+                                             asks for a full-shape gradient and reduces it */
+#define B2_ERR_LAUNCH (-7)                /* cudaGetLastError() != cudaSuccess after launch */
+#define B2_ERR_TOO_LARGE (-8)
+#define B2_ERR_NO_DEVICE (-9)
+
+/* ---- dtypes ------------------------------------------------------------------------------ */
+#define B2_F32 0
+#define B2_F64 1
+#define B2_I64 2
+#define B2_U8 3 /* torch.bool / uint8 masks */
+
+/* ---- distribution families ---------------------------------------------------------------
+ * Elementwise families (event_dim 0).  Parameter order is fixed, as listed.
+ * Formulas restate torch.distributions (the third-party arithmetic the reference delegates to,
+ * pyro/distributions/torch.py:23-257), see SURVEY.md Appendix A. */
+#define B2_NORMAL 0            /* (loc, scale)            torch/distributions/normal.py:87-102    */
+#define B2_BERNOULLI_LOGITS 1  /* (logits)                torch/distributions/bernoulli.py:121-125 */
+#define B2_GAMMA 2             /* (concentration, rate)   torch/distributions/gamma.py:89-98      */
+#define B2_BETA 3              /* (concentration1, concentration0)  beta.py:87-91                 */
+#define B2_POISSON 4           /* (rate)                  torch/distributions/poisson.py:75-79    */
+#define B2_CAUCHY 5            /* (loc, scale)            torch/distributions/cauchy.py:81-88     */
+#define B2_HALFCAUCHY 6        /* (scale)                 torch/distributions/half_cauchy.py:73-81 */
+#define B2_EXPONENTIAL 7       /* (rate)                  torch/distributions/exponential.py      */
+#define B2_LOGNORMAL 8         /* (loc, scale)            log_normal.py (Normal o Exp transform)  */
+#define B2_HALFNORMAL 9        /* (scale)                 torch/distributions/half_normal.py      */
+#define B2_BERNOULLI_PROBS 10  /* (probs)                 bernoulli.py (probs parametrisation)    */
+#define B2_UNIFORM 11          /* (low, high)             torch/distributions/uniform.py          */
+#define B2_KL_NORMAL_NORMAL 12 /* value unused; (loc_p, scale_p, loc_q, scale_q) kl.py:468-471    */
+#define B2_KL_GAMMA_GAMMA 13   /* value unused; (conc_p, rate_p, conc_q, rate_q) kl.py:301-306    */
+#define B2_NUM_ELEMENTWISE_FAMILIES 14
+/* Event families (event_dim >= 1), scored by b2_event_score. */
+#define B2_DIRICHLET 32   /* (concentration[...,K])           torch/distributions/dirichlet.py:90-97 */
+#define B2_CATEGORICAL 33 /* (logits[...,K]), int64 value      categorical.py:78,151-157             */
+#define B2_MVN_TRIL 34    /* (loc[...,n], scale_tril[...,n,n]) multivariate_normal.py:256-264        */
+
+#define B2_MAX_PARAMS 4
+
+typedef struct {
+  void* ptr;
+  int32_t dtype;
+  int32_t ndim;
+  int64_t shape[B2_MAX_DIMS];
+  int64_t stride[B2_MAX_DIMS]; /* in elements; 0 = broadcast */
+} b2_tensor;
+
+/* flags for b2_site_score */
+#define B2_FLAG_ACCUMULATE_SUM 1 /* out_sum += coeff*sum instead of out_sum = coeff*sum */
+
+/*
+ * b2_site_score -- fused log_prob + score of one sample site for an elementwise family.
+ *
+ * Replaces, in one pass over the operands:
+ *   site["fn"].log_prob(value)                      pyro/poutine/trace_struct.py:225,264,304
+ *   scale_and_mask(log_p, scale, mask)              pyro/distributions/util.py:311-328
+ *   log_p.sum()                                     pyro/poutine/trace_struct.py:240,278
+ *   and the autograd backward of those ATen chains  (pyro/infer/trace_elbo.py:153-157)
+ *
+ * All tensors are expressed on ONE common broadcast shape (value->shape); params[i], mask,
+ * upstream and the outputs carry their own strides (0 where broadcast).
+ *
+ *   lp_i      = family log density at element i
+ *   m_i       = mask ? mask_i : 1
+ *   out_logprob_i = m_i ? scale*lp_i : 0            (if out_logprob != NULL)
+ *   out_sum   (=|+=) sum_coeff * SUM_i m_i*scale*lp_i  (if out_sum != NULL; dtype of value)
+ *   u_i       = upstream ? upstream_i : 1
+ *   grad of operand o at i:  weight * u_i * m_i * scale * d lp_i / d o
+ * Gradient outputs (out_dvalue, out_dparams[k]; ptr may be NULL = not wanted) are written to a
+ * tensor that is either full shape (no zero stride on a dim of size > 1) or a scalar (all strides
+ * zero: the gradient is summed over every element).  Any other broadcast pattern returns
+ * B2_ERR_UNSUPPORTED_REDUCTION without launching.
+ *
+ * workspace: b2_site_score_workspace() bytes, zero-initialised ONCE by the caller; the library
+ * leaves it zeroed.  Must not be shared by kernels running concurrently on different streams.
+ */
+int b2_site_score(int family, const b2_tensor* value, const b2_tensor* params, int n_params,
+                  const b2_tensor* mask, double scale, const b2_tensor* upstream, double weight,
+                  double sum_coeff, int flags, b2_tensor* out_logprob, void* out_sum,
+                  b2_tensor* out_dvalue, b2_tensor* out_dparams, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+size_t b2_site_score_workspace(void);
+
+/*
+ * b2_event_score -- fused log_prob (+ gradients) for families with an event dimension.
+ * `batch` describes the common batch shape; the event dims are the trailing dims of each
+ * operand and must be contiguous.
+ *   DIRICHLET:   params[0]=concentration[batch,K], value[batch,K]
+ *   CATEGORICAL: params[0]=logits[batch,K] (un-normalised; normalised inside exactly like the
+ *                constructor's logits - logsumexp), value int64 [batch]
+ *   MVN_TRIL:    params[0]=loc[batch,n], params[1]=scale_tril[batch,n,n], value[batch,n]
+ * out_logprob is [batch] (scaled/masked like b2_site_score); gradients, when requested, are full
+ * shape [batch, event...] or, for a batch-broadcast operand (all batch strides zero), reduced
+ * over the batch.
+ */
+int b2_event_score(int family, const b2_tensor* value, const b2_tensor* params, int n_params,
+                   int event_size, const b2_tensor* mask, double scale, const b2_tensor* upstream,
+                   double weight, double sum_coeff, int flags, b2_tensor* out_logprob,
+                   void* out_sum, b2_tensor* out_dvalue, b2_tensor* out_dparams, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/*
+ * b2_reduce_to -- sum a strided full-shape tensor down to an output whose zero strides mark the
+ * reduced dims (the "sum_to_size" the fused kernels do not cover in-kernel).
+ */
+int b2_reduce_to(const b2_tensor* src, b2_tensor* dst, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/*
+ * b2_glm_bernoulli_logits -- fused Bayesian-logistic-regression likelihood term (BASELINE
+ * config 2): for P particles, logits[p,n] = <X[n,:], W[p,:]> + b[p];
+ *   sum_p[p]  = SUM_n ( y[n]*logits - softplus(logits) )               (Bernoulli log_prob)
+ *   dW[p,:]   = weight * SUM_n (y[n] - sigmoid(logits[p,n])) * X[n,:]
+ *   db[p]     = weight * SUM_n (y[n] - sigmoid(logits[p,n]))
+ * X and y are read from HBM exactly once for value AND gradient.  Replaces the chain
+ * matmul -> Bernoulli(logits).log_prob -> sum -> backward (pyro/poutine/trace_struct.py:264-278
+ * applied to the model of tests/infer/mcmc/test_hmc.py:189-198).
+ * X: [N,D] row-major fp32 (16-byte aligned), D in {4, 8, 16, 32}; W: [P,D]; b: [P] (nullable);
+ * y: [N] fp32.
+ * out_total (nullable): scalar, (=|+=) sum_coeff * scale * SUM_p sum_p[p].
+ */
+int b2_glm_bernoulli_logits(const float* X, const float* y, const float* W, const float* b,
+                            int64_t N, int D, int P, double scale, double weight, double sum_coeff,
+                            int flags, float* out_sum_p, float* out_total, float* out_dW,
+                            float* out_db, void* workspace, size_t workspace_bytes, void* stream);
+size_t b2_glm_workspace(int64_t N, int D, int P);
+
+/* ---- optimisers --------------------------------------------------------------------------
+ * Multi-tensor fused updates replacing PyroOptim's per-parameter Python loop
+ * (pyro/optim/optim.py:117-155).  Per-tensor scalar state lives in DEVICE arrays so a captured
+ * CUDA graph can be replayed: `steps` (int32) and `lrs` (double) are advanced on device. */
+
+/*
+ * b2_clipped_adam -- pyro/optim/clipped_adam.py:62-98 for n tensors in one launch sequence:
+ *   lr <- lr*lrd;  g <- clamp(g, -clip, clip);  t += 1;  g += wd*p (if wd != 0)
+ *   m <- b1*m + (1-b1)*g;  v <- b2*v + (1-b2)*g*g
+ *   p <- p - lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps)
+ * ptr tables (device arrays of n device pointers): p, g, m, v; numel: device int64[n].
+ * hyper: device double[n*8] rows (beta1, beta2, eps, weight_decay, clip_norm, lrd, -, -); slot 6
+ * receives the bias-corrected step size computed on device.
+ * lrs: device double[n] (current lr, updated in place); steps: device int32[n] (updated).
+ * zero_grad != 0 also zeroes g (pyro/infer/util.py:85-91 fused in).  dtype: B2_F32 or B2_F64.
+ * total_numel/max_numel are host-side hints for grid sizing.
+ */
+int b2_clipped_adam(int n, void* const* p, void* const* g, void* const* m, void* const* v,
+                    const int64_t* numel, double* hyper, double* lrs, int32_t* steps, int dtype,
+                    int zero_grad, int64_t max_numel, void* stream);
+
+/*
+ * b2_adagrad_rmsprop -- pyro/optim/adagrad_rmsprop.py:54-87:
+ *   s = g*g (first step) else s <- (1-t)*s + t*g*g;  lr = eta*step^(-0.5+delta)
+ *   p <- p - lr*g/(1+sqrt(s))
+ * hyper: device double[n*4] rows (eta, delta, t, -); slot 3 receives the step's lr.
+ */
+int b2_adagrad_rmsprop(int n, void* const* p, void* const* g, void* const* s,
+                       const int64_t* numel, double* hyper, int32_t* steps, int dtype,
+                       int zero_grad, int64_t max_numel, void* stream);
+
+/* ---- HMC / NUTS --------------------------------------------------------------------------
+ * State layout: chains are the leading dim, [C, D] row-major ("one row per chain"). */
+
+/*
+ * b2_leapfrog_half_kick_drift / b2_leapfrog_half_kick -- the two elementwise halves of
+ * pyro/ops/integrator.py:45-65 (_single_step_verlet) over [C,D] with per-chain step size and
+ * diagonal inverse mass (pyro/infer/mcmc/adaptation.py:328-347 kinetic_grad):
+ *   kick_drift:  r <- r - (eps/2)*g ;  z <- z + eps * minv * r
+ *   kick:        r <- r - (eps/2)*g ;  ke[c] = 0.5 * SUM_d minv*r*r   (optional)
+ * eps: [C] (signed: direction folded in); minv: [C,D] or [D] (minv_chain_stride 0);
+ * active (nullable uint8 [C]): chains with active==0 are left untouched.
+ * workspace for the kinetic-energy reduction and the potentials: b2_mcmc_workspace(C) bytes.
+ */
+size_t b2_mcmc_workspace(int64_t C);
+int b2_leapfrog_half_kick_drift(void* z, void* r, const void* g, const void* eps,
+                                const void* minv, int64_t minv_chain_stride,
+                                const uint8_t* active, int64_t C, int64_t D, int dtype,
+                                void* stream);
+int b2_leapfrog_half_kick(void* r, const void* g, const void* eps, const void* minv,
+                          int64_t minv_chain_stride, const uint8_t* active, void* ke, int64_t C,
+                          int64_t D, int dtype, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* Native potentials ("compiled model classes").  U is the potential energy in UNCONSTRAINED
+ * space including the log|det J| of the constraining transforms, exactly as
+ * pyro/infer/mcmc/util.py:275-286 builds it. */
+#define B2_MODEL_HIER_NORMAL 0 /* eight_schools family, examples/eight_schools/mcmc.py:27-34:
+                                  z = [mu, log_tau, eta[J]];  mu~N(0,s_mu), tau~HalfCauchy(s_tau),
+                                  eta~N(0,1), y~N(mu+tau*eta, sigma).  data = (y[J], sigma[J]),
+                                  hyper = (s_mu, s_tau) */
+#define B2_MODEL_LOGISTIC 1    /* tests/infer/mcmc/test_hmc.py:189-198 family:
+                                  z = beta[D];  beta ~ Normal(0, s) i.i.d.,
+                                  y ~ Bernoulli(logits = X beta).  data = (X[J,D], y[J]),
+                                  hyper = (s) */
+
+typedef struct {
+  int32_t model;  /* B2_MODEL_* */
+  int32_t dtype;  /* B2_F32 / B2_F64 for state and data */
+  int64_t J;      /* data size */
+  int64_t D;      /* latent dimension of one chain */
+  const void* data0; /* y      | X[J, D]  */
+  const void* data1; /* sigma  | y[J]     */
+  double hyper[4];
+} b2_model;
+
+/*
+ * b2_potential_grad -- U[c] and dU/dz[c,:] for C chains in one launch
+ * (pyro/ops/integrator.py:68-94 potential_grad + pyro/infer/mcmc/util.py:275-286).
+ */
+int b2_potential_grad(const b2_model* model, const void* z, void* U, void* grad, int64_t C,
+                      const uint8_t* active, void* workspace, size_t workspace_bytes,
+                      void* stream);
+size_t b2_potential_workspace(const b2_model* model, int64_t C);
+
+/*
+ * b2_nuts_small -- whole NUTS transitions on device for a native model with small D
+ * (D <= B2_NUTS_SMALL_MAX_D): one warp per chain keeps (z, r, grad) and the tree
+ * bookkeeping in registers/shared memory; iterative tree doubling, multinomial sampling,
+ * U-turn checks and Philox draws happen without returning to the host
+ * (pyro/infer/mcmc/nuts.py:197-522).  Runs `num_transitions` transitions per chain.
+ *   z [C,D] in/out; U [C], grad [C,D] in/out (cached, nuts.py:480-494);
+ *   step_size [C]; minv [C,D] (diag inverse mass);
+ *   seed + chain offset feed a counter-based Philox stream (rng_counter [C] uint64 in/out);
+ *   samples_out (nullable) [num_transitions, C, D]; accept_prob_out [num_transitions, C];
+ *   depth_out / diverging_out / num_steps_out [num_transitions, C] int32.
+ */
+#define B2_NUTS_SMALL_MAX_D 64
+int b2_nuts_small(const b2_model* model, void* z, void* U, void* grad, const void* step_size,
+                  const void* minv, int64_t C, int num_transitions, int max_tree_depth,
+                  double max_delta_energy, uint64_t seed, uint64_t* rng_counter,
+                  void* samples_out, void* accept_prob_out, int32_t* depth_out,
+                  int32_t* diverging_out, int32_t* num_steps_out, void* stream);
+
+/* ---- misc -------------------------------------------------------------------------------- */
+const char* b2_last_error(int code);
+int b2_version(void);
+/* number of kernel launches issued by this library in this process (for bench.py's
+ * gpu_launches claim). */
+int64_t b2_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYRO_B200_H_ */

@@ -1,0 +1,449 @@
+// b2_math.cuh -- per-element densities and their partial derivatives.
+//
+// Everything here is __host__ __device__ so the SAME code is exercised on the CPU by the
+// test-only host harness (hostcheck.cu, used by tests/ to pin the arithmetic against the
+// oracle before any GPU time is spent) and on the device by the fused kernels.
+//
+// The formulas restate torch.distributions (the arithmetic reference Pyro delegates to through
+// pyro/distributions/torch.py:23-257); operation order follows the cited torch source so fp32
+// results agree with the reference to rounding.  SURVEY.md Appendix A lists the originals.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#else
+#define B2_HD inline
+#endif
+
+namespace b2 {
+
+template <typename T>
+struct Consts;
+template <>
+struct Consts<float> {
+  static constexpr float kLogSqrt2Pi = 0.91893853320467274178f;  // log(sqrt(2*pi))
+  static constexpr float kLogPi = 1.14472988584940017414f;
+  static constexpr float kLog2 = 0.69314718055994530942f;
+  static constexpr float kHalfLog2OverPi = -0.22579135264472743236f;  // 0.5*log(2/pi)
+  static constexpr float kPi = 3.14159265358979323846f;
+};
+template <>
+struct Consts<double> {
+  static constexpr double kLogSqrt2Pi = 0.91893853320467274178;
+  static constexpr double kLogPi = 1.14472988584940017414;
+  static constexpr double kLog2 = 0.69314718055994530942;
+  static constexpr double kHalfLog2OverPi = -0.22579135264472743236;
+  static constexpr double kPi = 3.14159265358979323846;
+};
+
+// ---- thin overload set so templates pick the right libm / CUDA math entry ------------------
+B2_HD float b2_log(float x) { return logf(x); }
+B2_HD double b2_log(double x) { return log(x); }
+B2_HD float b2_exp(float x) { return expf(x); }
+B2_HD double b2_exp(double x) { return exp(x); }
+B2_HD float b2_log1p(float x) { return log1pf(x); }
+B2_HD double b2_log1p(double x) { return log1p(x); }
+B2_HD float b2_sqrt(float x) { return sqrtf(x); }
+B2_HD double b2_sqrt(double x) { return sqrt(x); }
+B2_HD float b2_lgamma(float x) { return lgammaf(x); }
+B2_HD double b2_lgamma(double x) { return lgamma(x); }
+B2_HD float b2_abs(float x) { return fabsf(x); }
+B2_HD double b2_abs(double x) { return fabs(x); }
+B2_HD float b2_floor(float x) { return floorf(x); }
+B2_HD double b2_floor(double x) { return floor(x); }
+B2_HD float b2_tan(float x) { return tanf(x); }
+B2_HD double b2_tan(double x) { return tan(x); }
+B2_HD float b2_max(float a, float b) { return fmaxf(a, b); }
+B2_HD double b2_max(double a, double b) { return fmax(a, b); }
+B2_HD float b2_min(float a, float b) { return fminf(a, b); }
+B2_HD double b2_min(double a, double b) { return fmin(a, b); }
+
+template <typename T>
+B2_HD T b2_inf() {
+  return (T)INFINITY;
+}
+template <typename T>
+B2_HD T b2_nan() {
+  return (T)NAN;
+}
+
+// xlogy(x, y) = x*log(y) with 0 where x == 0 (and NaN propagation from y), as
+// torch.xlogy (used by gamma.py:94-95, dirichlet.py:93, poisson.py:79).
+template <typename T>
+B2_HD T xlogy(T x, T y) {
+  if (y != y) return y;
+  if (x == (T)0) return (T)0;
+  return x * b2_log(y);
+}
+
+// digamma(x).  Positive arguments: upward recurrence to x >= 6 (fp32) / 12 (fp64) followed by the asymptotic
+// expansion  psi(x) ~ ln x - 1/(2x) - sum_k B_2k / (2k x^2k).  Non-positive arguments use the
+// reflection formula; poles return -inf at 0 (torch convention) and NaN at negative integers.
+template <typename T>
+B2_HD T digamma(T x) {
+  if (x != x) return x;
+  T reflect = (T)0;
+  if (x <= (T)0) {
+    if (x == (T)0) return -b2_inf<T>();
+    if (x == b2_floor(x)) return b2_nan<T>();
+    // psi(1-x) - psi(x) = pi / tan(pi x)
+    T frac = x - b2_floor(x);
+    reflect = -Consts<T>::kPi / b2_tan(Consts<T>::kPi * frac);
+    x = (T)1 - x;
+  }
+  T acc = (T)0;
+  const T shift = sizeof(T) == 8 ? (T)12 : (T)6;  // series error ~ x^-16
+  while (x < shift) {
+    acc -= (T)1 / x;
+    x += (T)1;
+  }
+  const T inv = (T)1 / x;
+  const T inv2 = inv * inv;
+  // Bernoulli-number coefficients B_2k/(2k): 1/12, -1/120, 1/252, -1/240, 1/132, -691/32760, 1/12
+  T series = inv2 * ((T)(1.0 / 12.0) -
+             inv2 * ((T)(1.0 / 120.0) -
+             inv2 * ((T)(1.0 / 252.0) -
+             inv2 * ((T)(1.0 / 240.0) -
+             inv2 * ((T)(1.0 / 132.0) -
+             inv2 * ((T)(691.0 / 32760.0) - inv2 * (T)(1.0 / 12.0)))))));
+  return acc + b2_log(x) - (T)0.5 * inv - series + reflect;
+}
+
+// softplus(l) = log(1 + exp(l)) and sigmoid(l), sharing one exp.
+template <typename T>
+B2_HD void softplus_sigmoid(T l, T& sp, T& sg) {
+  const T e = b2_exp(-b2_abs(l));  // in (0, 1]
+  const T inv = (T)1 / ((T)1 + e);
+  sp = b2_max(l, (T)0) + b2_log1p(e);
+  sg = (l >= (T)0) ? inv : e * inv;
+}
+
+// Result of one element: log density and partials w.r.t. value and up to four parameters.
+template <typename T>
+struct ElemOut {
+  T lp, dx, dp[4];
+};
+
+enum : int {
+  kNormal = 0,
+  kBernoulliLogits = 1,
+  kGamma = 2,
+  kBeta = 3,
+  kPoisson = 4,
+  kCauchy = 5,
+  kHalfCauchy = 6,
+  kExponential = 7,
+  kLogNormal = 8,
+  kHalfNormal = 9,
+  kBernoulliProbs = 10,
+  kUniform = 11,
+  kKLNormalNormal = 12,
+  kKLGammaGamma = 13,
+  kNumElementwise = 14
+};
+
+template <int FAM>
+struct FamilyTraits;
+#define B2_TRAITS(F, NP, HASV) \
+  template <>                  \
+  struct FamilyTraits<F> {     \
+    static constexpr int kNumParams = NP; \
+    static constexpr bool kHasValue = HASV; \
+  };
+B2_TRAITS(kNormal, 2, true)
+B2_TRAITS(kBernoulliLogits, 1, true)
+B2_TRAITS(kGamma, 2, true)
+B2_TRAITS(kBeta, 2, true)
+B2_TRAITS(kPoisson, 1, true)
+B2_TRAITS(kCauchy, 2, true)
+B2_TRAITS(kHalfCauchy, 1, true)
+B2_TRAITS(kExponential, 1, true)
+B2_TRAITS(kLogNormal, 2, true)
+B2_TRAITS(kHalfNormal, 1, true)
+B2_TRAITS(kBernoulliProbs, 1, true)
+B2_TRAITS(kUniform, 2, true)
+B2_TRAITS(kKLNormalNormal, 4, false)
+B2_TRAITS(kKLGammaGamma, 4, false)
+#undef B2_TRAITS
+
+// eval<FAM, T, GRAD>(x, p, out): p[k] are the parameters in the order pyro_b200.h documents.
+// With GRAD == false only out.lp is defined.
+template <int FAM, typename T, bool GRAD>
+struct Eval;
+
+// Normal(loc, scale): torch/distributions/normal.py:87-102
+//   -((x - loc)^2) / (2 var) - log(scale) - log(sqrt(2 pi)),  var = scale^2
+template <typename T, bool GRAD>
+struct Eval<kNormal, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T loc = p[0], scale = p[1];
+    const T var = scale * scale;
+    const T d = x - loc;
+    o.lp = -(d * d) / ((T)2 * var) - b2_log(scale) - Consts<T>::kLogSqrt2Pi;
+    if (GRAD) {
+      const T dloc = d / var;
+      o.dx = -dloc;
+      o.dp[0] = dloc;
+      o.dp[1] = (d * d / var - (T)1) / scale;
+    }
+  }
+};
+
+// Bernoulli(logits): torch/distributions/bernoulli.py:121-125 = -BCE_with_logits(l, x)
+//   = x*l - softplus(l)
+template <typename T, bool GRAD>
+struct Eval<kBernoulliLogits, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T l = p[0];
+    T sp, sg;
+    softplus_sigmoid(l, sp, sg);
+    o.lp = x * l - sp;
+    if (GRAD) {
+      o.dx = l;
+      o.dp[0] = x - sg;
+    }
+  }
+};
+
+// Bernoulli(probs): logits = log(p) - log1p(-p) with p clamped to [eps, 1-eps]
+// (torch/distributions/utils.py probs_to_logits + clamp_probs), then as above.
+template <typename T>
+B2_HD T b2_eps();
+template <>
+B2_HD float b2_eps<float>() { return 1.1920928955078125e-07f; }
+template <>
+B2_HD double b2_eps<double>() { return 2.220446049250313e-16; }
+
+template <typename T, bool GRAD>
+struct Eval<kBernoulliProbs, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T eps = b2_eps<T>();
+    const T pr = p[0];
+    const bool clamped = (pr < eps) || (pr > (T)1 - eps);
+    const T pc = b2_min(b2_max(pr, eps), (T)1 - eps);
+    const T l = b2_log(pc) - b2_log1p(-pc);
+    T sp, sg;
+    softplus_sigmoid(l, sp, sg);
+    o.lp = x * l - sp;
+    if (GRAD) {
+      o.dx = l;
+      // d l / d p = 1/(p (1-p)); zero gradient where the clamp is active
+      o.dp[0] = clamped ? (T)0 : (x - sg) / (pc * ((T)1 - pc));
+    }
+  }
+};
+
+// Gamma(concentration a, rate b): torch/distributions/gamma.py:89-98
+//   xlogy(a, b) + xlogy(a - 1, x) - b*x - lgamma(a)
+template <typename T, bool GRAD>
+struct Eval<kGamma, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T a = p[0], b = p[1];
+    o.lp = xlogy(a, b) + xlogy(a - (T)1, x) - b * x - b2_lgamma(a);
+    if (GRAD) {
+      o.dx = (a - (T)1) / x - b;
+      o.dp[0] = b2_log(b) + b2_log(x) - digamma(a);
+      o.dp[1] = a / b - x;
+    }
+  }
+};
+
+// Beta(c1, c0): torch/distributions/beta.py:87-91 -> Dirichlet([c1, c0]).log_prob([x, 1-x])
+// dirichlet.py:90-97:  xlogy(c1-1, x) + xlogy(c0-1, 1-x) + lgamma(c1+c0) - lgamma(c1) - lgamma(c0)
+template <typename T, bool GRAD>
+struct Eval<kBeta, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T c1 = p[0], c0 = p[1];
+    const T omx = (T)1 - x;
+    o.lp = (xlogy(c1 - (T)1, x) + xlogy(c0 - (T)1, omx)) + b2_lgamma(c1 + c0) -
+           (b2_lgamma(c1) + b2_lgamma(c0));
+    if (GRAD) {
+      const T psum = digamma(c1 + c0);
+      o.dx = (c1 - (T)1) / x - (c0 - (T)1) / omx;
+      o.dp[0] = b2_log(x) + psum - digamma(c1);
+      o.dp[1] = b2_log(omx) + psum - digamma(c0);
+    }
+  }
+};
+
+// Poisson(rate): torch/distributions/poisson.py:75-79   xlogy(x, rate) - rate - lgamma(x + 1)
+template <typename T, bool GRAD>
+struct Eval<kPoisson, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T rate = p[0];
+    o.lp = xlogy(x, rate) - rate - b2_lgamma(x + (T)1);
+    if (GRAD) {
+      o.dx = b2_log(rate) - digamma(x + (T)1);
+      o.dp[0] = x / rate - (T)1;
+    }
+  }
+};
+
+// Cauchy(loc, scale): torch/distributions/cauchy.py:81-88
+//   -log(pi) - log(scale) - log1p(((x - loc)/scale)^2)
+template <typename T, bool GRAD>
+struct Eval<kCauchy, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T loc = p[0], scale = p[1];
+    const T u = (x - loc) / scale;
+    const T u2 = u * u;
+    o.lp = -Consts<T>::kLogPi - b2_log(scale) - b2_log1p(u2);
+    if (GRAD) {
+      const T w = (T)2 * u / (((T)1 + u2) * scale);  // d log1p(u^2) / d x
+      o.dx = -w;
+      o.dp[0] = w;
+      o.dp[1] = (-(T)1 + (T)2 * u2 / ((T)1 + u2)) / scale;
+    }
+  }
+};
+
+// HalfCauchy(scale): torch/distributions/half_cauchy.py:73-81
+//   Cauchy(0, scale).log_prob(x) + log 2, -inf where x < 0
+template <typename T, bool GRAD>
+struct Eval<kHalfCauchy, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T scale = p[0];
+    const T u = x / scale;
+    const T u2 = u * u;
+    T lp = (-Consts<T>::kLogPi - b2_log(scale) - b2_log1p(u2)) + Consts<T>::kLog2;
+    const bool out = x < (T)0;
+    o.lp = out ? -b2_inf<T>() : lp;
+    if (GRAD) {
+      const T w = (T)2 * u / (((T)1 + u2) * scale);
+      o.dx = out ? (T)0 : -w;
+      o.dp[0] = out ? (T)0 : (-(T)1 + (T)2 * u2 / ((T)1 + u2)) / scale;
+    }
+  }
+};
+
+// Exponential(rate): rate.log() - rate * x
+template <typename T, bool GRAD>
+struct Eval<kExponential, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T rate = p[0];
+    o.lp = b2_log(rate) - rate * x;
+    if (GRAD) {
+      o.dx = -rate;
+      o.dp[0] = (T)1 / rate - x;
+    }
+  }
+};
+
+// LogNormal(loc, scale) = TransformedDistribution(Normal, ExpTransform):
+//   Normal.log_prob(log x) - log x
+template <typename T, bool GRAD>
+struct Eval<kLogNormal, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T loc = p[0], scale = p[1];
+    const T lx = b2_log(x);
+    const T var = scale * scale;
+    const T d = lx - loc;
+    o.lp = (-(d * d) / ((T)2 * var) - b2_log(scale) - Consts<T>::kLogSqrt2Pi) - lx;
+    if (GRAD) {
+      const T dloc = d / var;
+      o.dx = (-dloc - (T)1) / x;
+      o.dp[0] = dloc;
+      o.dp[1] = (d * d / var - (T)1) / scale;
+    }
+  }
+};
+
+// HalfNormal(scale): Normal(0, scale).log_prob(x) + log 2, -inf where x < 0
+template <typename T, bool GRAD>
+struct Eval<kHalfNormal, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T scale = p[0];
+    const T var = scale * scale;
+    const T lp = (-(x * x) / ((T)2 * var) - b2_log(scale) - Consts<T>::kLogSqrt2Pi) +
+                 Consts<T>::kLog2;
+    const bool out = x < (T)0;
+    o.lp = out ? -b2_inf<T>() : lp;
+    if (GRAD) {
+      o.dx = out ? (T)0 : -x / var;
+      o.dp[0] = out ? (T)0 : (x * x / var - (T)1) / scale;
+    }
+  }
+};
+
+// Uniform(low, high): torch/distributions/uniform.py  log(lb*ub) - log(high - low)
+template <typename T, bool GRAD>
+struct Eval<kUniform, T, GRAD> {
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    const T low = p[0], high = p[1];
+    const bool in = (low <= x) && (x < high);
+    const T w = high - low;
+    o.lp = in ? -b2_log(w) : -b2_inf<T>();
+    if (GRAD) {
+      o.dx = (T)0;
+      o.dp[0] = in ? (T)1 / w : (T)0;
+      o.dp[1] = in ? -(T)1 / w : (T)0;
+    }
+  }
+};
+
+// KL(Normal p || Normal q): torch/distributions/kl.py:468-471
+//   var_ratio = (sp/sq)^2 ; t1 = ((mp - mq)/sq)^2 ; 0.5*(var_ratio + t1 - 1 - log var_ratio)
+// "lp" carries the KL value; params = (loc_p, scale_p, loc_q, scale_q).
+template <typename T, bool GRAD>
+struct Eval<kKLNormalNormal, T, GRAD> {
+  static B2_HD void run(T, const T* p, ElemOut<T>& o) {
+    const T mp = p[0], sp = p[1], mq = p[2], sq = p[3];
+    const T ratio = sp / sq;
+    const T var_ratio = ratio * ratio;
+    const T dm = (mp - mq) / sq;
+    const T t1 = dm * dm;
+    o.lp = (T)0.5 * (var_ratio + t1 - (T)1 - b2_log(var_ratio));
+    if (GRAD) {
+      o.dx = (T)0;
+      o.dp[0] = dm / sq;
+      o.dp[1] = sp / (sq * sq) - (T)1 / sp;
+      o.dp[2] = -dm / sq;
+      o.dp[3] = (-var_ratio - t1 + (T)1) / sq;
+    }
+  }
+};
+
+// KL(Gamma p || Gamma q): torch/distributions/kl.py:301-306
+//   t1 = aq*log(bp/bq); t2 = lgamma(aq) - lgamma(ap); t3 = (ap-aq)*digamma(ap); t4 = (bq-bp)*ap/bp
+// params = (conc_p, rate_p, conc_q, rate_q).  d/d ap needs trigamma.
+template <typename T>
+B2_HD T trigamma(T x) {
+  // positive arguments only (concentrations); recurrence to x >= 6 then asymptotic series
+  T acc = (T)0;
+  const T shift = sizeof(T) == 8 ? (T)16 : (T)6;
+  while (x < shift) {
+    acc += (T)1 / (x * x);
+    x += (T)1;
+  }
+  const T inv = (T)1 / x;
+  const T inv2 = inv * inv;
+  // 1/x + 1/(2x^2) + sum B_2k / x^(2k+1): 1/6, -1/30, 1/42, -1/30, 5/66
+  return acc + inv + (T)0.5 * inv2 +
+         inv * inv2 * ((T)(1.0 / 6.0) -
+         inv2 * ((T)(1.0 / 30.0) -
+         inv2 * ((T)(1.0 / 42.0) - inv2 * ((T)(1.0 / 30.0) - inv2 * (T)(5.0 / 66.0)))));
+}
+
+template <typename T, bool GRAD>
+struct Eval<kKLGammaGamma, T, GRAD> {
+  static B2_HD void run(T, const T* p, ElemOut<T>& o) {
+    const T ap = p[0], bp = p[1], aq = p[2], bq = p[3];
+    const T t1 = aq * b2_log(bp / bq);
+    const T t2 = b2_lgamma(aq) - b2_lgamma(ap);
+    const T psi = digamma(ap);
+    const T t3 = (ap - aq) * psi;
+    const T t4 = (bq - bp) * (ap / bp);
+    o.lp = t1 + t2 + t3 + t4;
+    if (GRAD) {
+      o.dx = (T)0;
+      o.dp[0] = (ap - aq) * trigamma(ap) + (bq - bp) / bp;  // -psi + psi cancel
+      o.dp[1] = aq / bp - ap * bq / (bp * bp);
+      o.dp[2] = b2_log(bp / bq) + digamma(aq) - psi;
+      o.dp[3] = -aq / bq + ap / bp;
+    }
+  }
+};
+
+}  // namespace b2

@@ -1,0 +1,497 @@
+// event_score.cu -- fused log_prob + score for families with an event dimension:
+// Dirichlet, Categorical(logits), MultivariateNormal(scale_tril); and b2_reduce_to.
+//
+// One sub-warp group of G lanes (G = power of two <= 32, >= event size when that is < 32) owns
+// one batch row; event dims are contiguous so the lanes of a group read consecutive addresses.
+// Gradients are always written full shape [batch, event...]; batch-broadcast operands are summed
+// afterwards by b2_reduce_to (deterministic two-stage tree, no float atomics).
+#include <string.h>
+
+#include "b2_common.cuh"
+#include "b2_math.cuh"
+
+namespace b2 {
+
+struct EvOpnd {
+  const void* ptr;
+  int64_t st[kMaxD];  // batch strides (elements)
+};
+struct EvOut {
+  void* ptr;
+  int64_t st[kMaxD];
+};
+struct EventArgs {
+  int ndim;  // batch dims after coalescing
+  int64_t shape[kMaxD];
+  int64_t nbatch;
+  int K;  // event size
+  EvOpnd x, p0, p1, mask, up;
+  EvOut lp, gx, gp0, gp1;
+  double scale, weight, sum_coeff;
+  int flags;
+  void* out_sum;
+  double* partials;
+  unsigned int* ticket;
+  int g_log2;  // lanes per row = 1 << g_log2
+};
+
+template <typename T>
+__device__ __forceinline__ T group_sum(T v, int G) {
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T group_max(T v, int G) {
+  for (int o = G >> 1; o > 0; o >>= 1) v = b2_max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ void batch_offsets(const EventArgs& a, int64_t row, int64_t& ox,
+                                              int64_t& op0, int64_t& op1, int64_t& om, int64_t& ou,
+                                              int64_t& olp, int64_t& ogx, int64_t& ogp0,
+                                              int64_t& ogp1) {
+  ox = op0 = op1 = om = ou = olp = ogx = ogp0 = ogp1 = 0;
+  int64_t rem = row;
+  for (int d = a.ndim - 1; d >= 0; --d) {
+    const int64_t q = rem / a.shape[d];
+    const int64_t idx = rem - q * a.shape[d];
+    rem = q;
+    ox += idx * a.x.st[d];
+    op0 += idx * a.p0.st[d];
+    op1 += idx * a.p1.st[d];
+    om += idx * a.mask.st[d];
+    ou += idx * a.up.st[d];
+    olp += idx * a.lp.st[d];
+    ogx += idx * a.gx.st[d];
+    ogp0 += idx * a.gp0.st[d];
+    ogp1 += idx * a.gp1.st[d];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void finish_sum(const EventArgs& a, double tot) {
+  if (a.out_sum) {
+    T* o = reinterpret_cast<T*>(a.out_sum);
+    const double s = a.sum_coeff * tot;
+    *o = (a.flags & B2_FLAG_ACCUMULATE_SUM) ? (T)((double)*o + s) : (T)s;
+  }
+}
+
+// ---- Dirichlet: torch/distributions/dirichlet.py:90-97 -----------------------------------------
+//   sum_k xlogy(a_k - 1, x_k) + lgamma(sum a) - sum_k lgamma(a_k)
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(256) dirichlet_kernel(const EventArgs a) {
+  const int G = 1 << a.g_log2;
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> a.g_log2;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) >> a.g_log2;
+  const T* xp = reinterpret_cast<const T*>(a.x.ptr);
+  const T* cp = reinterpret_cast<const T*>(a.p0.ptr);
+  const int64_t nrows_pad = ((a.nbatch + ngroups - 1) / ngroups) * ngroups;
+  T acc = (T)0;
+  for (int64_t row = gid; row < nrows_pad; row += ngroups) {
+    const bool live = row < a.nbatch;  // keep the whole warp converged for the shuffles
+    int64_t ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1;
+    batch_offsets(a, live ? row : 0, ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1);
+    T s_xlogy = 0, s_conc = 0, s_lg = 0;
+    for (int k = lane; k < a.K; k += G) {
+      const T c = cp[op0 + k], x = xp[ox + k];
+      s_xlogy += xlogy(c - (T)1, x);
+      s_conc += c;
+      s_lg += b2_lgamma(c);
+    }
+    s_xlogy = group_sum(s_xlogy, G);
+    s_conc = group_sum(s_conc, G);
+    s_lg = group_sum(s_lg, G);
+    const T lp = s_xlogy + b2_lgamma(s_conc) - s_lg;
+    const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
+    const T slp = (m && live) ? lp * (T)a.scale : (T)0;
+    if (lane == 0 && live) {
+      acc += slp;
+      if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[olp] = slp;
+    }
+    if (GRAD && live) {
+      T f = m ? (T)(a.weight * a.scale) : (T)0;
+      if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[ou];
+      const T psum = digamma(s_conc);
+      for (int k = lane; k < a.K; k += G) {
+        const T c = cp[op0 + k], x = xp[ox + k];
+        if (a.gx.ptr) reinterpret_cast<T*>(a.gx.ptr)[ogx + k] = m ? f * (c - (T)1) / x : (T)0;
+        if (a.gp0.ptr)
+          reinterpret_cast<T*>(a.gp0.ptr)[ogp0 + k] = m ? f * (b2_log(x) + psum - digamma(c)) : (T)0;
+      }
+    }
+  }
+  __shared__ double smem[32];
+  double red[1] = {(double)acc};
+  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
+}
+
+// ---- Categorical(logits): torch/distributions/categorical.py:78 (logits - logsumexp) and
+// :151-157 (gather).  value is int64; the gathered index is exact. -------------------------------
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(256) categorical_kernel(const EventArgs a) {
+  const int G = 1 << a.g_log2;
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> a.g_log2;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) >> a.g_log2;
+  const int64_t* vp = reinterpret_cast<const int64_t*>(a.x.ptr);
+  const T* lg = reinterpret_cast<const T*>(a.p0.ptr);
+  const int64_t nrows_pad = ((a.nbatch + ngroups - 1) / ngroups) * ngroups;
+  T acc = (T)0;
+  for (int64_t row = gid; row < nrows_pad; row += ngroups) {
+    const bool live = row < a.nbatch;
+    int64_t ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1;
+    batch_offsets(a, live ? row : 0, ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1);
+    T mx = -b2_inf<T>();
+    for (int k = lane; k < a.K; k += G) mx = b2_max(mx, lg[op0 + k]);
+    mx = group_max(mx, G);
+    T se = 0;
+    for (int k = lane; k < a.K; k += G) se += b2_exp(lg[op0 + k] - mx);
+    se = group_sum(se, G);
+    const T lse = mx + b2_log(se);
+    const int64_t v = vp[ox];
+    const bool inb = v >= 0 && v < a.K;
+    const T lp = inb ? lg[op0 + v] - lse : b2_nan<T>();
+    const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
+    const T slp = (m && live) ? lp * (T)a.scale : (T)0;
+    if (lane == 0 && live) {
+      acc += slp;
+      if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[olp] = slp;
+    }
+    if (GRAD && live && a.gp0.ptr) {
+      T f = m ? (T)(a.weight * a.scale) : (T)0;
+      if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[ou];
+      for (int k = lane; k < a.K; k += G) {
+        const T sm = b2_exp(lg[op0 + k] - lse);
+        reinterpret_cast<T*>(a.gp0.ptr)[ogp0 + k] = m ? f * (((int64_t)k == v ? (T)1 : (T)0) - sm) : (T)0;
+      }
+    }
+  }
+  __shared__ double smem[32];
+  double red[1] = {(double)acc};
+  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
+}
+
+// ---- MultivariateNormal(loc, scale_tril): torch/distributions/multivariate_normal.py:256-264,
+// _batch_mahalanobis :29-80.   -0.5*(n log 2pi + |L^-1 (x-mu)|^2) - sum log diag L.
+// One full warp per row; forward substitution with a warp reduction per pivot.  n <= 128
+// (residual z kept in 4 registers per lane).  Larger n belongs on the tensor-core path. ----------
+constexpr int kMvnMaxN = 128;
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(256) mvn_tril_kernel(const EventArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int n = a.K;
+  const T* xp = reinterpret_cast<const T*>(a.x.ptr);
+  const T* mu = reinterpret_cast<const T*>(a.p0.ptr);
+  const T* Lp = reinterpret_cast<const T*>(a.p1.ptr);
+  const int64_t nrows_pad = ((a.nbatch + nwarps - 1) / nwarps) * nwarps;
+  T acc = (T)0;
+  for (int64_t row = wid; row < nrows_pad; row += nwarps) {
+    const bool live = row < a.nbatch;
+    int64_t ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1;
+    batch_offsets(a, live ? row : 0, ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1);
+    const T* L = Lp + op1;
+    // z = L^-1 (x - mu), element j lives in lane j%32, slot j/32
+    T z[4] = {0, 0, 0, 0};
+    T logdet = 0;
+    for (int i = 0; i < n; ++i) {
+      T part = 0;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int j = s * 32 + lane;
+        if (j < i) part += L[(int64_t)i * n + j] * z[s];
+      }
+      part = warp_sum(part);
+      const T lii = L[(int64_t)i * n + i];
+      const T zi = ((xp[ox + i] - mu[op0 + i]) - part) / lii;
+      logdet += b2_log(lii);
+      if ((i & 31) == lane) z[i >> 5] = zi;
+    }
+    T m2 = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) m2 += z[s] * z[s];
+    m2 = warp_sum(m2);
+    const T lp = (T)-0.5 * ((T)n * ((T)2 * Consts<T>::kLogSqrt2Pi) + m2) - logdet;
+    const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
+    const T slp = (m && live) ? lp * (T)a.scale : (T)0;
+    if (lane == 0 && live) {
+      acc += slp;
+      if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[olp] = slp;
+    }
+    if (GRAD) {
+      T f = m ? (T)(a.weight * a.scale) : (T)0;
+      if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[ou];
+      // w = L^-T z  (back substitution):  w_i = (z_i - sum_{j>i} L_ji w_j) / L_ii
+      T w[4] = {0, 0, 0, 0};
+      for (int i = n - 1; i >= 0; --i) {
+        T part = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const int j = s * 32 + lane;
+          if (j > i && j < n) part += L[(int64_t)j * n + i] * w[s];
+        }
+        part = warp_sum(part);
+        const T zi = __shfl_sync(0xffffffffu, z[i >> 5], i & 31);
+        const T wi = (zi - part) / L[(int64_t)i * n + i];
+        if ((i & 31) == lane) w[i >> 5] = wi;
+      }
+      if (live) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const int j = s * 32 + lane;
+          if (j < n) {
+            if (a.gx.ptr) reinterpret_cast<T*>(a.gx.ptr)[ogx + j] = m ? -f * w[s] : (T)0;
+            if (a.gp0.ptr) reinterpret_cast<T*>(a.gp0.ptr)[ogp0 + j] = m ? f * w[s] : (T)0;
+          }
+        }
+      }
+      if (a.gp1.ptr) {
+        // dL = f * (tril(w z^T) - diag(1/L_ii)); strictly upper part is zero
+        T* gL = reinterpret_cast<T*>(a.gp1.ptr) + ogp1;
+        for (int i = 0; i < n; ++i) {
+          const T wi = __shfl_sync(0xffffffffu, w[i >> 5], i & 31);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const int j = s * 32 + lane;
+            if (j < n && live) {
+              T g = (T)0;
+              if (j < i) g = wi * z[s];
+              else if (j == i) g = wi * z[s] - (T)1 / L[(int64_t)i * n + i];
+              gL[(int64_t)i * n + j] = m ? f * g : (T)0;
+            }
+          }
+        }
+      }
+    }
+  }
+  __shared__ double smem[32];
+  double red[1] = {(double)acc};
+  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
+}
+
+// ---- generic strided sum-to ---------------------------------------------------------------------
+struct ReduceArgs {
+  int nk, nr;                     // kept / reduced dims
+  int64_t kshape[kMaxD], rshape[kMaxD];
+  int64_t ksrc[kMaxD], kdst[kMaxD], rsrc[kMaxD];
+  int64_t nout, nred;
+  int splits;
+  const void* src;
+  void* dst;
+  double* partials;  // [nout, splits] when splits > 1
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_to_kernel(const ReduceArgs a) {
+  const int64_t o = blockIdx.x;
+  const int s = blockIdx.y;
+  int64_t rem = o, so = 0, dof = 0;
+  for (int d = a.nk - 1; d >= 0; --d) {
+    const int64_t q = rem / a.kshape[d];
+    const int64_t idx = rem - q * a.kshape[d];
+    rem = q;
+    so += idx * a.ksrc[d];
+    dof += idx * a.kdst[d];
+  }
+  const int64_t per = (a.nred + a.splits - 1) / a.splits;
+  const int64_t lo = (int64_t)s * per;
+  int64_t hi = lo + per;
+  if (hi > a.nred) hi = a.nred;
+  const T* src = reinterpret_cast<const T*>(a.src) + so;
+  double acc = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    int64_t r = i, off = 0;
+    for (int d = a.nr - 1; d >= 0; --d) {
+      const int64_t q = r / a.rshape[d];
+      off += (r - q * a.rshape[d]) * a.rsrc[d];
+      r = q;
+    }
+    acc += (double)src[off];
+  }
+  __shared__ double smem[32];
+  double red[1] = {acc};
+  block_sum<1>(red, smem);
+  if (threadIdx.x == 0) {
+    if (a.splits == 1) reinterpret_cast<T*>(a.dst)[dof] = (T)red[0];
+    else a.partials[o * a.splits + s] = red[0];
+  }
+}
+
+template <typename T>
+__global__ void reduce_to_finish_kernel(const ReduceArgs a) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= a.nout) return;
+  int64_t rem = o, dof = 0;
+  for (int d = a.nk - 1; d >= 0; --d) {
+    const int64_t q = rem / a.kshape[d];
+    dof += (rem - q * a.kshape[d]) * a.kdst[d];
+    rem = q;
+  }
+  double s = 0.0;
+  for (int i = 0; i < a.splits; ++i) s += a.partials[o * a.splits + i];
+  reinterpret_cast<T*>(a.dst)[dof] = (T)s;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tensor* params,
+                              int n_params, int event_size, const b2_tensor* mask, double scale,
+                              const b2_tensor* upstream, double weight, double sum_coeff,
+                              int flags, b2_tensor* out_logprob, void* out_sum,
+                              b2_tensor* out_dvalue, b2_tensor* out_dparams, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  if (!value || !params) return B2_ERR_NULL;
+  if (!workspace || workspace_bytes < kReduceWorkspaceBytes) return B2_ERR_WORKSPACE;
+  const int want_params = (family == B2_MVN_TRIL) ? 2 : 1;
+  if (family != B2_DIRICHLET && family != B2_CATEGORICAL && family != B2_MVN_TRIL)
+    return B2_ERR_BAD_FAMILY;
+  if (n_params != want_params) return B2_ERR_BAD_SHAPE;
+  const int dtype = params[0].dtype;
+  if (dtype != B2_F32 && dtype != B2_F64) return B2_ERR_BAD_DTYPE;
+  if (family == B2_CATEGORICAL) {
+    if (value->dtype != B2_I64) return B2_ERR_BAD_DTYPE;
+  } else if (value->dtype != dtype) {
+    return B2_ERR_BAD_DTYPE;
+  }
+  if (event_size < 1) return B2_ERR_BAD_SHAPE;
+  if (family == B2_MVN_TRIL && event_size > kMvnMaxN) return B2_ERR_TOO_LARGE;
+  // `value->shape[:ndim]` is the batch shape shared by every operand; strides are batch strides.
+  const int nd = value->ndim;
+  if (nd < 0 || nd > B2_MAX_DIMS) return B2_ERR_BAD_SHAPE;
+
+  EventArgs a;
+  memset(&a, 0, sizeof(a));
+  a.K = event_size;
+  a.scale = scale;
+  a.weight = weight;
+  a.sum_coeff = sum_coeff;
+  a.flags = flags;
+  a.out_sum = out_sum;
+  a.partials = ws_partials(workspace);
+  a.ticket = ws_ticket(workspace);
+  // drop size-1 batch dims (no merging: rows are decoded by division anyway)
+  int cd = 0;
+  int64_t nb = 1;
+  int keep[B2_MAX_DIMS];
+  for (int d = 0; d < nd; ++d) {
+    nb *= value->shape[d];
+    if (value->shape[d] != 1) keep[cd++] = d;
+  }
+  if (cd > kMaxD) return B2_ERR_BAD_SHAPE;
+  a.ndim = cd;
+  a.nbatch = nb;
+  for (int i = 0; i < cd; ++i) a.shape[i] = value->shape[keep[i]];
+  auto fin = [&](EvOpnd& o, const b2_tensor* t) {
+    if (!t || !t->ptr) return;
+    o.ptr = t->ptr;
+    for (int i = 0; i < cd; ++i) o.st[i] = t->stride[keep[i]];
+  };
+  auto fout = [&](EvOut& o, const b2_tensor* t) {
+    if (!t || !t->ptr) return;
+    o.ptr = t->ptr;
+    for (int i = 0; i < cd; ++i) o.st[i] = t->stride[keep[i]];
+  };
+  fin(a.x, value);
+  fin(a.p0, &params[0]);
+  if (n_params > 1) fin(a.p1, &params[1]);
+  fin(a.mask, mask);
+  fin(a.up, upstream);
+  fout(a.lp, out_logprob);
+  fout(a.gx, out_dvalue);
+  if (out_dparams) {
+    fout(a.gp0, &out_dparams[0]);
+    if (n_params > 1) fout(a.gp1, &out_dparams[1]);
+  }
+  if (mask && mask->ptr && mask->dtype != B2_U8) return B2_ERR_BAD_DTYPE;
+  const bool grad = a.gx.ptr || a.gp0.ptr || a.gp1.ptr;
+  int lg = 0;
+  while (lg < 5 && (1 << lg) < event_size) ++lg;
+  if (family == B2_MVN_TRIL) lg = 5;
+  a.g_log2 = lg;
+  const int64_t rows_per_block = 256 >> lg;
+  int64_t blocks = (nb + rows_per_block - 1) / rows_per_block;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+#define B2_EV_LAUNCH(KERNEL)                                                        \
+  if (dtype == B2_F32) {                                                            \
+    if (grad) KERNEL<float, true><<<(unsigned)blocks, 256, 0, s>>>(a);              \
+    else KERNEL<float, false><<<(unsigned)blocks, 256, 0, s>>>(a);                  \
+  } else {                                                                          \
+    if (grad) KERNEL<double, true><<<(unsigned)blocks, 256, 0, s>>>(a);             \
+    else KERNEL<double, false><<<(unsigned)blocks, 256, 0, s>>>(a);                 \
+  }
+  if (family == B2_DIRICHLET) { B2_EV_LAUNCH(dirichlet_kernel) }
+  else if (family == B2_CATEGORICAL) { B2_EV_LAUNCH(categorical_kernel) }
+  else { B2_EV_LAUNCH(mvn_tril_kernel) }
+#undef B2_EV_LAUNCH
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int b2_reduce_to(const b2_tensor* src, b2_tensor* dst, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (!src || !dst || !src->ptr || !dst->ptr) return B2_ERR_NULL;
+  if (src->ndim != dst->ndim || src->dtype != dst->dtype) return B2_ERR_BAD_SHAPE;
+  if (src->dtype != B2_F32 && src->dtype != B2_F64) return B2_ERR_BAD_DTYPE;
+  ReduceArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nout = 1;
+  a.nred = 1;
+  for (int d = 0; d < src->ndim; ++d) {
+    const int64_t sz = src->shape[d];
+    if (sz == 1) continue;
+    if (dst->stride[d] == 0) {
+      if (a.nr >= kMaxD) return B2_ERR_BAD_SHAPE;
+      a.rshape[a.nr] = sz;
+      a.rsrc[a.nr] = src->stride[d];
+      ++a.nr;
+      a.nred *= sz;
+    } else {
+      if (a.nk >= kMaxD) return B2_ERR_BAD_SHAPE;
+      a.kshape[a.nk] = sz;
+      a.ksrc[a.nk] = src->stride[d];
+      a.kdst[a.nk] = dst->stride[d];
+      ++a.nk;
+      a.nout *= sz;
+    }
+  }
+  if (a.nout > 0x7fffffffLL) return B2_ERR_TOO_LARGE;
+  a.src = src->ptr;
+  a.dst = dst->ptr;
+  // split the reduced range so that small-output / large-reduction cases still fill the GPU
+  int64_t splits = 1;
+  const int64_t target_blocks = (int64_t)kNumSMs * 4;
+  if (a.nout < target_blocks && a.nred > 4096) {
+    splits = target_blocks / (a.nout > 0 ? a.nout : 1);
+    const int64_t max_by_work = a.nred / 2048;
+    if (splits > max_by_work) splits = max_by_work;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+  }
+  if (splits > 1) {
+    const size_t need = sizeof(double) * (size_t)a.nout * (size_t)splits;
+    if (!workspace || workspace_bytes < 256 + need) splits = 1;
+  }
+  a.splits = (int)splits;
+  a.partials = workspace ? ws_partials(workspace) : nullptr;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a.nout == 0) return B2_OK;
+  dim3 grid((unsigned)a.nout, (unsigned)splits, 1);
+  if (src->dtype == B2_F32) reduce_to_kernel<float><<<grid, 256, 0, s>>>(a);
+  else reduce_to_kernel<double><<<grid, 256, 0, s>>>(a);
+  count_launch();
+  if (splits > 1) {
+    const unsigned fb = (unsigned)((a.nout + 255) / 256);
+    if (src->dtype == B2_F32) reduce_to_finish_kernel<float><<<fb, 256, 0, s>>>(a);
+    else reduce_to_finish_kernel<double><<<fb, 256, 0, s>>>(a);
+    count_launch();
+  }
+  return check_launch();
+}

@@ -1,0 +1,458 @@
+// mcmc.cu -- HMC/NUTS kernels.
+//   * leapfrog halves over [C, D] chain-major state (pyro/ops/integrator.py:45-65)
+//   * native potentials U, dU/dz for C chains in one launch (pyro/infer/mcmc/util.py:275-286)
+//   * nuts_small_kernel: whole NUTS transitions, one thread per chain, for small latent dims
+#include <string.h>
+
+#include "b2_common.cuh"
+#include "nuts_core.cuh"
+
+namespace b2 {
+
+// ---- leapfrog halves ------------------------------------------------------------------------------
+// kick_drift:  r <- r - (eps/2) g ;  z <- z + eps * minv * r        (integrator.py:52-59)
+template <typename T>
+__global__ void __launch_bounds__(256) kick_drift_kernel(T* __restrict__ z, T* __restrict__ r,
+                                                         const T* __restrict__ g,
+                                                         const T* __restrict__ eps,
+                                                         const T* __restrict__ minv,
+                                                         int64_t minv_cs,
+                                                         const uint8_t* __restrict__ active,
+                                                         int64_t C, int64_t D) {
+  for (int64_t c = blockIdx.y; c < C; c += gridDim.y) {
+    if (active && !active[c]) continue;
+    const T e = eps[c];
+    const T* mi = minv + c * minv_cs;
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D;
+         d += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i = c * D + d;
+      const T rn = r[i] + (T)0.5 * e * (-g[i]);
+      r[i] = rn;
+      z[i] = z[i] + e * (mi[d] * rn);
+    }
+  }
+}
+
+// kick:  r <- r - (eps/2) g ;  ke[c] = 0.5 * sum_d minv * r * r     (integrator.py:62-63, hmc.py:152-156)
+// grid = (bx, C): partial sums go to partials[c * bx + blockIdx.x]; finished by ke_finish_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) kick_kernel(T* __restrict__ r, const T* __restrict__ g,
+                                                   const T* __restrict__ eps,
+                                                   const T* __restrict__ minv, int64_t minv_cs,
+                                                   const uint8_t* __restrict__ active,
+                                                   double* __restrict__ partials, int64_t C,
+                                                   int64_t D) {
+  __shared__ double smem[32];
+  for (int64_t c = blockIdx.y; c < C; c += gridDim.y) {
+    double acc = 0.0;
+    if (!(active && !active[c])) {
+      const T e = eps[c];
+      const T* mi = minv + c * minv_cs;
+      for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D;
+           d += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = c * D + d;
+        const T rn = r[i] + (T)0.5 * e * (-g[i]);
+        r[i] = rn;
+        acc += (double)(mi[d] * rn * rn);
+      }
+    }
+    double red[1] = {acc};
+    block_sum<1>(red, smem);
+    if (threadIdx.x == 0 && partials) partials[c * gridDim.x + blockIdx.x] = red[0];
+  }
+}
+
+template <typename T>
+__global__ void ke_finish_kernel(const double* __restrict__ partials, int nb,
+                                 const uint8_t* __restrict__ active, T* __restrict__ ke,
+                                 int64_t C) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (active && !active[c]) return;
+  double s = 0.0;
+  for (int i = 0; i < nb; ++i) s += partials[c * nb + i];
+  ke[c] = (T)(0.5 * s);
+}
+
+// ---- native potentials over [C, D] ------------------------------------------------------------------
+// HierNormal: grid = (bx, C). Each CTA strides over j, writes grad_eta elementwise, and reduces
+// (U_part, sum_res, sum_res_eta); a finish kernel assembles U, dU/dmu, dU/dt per chain.
+template <typename T>
+__global__ void __launch_bounds__(256) hier_normal_kernel(const T* __restrict__ z,
+                                                          const T* __restrict__ y,
+                                                          const T* __restrict__ sigma,
+                                                          T* __restrict__ grad,
+                                                          const uint8_t* __restrict__ active,
+                                                          double* __restrict__ partials,
+                                                          int64_t C, int64_t J) {
+  __shared__ double smem[3 * 32];
+  const int64_t D = J + 2;
+  for (int64_t c = blockIdx.y; c < C; c += gridDim.y) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (!(active && !active[c])) {
+      const T* zc = z + c * D;
+      const T mu = zc[0];
+      const T tau = b2_exp(zc[1]);
+      for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < J;
+           j += (int64_t)gridDim.x * blockDim.x) {
+        const T eta = zc[2 + j];
+        const T sg = __ldg(sigma + j);
+        const T d = __ldg(y + j) - mu - tau * eta;
+        const T res = d / (sg * sg);
+        grad[c * D + 2 + j] = eta - tau * res;
+        acc[0] += (double)((T)0.5 * eta * eta + (T)0.5 * d * res + b2_log(sg));
+        acc[1] += (double)res;
+        acc[2] += (double)(res * eta);
+      }
+    }
+    block_sum<3>(acc, smem);
+    if (threadIdx.x == 0) {
+      double* p = partials + (c * gridDim.x + blockIdx.x) * 3;
+      p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2];
+    }
+  }
+}
+
+template <typename T>
+__global__ void hier_normal_finish_kernel(const T* __restrict__ z,
+                                          const double* __restrict__ partials, int nb,
+                                          const uint8_t* __restrict__ active, T* __restrict__ U,
+                                          T* __restrict__ grad, int64_t C, int64_t J, double s_mu,
+                                          double s_tau) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (active && !active[c]) return;
+  const int64_t D = J + 2;
+  double a0 = 0, a1 = 0, a2 = 0;
+  for (int i = 0; i < nb; ++i) {
+    const double* p = partials + (c * nb + i) * 3;
+    a0 += p[0]; a1 += p[1]; a2 += p[2];
+  }
+  const double mu = (double)z[c * D], t = (double)z[c * D + 1];
+  const double tau = exp(t);
+  const double u = tau / s_tau, u2 = u * u;
+  const double c0 = 0.91893853320467274178;  // log sqrt(2 pi)
+  double Uv = 0.5 * mu * mu / (s_mu * s_mu) + log(s_mu) + c0;
+  Uv += 1.14472988584940017414 + log(s_tau) - 0.69314718055994530942 + log1p(u2) - t;
+  Uv += a0 + 2.0 * c0 * (double)J;
+  U[c] = (T)Uv;
+  grad[c * D] = (T)(mu / (s_mu * s_mu) - a1);
+  grad[c * D + 1] = (T)(2.0 * u2 / (1.0 + u2) - 1.0 - tau * a2);
+}
+
+// Logistic: grid = (bx, C); CTA strides over data rows; D <= 64 gradient components reduced
+// through shared memory.  beta is staged in shared memory.
+constexpr int kLogisticMaxD = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) logistic_kernel(const T* __restrict__ z,
+                                                       const T* __restrict__ X,
+                                                       const T* __restrict__ y,
+                                                       const uint8_t* __restrict__ active,
+                                                       double* __restrict__ partials, int64_t C,
+                                                       int64_t N, int D) {
+  __shared__ T beta[kLogisticMaxD];
+  __shared__ double smem[32];
+  __shared__ double gacc[kLogisticMaxD + 1];
+  for (int64_t c = blockIdx.y; c < C; c += gridDim.y) {
+    const bool on = !(active && !active[c]);
+    __syncthreads();
+    if (threadIdx.x < D) beta[threadIdx.x] = z[c * D + threadIdx.x];
+    if (threadIdx.x <= D) gacc[threadIdx.x] = 0.0;
+    __syncthreads();
+    T gl[kLogisticMaxD];
+    double ul = 0.0;
+#pragma unroll
+    for (int d = 0; d < kLogisticMaxD; ++d) gl[d] = 0;
+    if (on) {
+      for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
+           n += (int64_t)gridDim.x * blockDim.x) {
+        T l = 0;
+        for (int d = 0; d < D; ++d) l += X[n * D + d] * beta[d];
+        T sp, sg;
+        softplus_sigmoid(l, sp, sg);
+        const T yn = y[n];
+        ul -= (double)(yn * l - sp);
+        const T rr = sg - yn;
+#pragma unroll
+        for (int d = 0; d < kLogisticMaxD; ++d)
+          if (d < D) gl[d] += rr * X[n * D + d];
+      }
+    }
+    // reduce: one component at a time (D is small)
+    {
+      double red[1] = {ul};
+      block_sum<1>(red, smem);
+      if (threadIdx.x == 0) gacc[D] = red[0];
+    }
+#pragma unroll
+    for (int d = 0; d < kLogisticMaxD; ++d) {
+      if (d < D) {
+        double red[1] = {(double)gl[d]};
+        block_sum<1>(red, smem);
+        if (threadIdx.x == 0) gacc[d] = red[0];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x <= D)
+      partials[(c * gridDim.x + blockIdx.x) * (kLogisticMaxD + 1) + threadIdx.x] = gacc[threadIdx.x];
+  }
+}
+
+template <typename T>
+__global__ void logistic_finish_kernel(const T* __restrict__ z,
+                                       const double* __restrict__ partials, int nb,
+                                       const uint8_t* __restrict__ active, T* __restrict__ U,
+                                       T* __restrict__ grad, int64_t C, int D, double s) {
+  const int64_t c = blockIdx.x;
+  if (c >= C) return;
+  if (active && !active[c]) return;
+  const int d = threadIdx.x;
+  if (d > D) return;
+  double a = 0.0;
+  for (int i = 0; i < nb; ++i) a += partials[(c * nb + i) * (kLogisticMaxD + 1) + d];
+  if (d < D) {
+    grad[c * D + d] = (T)(a + (double)z[c * D + d] / (s * s));
+  } else {
+    double prior = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double zk = (double)z[c * D + k];
+      prior += 0.5 * zk * zk / (s * s) + log(s) + 0.91893853320467274178;
+    }
+    U[c] = (T)(a + prior);
+  }
+}
+
+// ---- whole-transition NUTS, one thread per chain -----------------------------------------------------
+template <typename T, typename Model, int MAXD>
+__global__ void nuts_small_kernel(Model model, int D, T* __restrict__ z, T* __restrict__ U,
+                                  T* __restrict__ grad, const T* __restrict__ step_size,
+                                  const T* __restrict__ minv, int64_t C, int num_transitions,
+                                  int max_depth, T max_delta, uint64_t seed,
+                                  uint64_t* __restrict__ rng_counter, T* __restrict__ samples,
+                                  T* __restrict__ accept_out, int32_t* __restrict__ depth_out,
+                                  int32_t* __restrict__ div_out, int32_t* __restrict__ steps_out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  T zl[MAXD], gl[MAXD], sm[MAXD];
+  for (int d = 0; d < D; ++d) {
+    zl[d] = z[c * D + d];
+    gl[d] = grad[c * D + d];
+    sm[d] = b2_sqrt(minv[c * D + d]);
+  }
+  T Ul = U[c];
+  const T eps = step_size[c];
+  Philox rng;
+  rng.init(seed, (uint64_t)c, rng_counter ? rng_counter[c] : 0);
+  for (int t = 0; t < num_transitions; ++t) {
+    NutsStats st;
+    nuts_transition<T, Model, MAXD>(model, D, zl, gl, Ul, eps, sm, max_depth, max_delta, rng, st);
+    const int64_t o = (int64_t)t * C + c;
+    if (samples)
+      for (int d = 0; d < D; ++d) samples[o * D + d] = zl[d];
+    if (accept_out) accept_out[o] = (T)st.accept_prob;
+    if (depth_out) depth_out[o] = st.depth;
+    if (div_out) div_out[o] = st.diverging;
+    if (steps_out) steps_out[o] = st.num_steps;
+  }
+  for (int d = 0; d < D; ++d) {
+    z[c * D + d] = zl[d];
+    grad[c * D + d] = gl[d];
+  }
+  U[c] = Ul;
+  if (rng_counter) rng_counter[c] = rng.counter() + 1;
+}
+
+inline unsigned bx_for(int64_t D, int64_t C) {
+  // CTAs along the data axis per chain: enough to fill the machine, few enough to keep the
+  // second-stage reduction short
+  int64_t bx = (D + 256 * 4 - 1) / (256 * 4);
+  const int64_t cap = ((int64_t)kNumSMs * 8 + C - 1) / (C > 0 ? C : 1);
+  if (bx > cap) bx = cap;
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  return (unsigned)bx;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_leapfrog_half_kick_drift(void* z, void* r, const void* g, const void* eps,
+                                           const void* minv, int64_t minv_chain_stride,
+                                           const uint8_t* active, int64_t C, int64_t D, int dtype,
+                                           void* stream) {
+  if (!z || !r || !g || !eps || !minv) return B2_ERR_NULL;
+  if (C <= 0 || D <= 0) return B2_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(bx_for(D, C), (unsigned)(C > 65535 ? 65535 : C), 1);
+  if (dtype == B2_F32)
+    kick_drift_kernel<float><<<grid, 256, 0, s>>>((float*)z, (float*)r, (const float*)g,
+                                                  (const float*)eps, (const float*)minv,
+                                                  minv_chain_stride, active, C, D);
+  else if (dtype == B2_F64)
+    kick_drift_kernel<double><<<grid, 256, 0, s>>>((double*)z, (double*)r, (const double*)g,
+                                                   (const double*)eps, (const double*)minv,
+                                                   minv_chain_stride, active, C, D);
+  else
+    return B2_ERR_BAD_DTYPE;
+  count_launch();
+  return check_launch();
+}
+
+extern "C" size_t b2_mcmc_workspace(int64_t C) {
+  // partials: C chains x up to 64 CTAs x (kLogisticMaxD + 1) doubles
+  return (size_t)(C > 0 ? C : 1) * 64 * (kLogisticMaxD + 1) * sizeof(double);
+}
+
+extern "C" int b2_leapfrog_half_kick(void* r, const void* g, const void* eps, const void* minv,
+                                     int64_t minv_chain_stride, const uint8_t* active, void* ke,
+                                     int64_t C, int64_t D, int dtype, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (!r || !g || !eps || !minv) return B2_ERR_NULL;
+  if (C <= 0 || D <= 0) return B2_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned bx = bx_for(D, C);
+  if (C > 65535) return B2_ERR_TOO_LARGE;
+  double* partials = nullptr;
+  if (ke) {
+    if (!workspace || workspace_bytes < (size_t)C * bx * sizeof(double)) return B2_ERR_WORKSPACE;
+    partials = reinterpret_cast<double*>(workspace);
+  }
+  dim3 grid(bx, (unsigned)C, 1);
+  if (dtype == B2_F32) {
+    kick_kernel<float><<<grid, 256, 0, s>>>((float*)r, (const float*)g, (const float*)eps,
+                                            (const float*)minv, minv_chain_stride, active,
+                                            partials, C, D);
+    if (ke) ke_finish_kernel<float><<<(unsigned)((C + 127) / 128), 128, 0, s>>>(partials, (int)bx, active, (float*)ke, C);
+  } else if (dtype == B2_F64) {
+    kick_kernel<double><<<grid, 256, 0, s>>>((double*)r, (const double*)g, (const double*)eps,
+                                             (const double*)minv, minv_chain_stride, active,
+                                             partials, C, D);
+    if (ke) ke_finish_kernel<double><<<(unsigned)((C + 127) / 128), 128, 0, s>>>(partials, (int)bx, active, (double*)ke, C);
+  } else {
+    return B2_ERR_BAD_DTYPE;
+  }
+  count_launch(ke ? 2 : 1);
+  return check_launch();
+}
+
+extern "C" size_t b2_potential_workspace(const b2_model* model, int64_t C) {
+  (void)model;
+  return b2_mcmc_workspace(C);
+}
+
+extern "C" int b2_potential_grad(const b2_model* model, const void* z, void* U, void* grad,
+                                 int64_t C, const uint8_t* active, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (!model || !z || !U || !grad || !model->data0 || !model->data1) return B2_ERR_NULL;
+  if (C <= 0) return B2_OK;
+  if (C > 65535) return B2_ERR_TOO_LARGE;
+  if (!workspace || workspace_bytes < b2_mcmc_workspace(C)) return B2_ERR_WORKSPACE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  double* partials = reinterpret_cast<double*>(workspace);
+  const int dt = model->dtype;
+  if (dt != B2_F32 && dt != B2_F64) return B2_ERR_BAD_DTYPE;
+  if (model->model == B2_MODEL_HIER_NORMAL) {
+    const int64_t J = model->J;
+    if (model->D != J + 2) return B2_ERR_BAD_SHAPE;
+    const unsigned bx = bx_for(J, C);
+    dim3 grid(bx, (unsigned)C, 1);
+    const unsigned fb = (unsigned)((C + 127) / 128);
+    if (dt == B2_F32) {
+      hier_normal_kernel<float><<<grid, 256, 0, s>>>((const float*)z, (const float*)model->data0,
+                                                     (const float*)model->data1, (float*)grad,
+                                                     active, partials, C, J);
+      hier_normal_finish_kernel<float><<<fb, 128, 0, s>>>((const float*)z, partials, (int)bx, active,
+                                                          (float*)U, (float*)grad, C, J,
+                                                          model->hyper[0], model->hyper[1]);
+    } else {
+      hier_normal_kernel<double><<<grid, 256, 0, s>>>((const double*)z, (const double*)model->data0,
+                                                      (const double*)model->data1, (double*)grad,
+                                                      active, partials, C, J);
+      hier_normal_finish_kernel<double><<<fb, 128, 0, s>>>((const double*)z, partials, (int)bx,
+                                                           active, (double*)U, (double*)grad, C, J,
+                                                           model->hyper[0], model->hyper[1]);
+    }
+    count_launch(2);
+    return check_launch();
+  }
+  if (model->model == B2_MODEL_LOGISTIC) {
+    const int D = (int)model->D;
+    if (D < 1 || D > kLogisticMaxD) return B2_ERR_TOO_LARGE;
+    const unsigned bx = bx_for(model->J, C);
+    dim3 grid(bx, (unsigned)C, 1);
+    if (dt == B2_F32) {
+      logistic_kernel<float><<<grid, 256, 0, s>>>((const float*)z, (const float*)model->data0,
+                                                  (const float*)model->data1, active, partials, C,
+                                                  model->J, D);
+      logistic_finish_kernel<float><<<(unsigned)C, 128, 0, s>>>((const float*)z, partials, (int)bx,
+                                                                active, (float*)U, (float*)grad, C,
+                                                                D, model->hyper[0]);
+    } else {
+      logistic_kernel<double><<<grid, 256, 0, s>>>((const double*)z, (const double*)model->data0,
+                                                   (const double*)model->data1, active, partials, C,
+                                                   model->J, D);
+      logistic_finish_kernel<double><<<(unsigned)C, 128, 0, s>>>((const double*)z, partials, (int)bx,
+                                                                 active, (double*)U, (double*)grad,
+                                                                 C, D, model->hyper[0]);
+    }
+    count_launch(2);
+    return check_launch();
+  }
+  return B2_ERR_BAD_FAMILY;
+}
+
+namespace {
+template <typename T, int MAXD>
+int launch_nuts_small(const b2_model* model, void* z, void* U, void* grad, const void* step_size,
+                      const void* minv, int64_t C, int num_transitions, int max_tree_depth,
+                      double max_delta, uint64_t seed, uint64_t* rng_counter, void* samples,
+                      void* accept, int32_t* depth, int32_t* div, int32_t* steps, cudaStream_t s) {
+  const int threads = 32;  // one warp per CTA: chains are independent, spread them over SMs
+  const unsigned blocks = (unsigned)((C + threads - 1) / threads);
+  const int D = (int)model->D;
+  if (model->model == B2_MODEL_HIER_NORMAL) {
+    HierNormalModel<T> m{(const T*)model->data0, (const T*)model->data1, model->J,
+                         (T)model->hyper[0], (T)model->hyper[1]};
+    nuts_small_kernel<T, HierNormalModel<T>, MAXD><<<blocks, threads, 0, s>>>(
+        m, D, (T*)z, (T*)U, (T*)grad, (const T*)step_size, (const T*)minv, C, num_transitions,
+        max_tree_depth, (T)max_delta, seed, rng_counter, (T*)samples, (T*)accept, depth, div, steps);
+  } else if (model->model == B2_MODEL_LOGISTIC) {
+    LogisticModel<T> m{(const T*)model->data0, (const T*)model->data1, model->J, D,
+                       (T)model->hyper[0]};
+    nuts_small_kernel<T, LogisticModel<T>, MAXD><<<blocks, threads, 0, s>>>(
+        m, D, (T*)z, (T*)U, (T*)grad, (const T*)step_size, (const T*)minv, C, num_transitions,
+        max_tree_depth, (T)max_delta, seed, rng_counter, (T*)samples, (T*)accept, depth, div, steps);
+  } else {
+    return B2_ERR_BAD_FAMILY;
+  }
+  count_launch();
+  return check_launch();
+}
+}  // namespace
+
+extern "C" int b2_nuts_small(const b2_model* model, void* z, void* U, void* grad,
+                             const void* step_size, const void* minv, int64_t C,
+                             int num_transitions, int max_tree_depth, double max_delta_energy,
+                             uint64_t seed, uint64_t* rng_counter, void* samples_out,
+                             void* accept_prob_out, int32_t* depth_out, int32_t* diverging_out,
+                             int32_t* num_steps_out, void* stream) {
+  if (!model || !z || !U || !grad || !step_size || !minv) return B2_ERR_NULL;
+  if (C <= 0 || num_transitions <= 0) return B2_OK;
+  if (max_tree_depth < 1 || max_tree_depth > kNutsMaxDepth) return B2_ERR_BAD_SHAPE;
+  if (model->D < 1 || model->D > B2_NUTS_SMALL_MAX_D) return B2_ERR_TOO_LARGE;
+  if (model->model == B2_MODEL_HIER_NORMAL && model->D != model->J + 2) return B2_ERR_BAD_SHAPE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+#define B2_NUTS_ARGS                                                                         \
+  model, z, U, grad, step_size, minv, C, num_transitions, max_tree_depth, max_delta_energy, \
+      seed, rng_counter, samples_out, accept_prob_out, depth_out, diverging_out, num_steps_out, s
+  if (model->dtype == B2_F32) {
+    if (model->D <= 16) return launch_nuts_small<float, 16>(B2_NUTS_ARGS);
+    return launch_nuts_small<float, 64>(B2_NUTS_ARGS);
+  } else if (model->dtype == B2_F64) {
+    if (model->D <= 16) return launch_nuts_small<double, 16>(B2_NUTS_ARGS);
+    return launch_nuts_small<double, 64>(B2_NUTS_ARGS);
+  }
+#undef B2_NUTS_ARGS
+  return B2_ERR_BAD_DTYPE;
+}
