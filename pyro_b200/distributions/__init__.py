@@ -1,0 +1,770 @@
+"""Distribution classes of the B200 backend.
+
+Host-side mirror of the reference's distribution protocol (pyro/distributions/distribution.py:29-222,
+pyro/distributions/torch_distribution.py:19-232): ``sample/rsample/log_prob/score_parts/expand/
+mask/to_event/has_rsample/batch_shape/event_shape/support``.  What differs is WHERE the arithmetic
+runs: ``log_prob`` and ``score_parts`` dispatch to the fused sm_100a kernels through the C ABI
+(``pyro_b200._native``); there is no ATen fallback -- scoring a CPU tensor raises.
+
+Parameters are kept at their STORED shape; ``expand`` only records the new batch shape, and the
+kernels read the operands through broadcast strides (what ExpandedDistribution does with views,
+pyro/distributions/torch_distribution.py:399-488), so gradients are reduced to the stored shape
+inside the backend instead of by autograd's ``sum_to_size``.
+
+Sampling (``rsample``/``sample``) uses torch's generators; fusing it with scoring is the next
+row of the scope table.
+"""
+import math
+from collections import namedtuple
+from numbers import Number
+
+import torch
+from torch.distributions import constraints
+
+from .. import _native as N
+from . import _ops
+
+
+# ---------------------------------------------------------------------------------------------
+# scale_and_mask / ScoreParts   (pyro/distributions/util.py:311-328, score_parts.py:11-38)
+# ---------------------------------------------------------------------------------------------
+def is_identically_zero(x):
+    if isinstance(x, Number):
+        return x == 0
+    return False
+
+
+def is_identically_one(x):
+    if isinstance(x, Number):
+        return x == 1
+    return False
+
+
+def scale_and_mask(tensor, scale=1.0, mask=None):
+    if is_identically_zero(tensor) or (mask is None and is_identically_one(scale)):
+        return tensor
+    if mask is None or mask is True:
+        return tensor * scale
+    if mask is False:
+        return torch.zeros_like(tensor)
+    return torch.where(mask, tensor * scale, tensor.new_zeros(()))
+
+
+class ScoreParts(namedtuple("ScoreParts", ["log_prob", "score_function", "entropy_term"])):
+    def scale_and_mask(self, scale=1.0, mask=None):
+        log_prob = scale_and_mask(self.log_prob, scale, mask)
+        score_function = self.score_function  # not scaled
+        entropy_term = scale_and_mask(self.entropy_term, scale, mask)
+        return ScoreParts(log_prob, score_function, entropy_term)
+
+
+def _as_tensor(x, like=None):
+    if isinstance(x, torch.Tensor):
+        return x
+    if like is not None:
+        return torch.as_tensor(x, dtype=like.dtype, device=like.device)
+    return torch.as_tensor(x, dtype=torch.get_default_dtype())
+
+
+def _broadcast_params(*xs):
+    """Tensor-ify python numbers next to the first tensor argument (dtype/device follow it)."""
+    ref = None
+    for x in xs:
+        if isinstance(x, torch.Tensor):
+            ref = x
+            break
+    out = []
+    for x in xs:
+        t = _as_tensor(x, ref)
+        if ref is not None and t.dtype != ref.dtype and t.is_floating_point():
+            t = t.to(ref.dtype)
+        out.append(t)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# base class
+# ---------------------------------------------------------------------------------------------
+class Distribution:
+    has_rsample = False
+    has_enumerate_support = False
+    arg_constraints = {}
+    support = constraints.real
+    _event_ndim = 0
+
+    def __init__(self, batch_shape=torch.Size(), event_shape=torch.Size()):
+        self._batch_shape = torch.Size(batch_shape)
+        self._event_shape = torch.Size(event_shape)
+
+    # -- shapes ---------------------------------------------------------------------------------
+    @property
+    def batch_shape(self):
+        return self._batch_shape
+
+    @property
+    def event_shape(self):
+        return self._event_shape
+
+    @property
+    def event_dim(self):
+        return len(self._event_shape)
+
+    def shape(self, sample_shape=torch.Size()):
+        return torch.Size(sample_shape) + self.batch_shape + self.event_shape
+
+    # -- sampling -------------------------------------------------------------------------------
+    def __call__(self, sample_shape=torch.Size()):
+        # pyro/distributions/torch_distribution.py:31-52
+        return self.rsample(sample_shape) if self.has_rsample else self.sample(sample_shape)
+
+    def sample(self, sample_shape=torch.Size()):
+        with torch.no_grad():
+            return self.rsample(sample_shape)
+
+    def rsample(self, sample_shape=torch.Size()):
+        raise NotImplementedError
+
+    def has_rsample_(self, value):
+        if not (value is True or value is False):
+            raise ValueError("Expected value in [False,True], actual {}".format(value))
+        self.has_rsample = value
+        return self
+
+    # -- scoring --------------------------------------------------------------------------------
+    def log_prob(self, value):
+        raise NotImplementedError
+
+    def score_parts(self, value):
+        # pyro/distributions/distribution.py:98-125
+        log_prob = self.log_prob(value)
+        if self.has_rsample:
+            return ScoreParts(log_prob=log_prob, score_function=0, entropy_term=log_prob)
+        return ScoreParts(log_prob=log_prob, score_function=log_prob, entropy_term=0)
+
+    def _fused_sum(self, value, mask, scale, weight, sum_coeff, unit=True):
+        """0-d ``sum_coeff*sum(scale*mask*log_prob(value))`` with fused final gradients, or None
+        if this distribution has no fused path (the caller then uses ``log_prob``)."""
+        return None
+
+    # -- structure ------------------------------------------------------------------------------
+    def expand(self, batch_shape, _instance=None):
+        raise NotImplementedError
+
+    def expand_by(self, sample_shape):
+        return self.expand(torch.Size(sample_shape) + self.batch_shape)
+
+    def to_event(self, reinterpreted_batch_ndims=None):
+        if reinterpreted_batch_ndims is None:
+            reinterpreted_batch_ndims = len(self.batch_shape)
+        if reinterpreted_batch_ndims == 0:
+            return self
+        return Independent(self, reinterpreted_batch_ndims)
+
+    def independent(self, reinterpreted_batch_ndims=None):
+        return self.to_event(reinterpreted_batch_ndims)
+
+    def mask(self, mask):
+        return MaskedDistribution(self, mask)
+
+
+# ---------------------------------------------------------------------------------------------
+# elementwise families on the fused kernel
+# ---------------------------------------------------------------------------------------------
+class _Elementwise(Distribution):
+    family = None
+    param_names = ()
+    _torch_cls = None
+
+    def __init__(self, *params, batch_shape=None):
+        params = _broadcast_params(*params)
+        self._params = params
+        for n, p in zip(self.param_names, params):
+            setattr(self, n, p)
+        if batch_shape is None:
+            batch_shape = torch.broadcast_shapes(*[p.shape for p in params])
+        super().__init__(batch_shape)
+
+    def _kernel_params(self):
+        return self._params
+
+    def expand(self, batch_shape, _instance=None):
+        batch_shape = torch.Size(batch_shape)
+        torch.broadcast_shapes(self.batch_shape, batch_shape)  # validates
+        new = self.__class__.__new__(self.__class__)
+        new.__dict__.update(self.__dict__)
+        new._batch_shape = batch_shape
+        return new
+
+    def _torch(self):
+        kw = {n: p.expand(self.batch_shape) if tuple(p.shape) != tuple(self.batch_shape) else p
+              for n, p in zip(self.param_names, self._params)}
+        return self._torch_cls(**kw, validate_args=False)
+
+    def rsample(self, sample_shape=torch.Size()):
+        return self._torch().rsample(sample_shape)
+
+    def sample(self, sample_shape=torch.Size()):
+        return self._torch().sample(sample_shape)
+
+    def _value(self, value):
+        ref = self._params[0]
+        if not isinstance(value, torch.Tensor):
+            value = torch.as_tensor(value, dtype=ref.dtype, device=ref.device)
+        if value.dtype != ref.dtype:
+            value = value.to(ref.dtype)
+        return value
+
+    def log_prob(self, value):
+        return _ops.log_prob_op(self.family, self._value(value), self._kernel_params(),
+                                self.batch_shape)
+
+    def _fused_sum(self, value, mask, scale, weight, sum_coeff, unit=True):
+        return _ops.fused_site_sum(self.family, self._value(value), self._kernel_params(),
+                                   self.batch_shape, mask=mask, scale=scale, weight=weight,
+                                   sum_coeff=sum_coeff, assume_unit_upstream=unit)
+
+    @property
+    def mean(self):
+        return self._torch().mean
+
+    @property
+    def variance(self):
+        return self._torch().variance
+
+    def entropy(self):
+        return self._torch().entropy()
+
+    def __repr__(self):
+        args = ", ".join("{}: {}".format(n, tuple(p.shape)) for n, p in zip(self.param_names, self._params))
+        return "{}({}; batch_shape={})".format(type(self).__name__, args, tuple(self.batch_shape))
+
+
+class Normal(_Elementwise):
+    family = N.NORMAL
+    param_names = ("loc", "scale")
+    arg_constraints = {"loc": constraints.real, "scale": constraints.positive}
+    support = constraints.real
+    has_rsample = True
+    _torch_cls = torch.distributions.Normal
+
+    def __init__(self, loc, scale, validate_args=None):
+        super().__init__(loc, scale)
+
+    def rsample(self, sample_shape=torch.Size()):
+        shape = self.shape(sample_shape)
+        eps = torch.randn(shape, dtype=self.loc.dtype, device=self.loc.device)
+        return self.loc + eps * self.scale
+
+
+class Cauchy(_Elementwise):
+    family = N.CAUCHY
+    param_names = ("loc", "scale")
+    arg_constraints = {"loc": constraints.real, "scale": constraints.positive}
+    has_rsample = True
+    _torch_cls = torch.distributions.Cauchy
+
+    def __init__(self, loc, scale, validate_args=None):
+        super().__init__(loc, scale)
+
+
+class HalfCauchy(_Elementwise):
+    family = N.HALFCAUCHY
+    param_names = ("scale",)
+    arg_constraints = {"scale": constraints.positive}
+    support = constraints.nonnegative
+    has_rsample = True
+    _torch_cls = torch.distributions.HalfCauchy
+
+    def __init__(self, scale, validate_args=None):
+        super().__init__(scale)
+
+
+class HalfNormal(_Elementwise):
+    family = N.HALFNORMAL
+    param_names = ("scale",)
+    arg_constraints = {"scale": constraints.positive}
+    support = constraints.nonnegative
+    has_rsample = True
+    _torch_cls = torch.distributions.HalfNormal
+
+    def __init__(self, scale, validate_args=None):
+        super().__init__(scale)
+
+
+class LogNormal(_Elementwise):
+    family = N.LOGNORMAL
+    param_names = ("loc", "scale")
+    arg_constraints = {"loc": constraints.real, "scale": constraints.positive}
+    support = constraints.positive
+    has_rsample = True
+    _torch_cls = torch.distributions.LogNormal
+
+    def __init__(self, loc, scale, validate_args=None):
+        super().__init__(loc, scale)
+
+
+class Exponential(_Elementwise):
+    family = N.EXPONENTIAL
+    param_names = ("rate",)
+    arg_constraints = {"rate": constraints.positive}
+    support = constraints.nonnegative
+    has_rsample = True
+    _torch_cls = torch.distributions.Exponential
+
+    def __init__(self, rate, validate_args=None):
+        super().__init__(rate)
+
+
+class Uniform(_Elementwise):
+    family = N.UNIFORM
+    param_names = ("low", "high")
+    arg_constraints = {"low": constraints.dependent, "high": constraints.dependent}
+    has_rsample = True
+    _torch_cls = torch.distributions.Uniform
+
+    def __init__(self, low, high, validate_args=None):
+        super().__init__(low, high)
+
+    @property
+    def support(self):
+        return constraints.interval(self.low, self.high)
+
+
+class Gamma(_Elementwise):
+    family = N.GAMMA
+    param_names = ("concentration", "rate")
+    arg_constraints = {"concentration": constraints.positive, "rate": constraints.positive}
+    support = constraints.nonnegative
+    has_rsample = True
+    _torch_cls = torch.distributions.Gamma
+
+    def __init__(self, concentration, rate, validate_args=None):
+        super().__init__(concentration, rate)
+
+
+class Beta(_Elementwise):
+    family = N.BETA
+    param_names = ("concentration1", "concentration0")
+    arg_constraints = {"concentration1": constraints.positive, "concentration0": constraints.positive}
+    support = constraints.unit_interval
+    has_rsample = True
+    _torch_cls = torch.distributions.Beta
+
+    def __init__(self, concentration1, concentration0, validate_args=None):
+        super().__init__(concentration1, concentration0)
+
+
+class Poisson(_Elementwise):
+    family = N.POISSON
+    param_names = ("rate",)
+    arg_constraints = {"rate": constraints.nonnegative}
+    support = constraints.nonnegative_integer
+    has_rsample = False
+    _torch_cls = torch.distributions.Poisson
+
+    def __init__(self, rate, validate_args=None, is_sparse=False):
+        # is_sparse (pyro/distributions/torch.py:280-294) changes only which elements are
+        # evaluated; the fused kernel evaluates the dense form in one pass either way.
+        super().__init__(rate)
+
+    def rsample(self, sample_shape=torch.Size()):
+        raise NotImplementedError("Poisson has no rsample")
+
+    def sample(self, sample_shape=torch.Size()):
+        return self._torch().sample(sample_shape)
+
+
+class Bernoulli(_Elementwise):
+    arg_constraints = {"probs": constraints.unit_interval, "logits": constraints.real}
+    support = constraints.boolean
+    has_rsample = False
+
+    def __init__(self, probs=None, logits=None, validate_args=None):
+        if (probs is None) == (logits is None):
+            raise ValueError("Either `probs` or `logits` must be specified, but not both.")
+        if logits is not None:
+            self.family = N.BERNOULLI_LOGITS
+            self.param_names = ("logits",)
+            super().__init__(logits)
+        else:
+            self.family = N.BERNOULLI_PROBS
+            self.param_names = ("probs",)
+            super().__init__(probs)
+
+    def _torch(self):
+        p = self._params[0]
+        p = p.expand(self.batch_shape) if tuple(p.shape) != tuple(self.batch_shape) else p
+        if self.family == N.BERNOULLI_LOGITS:
+            return torch.distributions.Bernoulli(logits=p, validate_args=False)
+        return torch.distributions.Bernoulli(probs=p, validate_args=False)
+
+    def rsample(self, sample_shape=torch.Size()):
+        raise NotImplementedError("Bernoulli has no rsample")
+
+    def sample(self, sample_shape=torch.Size()):
+        return self._torch().sample(sample_shape)
+
+
+# ---------------------------------------------------------------------------------------------
+# event families
+# ---------------------------------------------------------------------------------------------
+class _EventFamily(Distribution):
+    family = None
+
+    def expand(self, batch_shape, _instance=None):
+        batch_shape = torch.Size(batch_shape)
+        torch.broadcast_shapes(self.batch_shape, batch_shape)
+        new = self.__class__.__new__(self.__class__)
+        new.__dict__.update(self.__dict__)
+        new._batch_shape = batch_shape
+        return new
+
+    def rsample(self, sample_shape=torch.Size()):
+        return self._torch().rsample(sample_shape)
+
+    def sample(self, sample_shape=torch.Size()):
+        return self._torch().sample(sample_shape)
+
+
+class Dirichlet(_EventFamily):
+    family = N.DIRICHLET
+    arg_constraints = {"concentration": constraints.independent(constraints.positive, 1)}
+    support = constraints.simplex
+    has_rsample = True
+
+    def __init__(self, concentration, validate_args=None):
+        self.concentration = concentration
+        super().__init__(concentration.shape[:-1], concentration.shape[-1:])
+
+    def _torch(self):
+        c = self.concentration.expand(self.batch_shape + self.event_shape)
+        return torch.distributions.Dirichlet(c, validate_args=False)
+
+    def log_prob(self, value):
+        bshape = torch.broadcast_shapes(self.batch_shape, value.shape[:-1])
+        return _ops.log_prob_op(self.family, value, [self.concentration], bshape,
+                                event_size=self.event_shape[0])
+
+    def _fused_sum(self, value, mask, scale, weight, sum_coeff, unit=True):
+        bshape = torch.broadcast_shapes(self.batch_shape, value.shape[:-1])
+        return _ops.fused_site_sum(self.family, value, [self.concentration], bshape, mask=mask,
+                                   scale=scale, weight=weight, sum_coeff=sum_coeff,
+                                   event_size=self.event_shape[0], assume_unit_upstream=unit)
+
+
+class Categorical(_EventFamily):
+    family = N.CATEGORICAL
+    arg_constraints = {"probs": constraints.simplex, "logits": constraints.real_vector}
+    has_rsample = False
+    has_enumerate_support = True
+
+    def __init__(self, probs=None, logits=None, validate_args=None):
+        if (probs is None) == (logits is None):
+            raise ValueError("Either `probs` or `logits` must be specified, but not both.")
+        if probs is not None:
+            # torch/distributions/categorical.py:70-72 + utils.probs_to_logits: log of the
+            # normalised, clamped probabilities.  The kernel normalises logits itself.
+            eps = torch.finfo(probs.dtype).eps
+            logits = torch.log((probs / probs.sum(-1, keepdim=True)).clamp(min=eps, max=1 - eps))
+        self._logits_raw = logits
+        self._num_events = logits.shape[-1]
+        super().__init__(logits.shape[:-1])
+
+    @property
+    def logits(self):
+        return self._logits_raw - self._logits_raw.logsumexp(dim=-1, keepdim=True)
+
+    @property
+    def probs(self):
+        return torch.softmax(self._logits_raw, dim=-1)
+
+    @property
+    def support(self):
+        return constraints.integer_interval(0, self._num_events - 1)
+
+    def _torch(self):
+        lg = self._logits_raw.expand(self.batch_shape + (self._num_events,))
+        return torch.distributions.Categorical(logits=lg, validate_args=False)
+
+    def rsample(self, sample_shape=torch.Size()):
+        raise NotImplementedError("Categorical has no rsample")
+
+    def sample(self, sample_shape=torch.Size()):
+        return self._torch().sample(sample_shape)
+
+    def _value(self, value):
+        if value.dtype != torch.int64:
+            value = value.long()
+        return value
+
+    def log_prob(self, value):
+        value = self._value(value)
+        bshape = torch.broadcast_shapes(self.batch_shape, value.shape)
+        return _ops.log_prob_op(self.family, value, [self._logits_raw], bshape,
+                                event_size=self._num_events)
+
+    def _fused_sum(self, value, mask, scale, weight, sum_coeff, unit=True):
+        value = self._value(value)
+        bshape = torch.broadcast_shapes(self.batch_shape, value.shape)
+        return _ops.fused_site_sum(self.family, value, [self._logits_raw], bshape, mask=mask,
+                                   scale=scale, weight=weight, sum_coeff=sum_coeff,
+                                   event_size=self._num_events, assume_unit_upstream=unit)
+
+    def enumerate_support(self, expand=True):
+        return self._torch().enumerate_support(expand)
+
+
+class MultivariateNormal(_EventFamily):
+    family = N.MVN_TRIL
+    arg_constraints = {"loc": constraints.real_vector, "scale_tril": constraints.lower_cholesky}
+    support = constraints.real_vector
+    has_rsample = True
+
+    def __init__(self, loc, covariance_matrix=None, precision_matrix=None, scale_tril=None,
+                 validate_args=None):
+        if (covariance_matrix is not None) + (scale_tril is not None) + (precision_matrix is not None) != 1:
+            raise ValueError("Exactly one of covariance_matrix or precision_matrix or scale_tril "
+                             "may be specified.")
+        if covariance_matrix is not None:
+            scale_tril = torch.linalg.cholesky(covariance_matrix)
+        elif precision_matrix is not None:
+            # torch/distributions/multivariate_normal.py:_precision_to_scale_tril
+            Lf = torch.linalg.cholesky(torch.flip(precision_matrix, (-2, -1)))
+            L_inv = torch.transpose(torch.flip(Lf, (-2, -1)), -2, -1)
+            Id = torch.eye(precision_matrix.shape[-1], dtype=precision_matrix.dtype,
+                           device=precision_matrix.device)
+            scale_tril = torch.linalg.solve_triangular(L_inv, Id, upper=False)
+        self.loc = loc
+        self.scale_tril = scale_tril
+        batch = torch.broadcast_shapes(loc.shape[:-1], scale_tril.shape[:-2])
+        super().__init__(batch, loc.shape[-1:])
+
+    def _torch(self):
+        return torch.distributions.MultivariateNormal(
+            self.loc.expand(self.batch_shape + self.event_shape),
+            scale_tril=self.scale_tril.expand(self.batch_shape + self.event_shape * 2),
+            validate_args=False)
+
+    def log_prob(self, value):
+        bshape = torch.broadcast_shapes(self.batch_shape, value.shape[:-1])
+        return _ops.log_prob_op(self.family, value, [self.loc, self.scale_tril], bshape,
+                                event_size=self.event_shape[0])
+
+    def _fused_sum(self, value, mask, scale, weight, sum_coeff, unit=True):
+        bshape = torch.broadcast_shapes(self.batch_shape, value.shape[:-1])
+        return _ops.fused_site_sum(self.family, value, [self.loc, self.scale_tril], bshape,
+                                   mask=mask, scale=scale, weight=weight, sum_coeff=sum_coeff,
+                                   event_size=self.event_shape[0], assume_unit_upstream=unit)
+
+
+class Delta(Distribution):
+    """Degenerate point mass (pyro/distributions/delta.py); pure bookkeeping, no kernel needed:
+    log_prob is ``log_density`` where value == v (always true for replayed sites)."""
+    has_rsample = True
+    arg_constraints = {"v": constraints.dependent, "log_density": constraints.real}
+
+    def __init__(self, v, log_density=0.0, event_dim=0, validate_args=None):
+        self.v = v
+        self.log_density = _as_tensor(log_density, v) if not isinstance(log_density, torch.Tensor) else log_density
+        batch_dim = v.dim() - event_dim
+        super().__init__(v.shape[:batch_dim], v.shape[batch_dim:])
+
+    @property
+    def support(self):
+        return constraints.independent(constraints.real, len(self.event_shape))
+
+    def expand(self, batch_shape, _instance=None):
+        batch_shape = torch.Size(batch_shape)
+        new = Delta.__new__(Delta)
+        new.v = self.v.expand(batch_shape + self.event_shape)
+        new.log_density = self.log_density.expand(batch_shape) if self.log_density.dim() else self.log_density
+        Distribution.__init__(new, batch_shape, self.event_shape)
+        return new
+
+    def rsample(self, sample_shape=torch.Size()):
+        return self.v.expand(self.shape(sample_shape))
+
+    def log_prob(self, x):
+        v = self.v.expand(self.shape())
+        lp = (x == v).type(x.dtype).log()
+        for _ in range(len(self.event_shape)):
+            lp = lp.sum(-1)
+        return lp + self.log_density
+
+
+# ---------------------------------------------------------------------------------------------
+# wrappers
+# ---------------------------------------------------------------------------------------------
+class Independent(Distribution):
+    """Reinterprets batch dims as event dims (torch.distributions.Independent semantics,
+    reached in the reference through TorchDistributionMixin.to_event,
+    pyro/distributions/torch_distribution.py:163-213)."""
+
+    def __init__(self, base_dist, reinterpreted_batch_ndims, validate_args=None):
+        if reinterpreted_batch_ndims > len(base_dist.batch_shape):
+            raise ValueError("Expected reinterpreted_batch_ndims <= len(base_distribution.batch_shape), "
+                             "actual {} vs {}".format(reinterpreted_batch_ndims, len(base_dist.batch_shape)))
+        self.base_dist = base_dist
+        self.reinterpreted_batch_ndims = reinterpreted_batch_ndims
+        shape = base_dist.batch_shape + base_dist.event_shape
+        ev = reinterpreted_batch_ndims + len(base_dist.event_shape)
+        super().__init__(shape[: len(shape) - ev], shape[len(shape) - ev:])
+
+    @property
+    def has_rsample(self):
+        return self.base_dist.has_rsample
+
+    @has_rsample.setter
+    def has_rsample(self, value):
+        self.base_dist.has_rsample = value
+
+    @property
+    def support(self):
+        return constraints.independent(self.base_dist.support, self.reinterpreted_batch_ndims)
+
+    def rsample(self, sample_shape=torch.Size()):
+        return self.base_dist.rsample(sample_shape)
+
+    def sample(self, sample_shape=torch.Size()):
+        return self.base_dist.sample(sample_shape)
+
+    def log_prob(self, value):
+        lp = self.base_dist.log_prob(value)
+        n = self.reinterpreted_batch_ndims
+        return lp.sum(dim=tuple(range(-n, 0))) if n else lp
+
+    def _fused_sum(self, value, mask, scale, weight, sum_coeff, unit=True):
+        # the total over batch AND event dims is what the ELBO needs; a site mask has batch
+        # shape, so align it with the base distribution's batch dims
+        if mask is not None and isinstance(mask, torch.Tensor):
+            mask = mask.reshape(mask.shape + (1,) * self.reinterpreted_batch_ndims)
+        return self.base_dist._fused_sum(value, mask, scale, weight, sum_coeff, unit)
+
+    def expand(self, batch_shape, _instance=None):
+        batch_shape = torch.Size(batch_shape)
+        n = self.reinterpreted_batch_ndims
+        base_event = self.event_shape[:n]
+        return Independent(self.base_dist.expand(batch_shape + base_event), n)
+
+    def to_event(self, reinterpreted_batch_ndims=None):
+        if reinterpreted_batch_ndims is None:
+            reinterpreted_batch_ndims = len(self.batch_shape)
+        if reinterpreted_batch_ndims == 0:
+            return self
+        return Independent(self.base_dist, self.reinterpreted_batch_ndims + reinterpreted_batch_ndims)
+
+    def entropy(self):
+        e = self.base_dist.entropy()
+        n = self.reinterpreted_batch_ndims
+        return e.sum(dim=tuple(range(-n, 0))) if n else e
+
+
+class MaskedDistribution(Distribution):
+    """pyro/distributions/torch_distribution.py:302-374."""
+
+    def __init__(self, base_dist, mask):
+        if isinstance(mask, bool):
+            self._mask = mask
+        else:
+            batch_shape = torch.broadcast_shapes(mask.shape, base_dist.batch_shape)
+            if mask.shape != batch_shape:
+                mask = mask.expand(batch_shape)
+            if base_dist.batch_shape != batch_shape:
+                base_dist = base_dist.expand(batch_shape)
+            self._mask = mask.bool()
+        self.base_dist = base_dist
+        super().__init__(base_dist.batch_shape, base_dist.event_shape)
+
+    @property
+    def has_rsample(self):
+        return self.base_dist.has_rsample
+
+    @has_rsample.setter
+    def has_rsample(self, value):
+        self.base_dist.has_rsample = value
+
+    @property
+    def support(self):
+        return self.base_dist.support
+
+    def expand(self, batch_shape, _instance=None):
+        batch_shape = torch.Size(batch_shape)
+        mask = self._mask
+        if isinstance(mask, torch.Tensor):
+            mask = mask.expand(batch_shape)
+        return MaskedDistribution(self.base_dist.expand(batch_shape), mask)
+
+    def rsample(self, sample_shape=torch.Size()):
+        return self.base_dist.rsample(sample_shape)
+
+    def sample(self, sample_shape=torch.Size()):
+        return self.base_dist.sample(sample_shape)
+
+    def log_prob(self, value):
+        if self._mask is False:
+            shape = torch.broadcast_shapes(self.base_dist.batch_shape,
+                                           value.shape[: value.dim() - self.event_dim])
+            return torch.zeros((), device=value.device).expand(shape)
+        if self._mask is True:
+            return self.base_dist.log_prob(value)
+        return scale_and_mask(self.base_dist.log_prob(value), mask=self._mask)
+
+    def score_parts(self, value):
+        if isinstance(self._mask, bool):
+            return super().score_parts(value)
+        return self.base_dist.score_parts(value).scale_and_mask(mask=self._mask)
+
+    def _fused_sum(self, value, mask, scale, weight, sum_coeff, unit=True):
+        if self._mask is False:
+            return None
+        m = self._mask if isinstance(self._mask, torch.Tensor) else None
+        if m is not None and mask is not None and isinstance(mask, torch.Tensor):
+            m = m & mask
+        elif m is None:
+            m = mask
+        return self.base_dist._fused_sum(value, m, scale, weight, sum_coeff, unit)
+
+
+# ---------------------------------------------------------------------------------------------
+# KL divergences on the fused kernel (torch/distributions/kl.py:301-306,468-471), used by
+# TraceMeanField_ELBO (pyro/infer/trace_mean_field_elbo.py:117-132)
+# ---------------------------------------------------------------------------------------------
+def kl_divergence(p, q):
+    if isinstance(p, Independent) and isinstance(q, Independent):
+        if p.reinterpreted_batch_ndims != q.reinterpreted_batch_ndims:
+            raise NotImplementedError
+        kl = kl_divergence(p.base_dist, q.base_dist)
+        n = p.reinterpreted_batch_ndims
+        return kl.sum(dim=tuple(range(-n, 0))) if n else kl
+    if type(p) is Normal and type(q) is Normal:
+        fam = N.KL_NORMAL_NORMAL
+    elif type(p) is Gamma and type(q) is Gamma:
+        fam = N.KL_GAMMA_GAMMA
+    else:
+        raise NotImplementedError("kl_divergence({}, {})".format(type(p).__name__, type(q).__name__))
+    shape = torch.broadcast_shapes(p.batch_shape, q.batch_shape)
+    return _ops.log_prob_op(fam, None, list(p._params) + list(q._params), shape)
+
+
+def fused_kl_sum(p, q, mask, scale, weight, sum_coeff, unit=True):
+    """0-d ``sum_coeff*sum(scale*mask*KL(p||q))`` with fused final gradients, or None."""
+    while isinstance(p, Independent) and isinstance(q, Independent) and \
+            p.reinterpreted_batch_ndims == q.reinterpreted_batch_ndims:
+        if mask is not None and isinstance(mask, torch.Tensor):
+            mask = mask.reshape(mask.shape + (1,) * p.reinterpreted_batch_ndims)
+        p, q = p.base_dist, q.base_dist
+    if type(p) is Normal and type(q) is Normal:
+        fam = N.KL_NORMAL_NORMAL
+    elif type(p) is Gamma and type(q) is Gamma:
+        fam = N.KL_GAMMA_GAMMA
+    else:
+        return None
+    shape = torch.broadcast_shapes(p.batch_shape, q.batch_shape)
+    return _ops.fused_site_sum(fam, None, list(p._params) + list(q._params), shape, mask=mask,
+                               scale=scale, weight=weight, sum_coeff=sum_coeff, assume_unit_upstream=unit)
+
+
+__all__ = ["Distribution", "Normal", "Bernoulli", "Gamma", "Beta", "Poisson", "Cauchy", "HalfCauchy",
+           "HalfNormal", "LogNormal", "Exponential", "Uniform", "Dirichlet", "Categorical",
+           "MultivariateNormal", "Delta", "Independent", "MaskedDistribution", "ScoreParts",
+           "kl_divergence", "scale_and_mask", "is_identically_zero", "is_identically_one"]

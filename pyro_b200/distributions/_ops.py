@@ -1,0 +1,316 @@
+"""Native-backed scoring ops: thin wrappers over the C ABI plus the autograd glue.
+
+Two entry points per family kind:
+
+``log_prob_op``   materialised ``log_prob`` tensor with autograd (drop-in for
+                  ``site["fn"].log_prob(value)``, pyro/poutine/trace_struct.py:264).  Backward is
+                  one more fused kernel that consumes the upstream gradient.
+``fused_site_sum``  the ELBO fast path: ONE kernel returns ``sum(scale*mask*log_prob)`` and, in the
+                  same pass, the final (weight-multiplied) gradients of every operand that
+                  requires grad.  Its autograd node only hands those gradients back, under the
+                  contract that the upstream gradient is exactly 1 (our Trace_ELBO guarantees it).
+"""
+import ctypes
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from .. import _native as N
+
+
+def _common_shape(value, params, batch_shape=None):
+    shapes = [p.shape for p in params]
+    if value is not None:
+        shapes.append(value.shape)
+    if batch_shape is not None:
+        shapes.append(torch.Size(batch_shape))
+    return torch.broadcast_shapes(*shapes)
+
+
+def _pad_shape(t_shape, nd):
+    return (1,) * (nd - len(t_shape)) + tuple(t_shape)
+
+
+def _grad_plan(t, shape):
+    """How the gradient of operand ``t`` (stored shape) comes out of a kernel working on ``shape``:
+    ('full', out), ('scalar', out) or ('reduce', out, tmp)."""
+    if t.numel() == 1 and len(shape) > 0 and _numel(shape) > 1:
+        out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+        return ("scalar", out, None)
+    if _pad_shape(t.shape, len(shape)) == tuple(shape):
+        out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+        return ("full", out, None)
+    out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+    tmp = torch.empty(shape, dtype=t.dtype, device=t.device)
+    return ("reduce", out, tmp)
+
+
+def _numel(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+def _plan_desc(plan, shape):
+    kind, out, tmp = plan
+    nd = len(shape)
+    if kind == "scalar":
+        d = N.b2_tensor()
+        d.ptr = out.data_ptr()
+        d.dtype = N._DTYPES[out.dtype]
+        d.ndim = nd
+        for i in range(nd):
+            d.shape[i] = shape[i]
+            d.stride[i] = 0
+        return d
+    if kind == "full":
+        return N.desc(out.reshape(_pad_shape(out.shape, nd)), shape)
+    return N.desc(tmp, shape)
+
+
+def reduce_to(src, dst):
+    """dst[stored shape] = sum of src over the dims where dst is broadcast (own kernel, fixed order)."""
+    shape = tuple(src.shape)
+    nd = len(shape)
+    dv = dst.reshape(_pad_shape(dst.shape, nd))
+    sd = N.desc(src, shape)
+    dd = N.desc(dv.expand(shape) if tuple(dv.shape) != shape else dv, shape)
+    ws = N.workspace(src.device)
+    N.check(N.lib().b2_reduce_to(ctypes.byref(sd), ctypes.byref(dd), ws.data_ptr(), ws.numel(),
+                                 N.stream_ptr(src.device)), "b2_reduce_to")
+
+
+def _finish_plans(plans):
+    outs = []
+    for plan in plans:
+        if plan is None:
+            outs.append(None)
+            continue
+        kind, out, tmp = plan
+        if kind == "reduce":
+            reduce_to(tmp, out)
+        outs.append(out)
+    return outs
+
+
+def site_score(family, value, params, shape, *, mask=None, scale=1.0, upstream=None, weight=1.0,
+               sum_coeff=1.0, accumulate=False, want_logprob=False, out_sum=None,
+               need_dvalue=False, need_dparams=None, event_size=None):
+    """Launch the fused kernel for one site.  Returns (logprob | None, dvalue | None, [dparams])."""
+    ref = params[0]
+    N.require_cuda(ref, "log_prob scoring")
+    dev = ref.device
+    if _numel(shape) == 0:
+        return _empty_site(value, params, shape, want_logprob, out_sum, accumulate, need_dvalue,
+                           need_dparams)
+    nd = len(shape)
+    np_ = len(params)
+    need_dparams = need_dparams or [False] * np_
+    elementwise = event_size is None
+    if elementwise:
+        bshape = tuple(shape)
+    else:
+        bshape = tuple(shape)  # batch shape; event dims are trailing dims of each operand
+
+    def ev_desc(t, ev_ndim):
+        # descriptor over the batch dims only (event dims contiguous)
+        bs = t.shape[: t.dim() - ev_ndim] if ev_ndim else t.shape
+        view = t
+        full = tuple(bshape) + tuple(t.shape[t.dim() - ev_ndim:]) if ev_ndim else tuple(bshape)
+        view = t.expand(full) if tuple(t.shape) != full else t
+        d = N.b2_tensor()
+        d.ptr = view.data_ptr()
+        d.dtype = N._DTYPES[view.dtype]
+        d.ndim = len(bshape)
+        st = view.stride()
+        for i in range(len(bshape)):
+            d.shape[i] = bshape[i]
+            d.stride[i] = st[i] if bshape[i] != 1 else 0
+        return d
+
+    lp = torch.empty(bshape, dtype=ref.dtype, device=dev) if want_logprob else None
+    ws = N.workspace(dev)
+    flags = N.B2_FLAG_ACCUMULATE_SUM if accumulate else 0
+    pdesc = (N.b2_tensor * np_)()
+    gdesc = (N.b2_tensor * np_)()
+    if elementwise:
+        vd = N.desc(value, shape) if value is not None else N.desc(None, shape)
+        if value is None:
+            vd.dtype = N._DTYPES[ref.dtype]
+            for i in range(nd):
+                vd.shape[i] = shape[i]
+        for k in range(np_):
+            pdesc[k] = N.desc(params[k], shape)
+        md = N.desc(mask, shape) if mask is not None else None
+        ud = N.desc(upstream, shape) if upstream is not None else None
+        lpd = N.desc(lp, shape) if lp is not None else None
+        vplan = _grad_plan(value, shape) if need_dvalue else None
+        pplans = [(_grad_plan(params[k], shape) if need_dparams[k] else None) for k in range(np_)]
+        gvd = _plan_desc(vplan, shape) if vplan else None
+        for k in range(np_):
+            if pplans[k] is not None:
+                gdesc[k] = _plan_desc(pplans[k], shape)
+            else:
+                gdesc[k].ptr = None
+                gdesc[k].ndim = nd
+        code = N.lib().b2_site_score(
+            family, ctypes.byref(vd), pdesc, np_, ctypes.byref(md) if md is not None else None,
+            float(scale), ctypes.byref(ud) if ud is not None else None, float(weight),
+            float(sum_coeff), flags, ctypes.byref(lpd) if lpd is not None else None,
+            out_sum.data_ptr() if out_sum is not None else None,
+            ctypes.byref(gvd) if gvd is not None else None, gdesc, ws.data_ptr(), ws.numel(),
+            N.stream_ptr(dev))
+        N.check(code, "b2_site_score")
+        outs = _finish_plans([vplan] + pplans)
+        return lp, outs[0], outs[1:]
+
+    # ---- event families: gradients are produced full shape, then reduced if the operand was
+    # batch-broadcast --------------------------------------------------------------------------------
+    ev_dims = {N.DIRICHLET: (1, [1]), N.CATEGORICAL: (0, [1]), N.MVN_TRIL: (1, [1, 2])}[family]
+    v_ev, p_ev = ev_dims
+    vd = ev_desc(value, v_ev)
+    for k in range(np_):
+        pdesc[k] = ev_desc(params[k], p_ev[k])
+    md = ev_desc(mask, 0) if mask is not None else None
+    ud = ev_desc(upstream, 0) if upstream is not None else None
+    lpd = ev_desc(lp, 0) if lp is not None else None
+
+    def full_grad(t, ev_ndim):
+        full = tuple(bshape) + tuple(t.shape[t.dim() - ev_ndim:]) if ev_ndim else tuple(bshape)
+        return torch.empty(full, dtype=ref.dtype, device=dev), full
+
+    gv_full = None
+    if need_dvalue:
+        gv_full, _ = full_grad(value, v_ev)
+        gvd = ev_desc(gv_full, v_ev)
+    else:
+        gvd = None
+    gp_full = [None] * np_
+    for k in range(np_):
+        if need_dparams[k]:
+            gp_full[k], _ = full_grad(params[k], p_ev[k])
+            gdesc[k] = ev_desc(gp_full[k], p_ev[k])
+        else:
+            gdesc[k].ptr = None
+            gdesc[k].ndim = len(bshape)
+    code = N.lib().b2_event_score(
+        family, ctypes.byref(vd), pdesc, np_, int(event_size),
+        ctypes.byref(md) if md is not None else None, float(scale),
+        ctypes.byref(ud) if ud is not None else None, float(weight), float(sum_coeff), flags,
+        ctypes.byref(lpd) if lpd is not None else None,
+        out_sum.data_ptr() if out_sum is not None else None,
+        ctypes.byref(gvd) if gvd is not None else None, gdesc, ws.data_ptr(), ws.numel(),
+        N.stream_ptr(dev))
+    N.check(code, "b2_event_score")
+
+    def back_to_stored(gfull, t):
+        if gfull is None:
+            return None
+        if tuple(gfull.shape) == tuple(t.shape):
+            return gfull
+        out = torch.empty(t.shape, dtype=gfull.dtype, device=dev)
+        reduce_to(gfull, out)
+        return out
+
+    return lp, back_to_stored(gv_full, value), [back_to_stored(gp_full[k], params[k]) for k in range(np_)]
+
+
+def _empty_site(value, params, shape, want_logprob, out_sum, accumulate, need_dvalue, need_dparams):
+    """A site with zero elements: log_prob is empty, its sum and every gradient are zero."""
+    ref = params[0]
+    lp = torch.empty(shape, dtype=ref.dtype, device=ref.device) if want_logprob else None
+    if out_sum is not None and not accumulate:
+        out_sum.zero_()
+    gv = torch.zeros_like(value) if need_dvalue else None
+    need_dparams = need_dparams or [False] * len(params)
+    gp = [torch.zeros_like(p) if need_dparams[k] else None for k, p in enumerate(params)]
+    return lp, gv, gp
+
+
+class _LogProbFn(torch.autograd.Function):
+    """Materialised log_prob with a fused backward."""
+
+    @staticmethod
+    def forward(ctx, meta, value, *params):
+        family, shape, event_size, value_is_float = meta
+        ctx.meta = meta
+        lp, _, _ = site_score(family, value, list(params), shape, want_logprob=True,
+                              event_size=event_size)
+        ctx.save_for_backward(value, *params)
+        return lp
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        family, shape, event_size, value_is_float = ctx.meta
+        value, *params = ctx.saved_tensors
+        need_v = ctx.needs_input_grad[1] and value_is_float
+        need_p = list(ctx.needs_input_grad[2:])
+        gout = gout.contiguous() if not gout.is_contiguous() and gout.numel() > 0 else gout
+        _, gv, gp = site_score(family, value, params, shape, upstream=gout, need_dvalue=need_v,
+                               need_dparams=need_p, event_size=event_size)
+        return (None, gv) + tuple(gp)
+
+
+def log_prob_op(family, value, params, batch_shape, event_size=None):
+    if event_size is None:
+        shape = _common_shape(value, params, batch_shape)
+        value_is_float = value is not None and value.is_floating_point()
+    else:
+        shape = torch.Size(batch_shape)
+        value_is_float = value.is_floating_point()
+    meta = (family, tuple(shape), event_size, value_is_float)
+    return _LogProbFn.apply(meta, value, *params)
+
+
+class _FusedSiteSumFn(torch.autograd.Function):
+    """sum(scale*mask*log_prob) with the FINAL gradients computed in the same pass.
+
+    With ``unit`` set the upstream gradient reaching this node is taken to be exactly 1 (the
+    caller has folded its coefficient into ``weight``; pyro_b200's ELBOs and potentials guarantee
+    it).  Otherwise the stored gradients are multiplied by the upstream scalar.
+    """
+
+    @staticmethod
+    def forward(ctx, meta, value, *params):
+        (family, shape, event_size, mask, scale, weight, sum_coeff, out_sum, accumulate, vfloat,
+         unit) = meta
+        ctx.unit = unit
+        need_v = vfloat and value is not None and value.requires_grad
+        need_p = [p.requires_grad for p in params]
+        dev = params[0].device
+        res = out_sum if out_sum is not None else torch.empty((), dtype=params[0].dtype, device=dev)
+        _, gv, gp = site_score(family, value, list(params), shape, mask=mask, scale=scale,
+                               weight=weight, sum_coeff=sum_coeff, accumulate=accumulate,
+                               out_sum=res, need_dvalue=need_v, need_dparams=need_p,
+                               event_size=event_size)
+        ctx.grads = (gv, gp)
+        return res
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        gv, gp = ctx.grads
+        if not ctx.unit:
+            # general autograd use: honour the upstream scalar (one small extra multiply)
+            gv = gv * gout if gv is not None else None
+            gp = [g * gout if g is not None else None for g in gp]
+        return (None, gv) + tuple(gp)
+
+
+def fused_site_sum(family, value, params, batch_shape, *, mask=None, scale=1.0, weight=1.0,
+                   sum_coeff=1.0, event_size=None, assume_unit_upstream=True):
+    """0-d tensor ``sum_coeff * sum(scale*mask*log_prob)`` whose backward delivers
+    ``weight * d(sum)/d(operand)`` for every operand requiring grad (assuming upstream == 1)."""
+    if event_size is None:
+        shape = _common_shape(value, params, batch_shape)
+        vfloat = value is not None and value.is_floating_point()
+    else:
+        shape = torch.Size(batch_shape)
+        vfloat = value.is_floating_point()
+    if mask is not None and mask.dtype != torch.bool:
+        mask = mask.bool()
+    meta = (family, tuple(shape), event_size, mask, float(scale), float(weight), float(sum_coeff),
+            None, False, vfloat, bool(assume_unit_upstream))
+    return _FusedSiteSumFn.apply(meta, value, *params)

@@ -1,0 +1,6 @@
+"""Inference algorithms on the fused kernels: SVI + Trace_ELBO / TraceMeanField_ELBO, MCMC + NUTS / HMC."""
+from .elbo import ELBO  # noqa: F401
+from .svi import SVI  # noqa: F401
+from .trace_elbo import JitTrace_ELBO, Trace_ELBO  # noqa: F401
+from .trace_mean_field_elbo import TraceMeanField_ELBO  # noqa: F401
+from .mcmc import HMC, MCMC, NUTS  # noqa: F401

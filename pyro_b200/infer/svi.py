@@ -1,0 +1,145 @@
+"""SVI driver (mirror of pyro/infer/svi.py:38-162).
+
+``step`` = capture the parameters touched by the loss, ``loss_and_grads``, one fused optimiser
+call; gradients are zeroed inside the optimiser kernel.  With a loss whose ``capture_graph`` is
+true (``JitTrace_ELBO``) the whole step is captured into a CUDA graph on the second call and
+replayed afterwards, so the per-step host cost is one graph launch plus one 4-byte read-back.
+"""
+import warnings
+
+import torch
+
+from .. import poutine
+from ..util import torch_item, warn_if_nan
+from .elbo import ELBO
+
+
+class SVI:
+    def __init__(self, model, guide, optim, loss, loss_and_grads=None, num_samples=0, num_steps=0,
+                 **kwargs):
+        if num_steps:
+            warnings.warn("The `num_steps` argument to SVI is deprecated", FutureWarning)
+        self.model = model
+        self.guide = guide
+        self.optim = optim
+        self.num_steps = num_steps
+        self.num_samples = num_samples
+        self._loss_obj = loss
+        if isinstance(loss, ELBO):
+            self.loss = loss.loss
+            self.loss_and_grads = loss.loss_and_grads
+            self._loss_and_grads_tensor = getattr(loss, "loss_and_grads_tensor", None)
+        else:
+            if loss_and_grads is None:
+                def _loss_and_grads(model, guide, *args, **kwargs):
+                    loss_val = loss(model, guide, *args, **kwargs)
+                    if getattr(loss_val, "requires_grad", False):
+                        loss_val.backward(retain_graph=True)
+                    return loss_val
+                loss_and_grads = _loss_and_grads
+            self.loss = loss
+            self.loss_and_grads = loss_and_grads
+            self._loss_and_grads_tensor = None
+        self._capture = bool(getattr(loss, "capture_graph", False))
+        self._graph = None
+        self._graph_state = None
+        self._steps_done = 0
+
+    # ---- evaluation ---------------------------------------------------------------------------------
+    def evaluate_loss(self, *args, **kwargs):
+        with torch.no_grad():
+            loss = self.loss(self.model, self.guide, *args, **kwargs)
+            return loss if isinstance(loss, float) else torch_item(loss)
+
+    # ---- one eager step -----------------------------------------------------------------------------
+    def _eager_step(self, args, kwargs, want_tensor=False):
+        with poutine.trace(param_only=True) as param_capture:
+            if want_tensor and self._loss_and_grads_tensor is not None:
+                loss = self._loss_and_grads_tensor(self.model, self.guide, *args, **kwargs)
+            else:
+                loss = self.loss_and_grads(self.model, self.guide, *args, **kwargs)
+        params = []
+        seen = set()
+        for site in param_capture.trace.nodes.values():
+            if site["type"] != "param":
+                continue
+            v = site["value"]
+            u = getattr(v, "_pyro_unconstrained_param", None)
+            if u is None:
+                u = v.unconstrained() if hasattr(v, "unconstrained") else v
+            if id(u) not in seen:
+                seen.add(id(u))
+                params.append(u)
+        self.optim(params)  # fused update; zeroes the gradients in the same pass
+        return loss
+
+    def step(self, *args, **kwargs):
+        """One gradient step; returns the loss estimate as a python float."""
+        if self._capture and self._steps_done >= 1:
+            loss = self._captured_step(args, kwargs)
+        else:
+            loss = self._eager_step(args, kwargs)
+        self._steps_done += 1
+        if isinstance(loss, torch.Tensor):
+            loss = torch_item(loss)
+        warn_if_nan(loss, "loss")
+        return loss
+
+    def step_async(self, *args, **kwargs):
+        """Like ``step`` but returns the loss as a 0-d device tensor without synchronising."""
+        if self._capture and self._steps_done >= 1:
+            loss = self._captured_step(args, kwargs)
+        else:
+            loss = self._eager_step(args, kwargs, want_tensor=True)
+        self._steps_done += 1
+        return loss
+
+    # ---- CUDA-graph captured step ------------------------------------------------------------------
+    def _captured_step(self, args, kwargs):
+        if kwargs:
+            raise ValueError("graph-captured SVI steps take tensor positional arguments only")
+        if self._graph is None:
+            self._capture_graph(args)
+        st = self._graph_state
+        if len(args) != len(st["static_args"]):
+            raise ValueError("graph-captured SVI step called with a different number of arguments")
+        for a, s in zip(args, st["static_args"]):
+            if isinstance(a, torch.Tensor):
+                if a.shape != s.shape or a.dtype != s.dtype:
+                    raise ValueError("graph-captured SVI step called with different argument shapes")
+                if a.data_ptr() != s.data_ptr():
+                    s.copy_(a, non_blocking=True)
+            elif a != s:
+                raise ValueError("non-tensor argument of a graph-captured SVI step changed")
+        self._graph.replay()
+        return st["loss"]
+
+    def _capture_graph(self, args):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+        if dev is None:
+            raise RuntimeError("graph capture needs CUDA tensor arguments")
+        static_args = []
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                static_args.append(a if a.is_cuda else a.to(dev))
+            else:
+                static_args.append(a)
+        if self._loss_and_grads_tensor is None:
+            raise RuntimeError("this loss cannot be captured (no loss_and_grads_tensor)")
+        # one more eager step on a side stream so every lazily created buffer exists
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._eager_step(tuple(static_args), {}, want_tensor=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self._eager_step(tuple(static_args), {}, want_tensor=True)
+            loss = loss.reshape(()) if isinstance(loss, torch.Tensor) else torch.as_tensor(loss, device=dev)
+        self._graph = graph
+        self._graph_state = {"static_args": static_args, "loss": loss}
+        self._steps_done += 1  # the warm-up step above was a real optimisation step
