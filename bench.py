@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of BASELINE.json measured on B200.
+
+Workload (config 2 of BASELINE.json, the one the metric is quoted on):
+  Bayesian logistic regression, synthetic X[1e6, 32] fp32, 64 vectorised particles, Trace_ELBO,
+  ClippedAdam(lr 0.01), through the public API ``SVI.step``.  One "step" = one full SVI step
+  (guide sampling, model, fused scoring, backward, fused optimiser, loss read-back).
+
+    python bench.py --gpus N --steps K --warmup W          # our arm  (torchrun for N > 1)
+    python bench.py --impl reference ...                   # reference CPU arm (oracle port)
+
+One JSON line on stdout (rank 0).  Keys follow the driver contract; extra keys:
+  roofline      dominant kernel of the measured path: algorithmic bytes per launch / its average
+                duration (CUDA events on the launching stream) vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference's CPU path timed on this box's host cores
+  variants      the other execution paths of the same workload (generic per-site kernels / fused
+                GLM kernel, eager / CUDA-graph) with their own step time and kernel roofline
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+N_ROWS, D_FEAT, PARTICLES = 1_000_000, 32, 64
+METRIC = "svi_steps_per_sec"
+UNIT = "steps/s"
+WORKLOAD = "bayesian_logistic_regression_svi N=1e6 D=32 Trace_ELBO P=64 ClippedAdam"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_data(device, dtype=torch.float32, n=N_ROWS, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randn(n, D_FEAT, generator=g, dtype=dtype)
+    w_true = torch.randn(D_FEAT, generator=g, dtype=dtype) / D_FEAT ** 0.5
+    y = torch.bernoulli(torch.sigmoid(X @ w_true + 0.5), generator=g)
+    return X.to(device), y.to(device)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_svi(path, particles, lr=0.01):
+    import models
+    import pyro_b200 as pyro
+    from pyro_b200.infer import SVI, JitTrace_ELBO, Trace_ELBO
+    from pyro_b200.optim import ClippedAdam
+    pyro.clear_param_store()
+    model = models.logistic_model_fused if "glm" in path else models.logistic_model
+    elbo_cls = JitTrace_ELBO if "graph" in path else Trace_ELBO
+    return SVI(model, models.logistic_guide, ClippedAdam({"lr": lr}),
+               elbo_cls(num_particles=particles, vectorize_particles=True, max_plate_nesting=1))
+
+
+def time_steps(svi, args, steps, warmup, device, flush, sync_each=True):
+    """Per-step CUDA-event timing on the current stream; the L2 is flushed (256 MB write) between
+    steps, outside the timed interval.  Returns (list of ms per step, last loss)."""
+    for _ in range(warmup):
+        loss = svi.step(*args)
+    torch.cuda.synchronize(device)
+    ms = []
+    for _ in range(steps):
+        if flush is not None:
+            flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = svi.step(*args)
+        e1.record()
+        e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return ms, loss
+
+
+def kernel_time_ms(fn, iters, flush):
+    """Average device time of one launch sequence ``fn`` (CUDA events on the launching stream)."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def roofline_for(path, X, y, particles, flush):
+    """Dominant kernel of the path, timed alone on its own inputs."""
+    import pyro_b200.distributions as dist
+    peak, how = peaks()
+    dev = X.device
+    P, n = particles, X.shape[0]
+    if "glm" in path:
+        w = (0.1 * torch.randn(P, 1, D_FEAT, device=dev)).requires_grad_(True)
+        b = torch.zeros(P, 1, device=dev, requires_grad=True)
+
+        def fn():
+            dist.Bernoulli(logits=dist.linear_predictor(X, w, b))._fused_sum(y, None, 1.0, -1.0 / P, 1.0, True)
+        ms = kernel_time_ms(fn, 20, flush)
+        alg = n * D_FEAT * 4 + n * 4  # X and y once, for value AND gradient
+        name = "glm_bernoulli_kernel<32> (+2 finish kernels)"
+    else:
+        logits = torch.randn(P, n, device=dev).requires_grad_(True)
+
+        def fn():
+            dist.Bernoulli(logits=logits)._fused_sum(y, None, 1.0, -1.0 / P, 1.0, True)
+        ms = kernel_time_ms(fn, 20, flush)
+        alg = P * n * 4 + n * 4 + P * n * 4  # read logits + y, write d/dlogits (full shape)
+        name = "site_vec_kernel<BernoulliLogits,float,GRAD>"
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": name, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(ach / peak, 4), "traffic": None, "ms_per_launch": round(ms, 4),
+            "algorithmic_bytes": alg, "peak_source": how}
+
+
+def cpu_reference(steps, warmup, threads=None, n=N_ROWS):
+    """The reference's CPU path for this workload: oracle port (oracle/svi.py, pinned against
+    reference Pyro's own trajectory in tests/test_oracle_golden.py), all host threads."""
+    from oracle import svi as osvi
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    X, y = make_data("cpu", n=n)
+    m = osvi.LogisticSVIMatmul(D_FEAT, PARTICLES, lr=0.01)
+    for _ in range(warmup):
+        m.step(X, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = m.step(X, y)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3, threads, loss
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--path", default="glm+graph",
+                    help="ours: site | site+graph | glm | glm+graph (default)")
+    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(a.steps, 20)
+        v, ms, threads, loss = cpu_reference(steps, min(a.warmup, 2))
+        out = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": a.gpus,
+               "steps": steps, "warmup": min(a.warmup, 2), "ms_per_step": round(ms, 3),
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": {"workload": WORKLOAD, "global_particles": PARTICLES},
+               "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%d full-size steps (N=1e6) of oracle/svi.py LogisticSVIMatmul" % steps},
+               "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from pyro_b200 import _native
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    _native.lib()
+    torch.manual_seed(1234 + rank)
+    P_local = PARTICLES // world
+    X, y = make_data(dev)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+    path = a.path if world == 1 else a.path.replace("+graph", "")  # NCCL stays outside graphs
+
+    # launches per step, counted on an eager twin of the path (a graph replay re-issues exactly the
+    # launches captured from one eager step)
+    probe = build_svi(path.replace("+graph", ""), P_local)
+    probe.step(X, y)
+    n0 = _native.launch_count()
+    probe.step(X, y)
+    per_step_launches = _native.launch_count() - n0
+    del probe
+    svi = build_svi(path, P_local)
+
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        sampler.start()
+    ms, loss = time_steps(svi, (X, y), a.steps, a.warmup + 2, dev, flush)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    value = a.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host (pinned) inputs copied every step through the same public call --------------------
+    Xh = X.cpu().pin_memory()
+    yh = y.cpu().pin_memory()
+    Xs, ys = torch.empty_like(X), torch.empty_like(y)
+
+    def e2e_step():
+        Xs.copy_(Xh, non_blocking=True)
+        ys.copy_(yh, non_blocking=True)
+        return svi.step(Xs, ys)
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_n = max(5, min(a.steps, 20))
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_n):
+        e2e_step()
+    e1.record()
+    e1.synchronize()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = e2e_n / (float(e2e_ms) * 1e-3)
+    h2d = Xh.numel() * 4 + yh.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+           "warmup": a.warmup + 2, "ms_per_step": round(total_ms / a.steps, 4), "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "global_particles": PARTICLES,
+                      "parallelism": "particles sharded over %d rank(s), 1 all-reduce/step" % world,
+                      "path": path, "l2": "256 MB flush write between timed steps (outside the timed interval); "
+                                          "inputs 132 MB > 126 MB L2",
+                      "timing": "per-step CUDA events on the launching stream, summed; max over ranks"},
+           "final_loss": round(float(loss), 3),
+           "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "note": "SVI.step on pinned host X,y copied to the device inside the timed region every step"},
+           "gpu_launches": int(per_step_launches * a.steps), "gpu_launches_per_step": int(per_step_launches),
+           "clocks": clocks}
+    if world == 1:
+        out["roofline"] = roofline_for(path, X, y, P_local, flush)
+        if not a.no_variants:
+            variants = {}
+            for vp in ("site", "site+graph", "glm", "glm+graph"):
+                if vp == path:
+                    continue
+                try:
+                    s2 = build_svi(vp, P_local)
+                    vms, _ = time_steps(s2, (X, y), max(10, a.steps // 3), 5, dev, flush)
+                    variants[vp] = {"ms_per_step": round(sum(vms) / len(vms), 4),
+                                    "steps_per_sec": round(len(vms) / (sum(vms) * 1e-3), 2)}
+                except Exception as e:  # pragma: no cover
+                    variants[vp] = {"error": repr(e)[:200]}
+            for vp in ("site", "glm"):
+                if vp in variants and "error" not in variants[vp]:
+                    variants[vp]["roofline"] = roofline_for(vp, X, y, P_local, flush)
+            out["variants"] = variants
+        v, cms, threads, _ = cpu_reference(a.cpu_steps, 1)
+        out["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": "%d full-size steps (N=1e6, P=64) of oracle/svi.py LogisticSVIMatmul "
+                                         "(CPU restatement of reference SVI.step, torch CPU ops, all host threads)" % a.cpu_steps,
+                               "ms_per_step": round(cms, 2)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,10 +1,12 @@
 """Build the native library in-tree with nvcc for sm_100a.
 
 ``libpyro_b200.so`` (the C-ABI of include/pyro_b200.h; pure CUDA runtime, no torch types) and
-``libpyro_b200_hostcheck.so`` (test-only CPU build of the element functors).  The objects go to
-``build/`` and the shared objects next to this file, so they travel to the GPU box with the
-snapshot (they are git-ignored, not gpurun-ignored).
+``libpyro_b200_hostcheck.so`` (test-only CPU build of the element functors and the NUTS core).
+Objects go to ``build/``; the shared objects sit next to this file, so they travel to the GPU box
+with the snapshot (git-ignored, not gpurun-ignored).  Staleness is decided by a content hash of
+the sources (file times do not survive the snapshot copy), stored next to each library.
 """
+import hashlib
 import os
 import shutil
 import subprocess
@@ -21,8 +23,7 @@ HOSTCHECK = os.path.join(HERE, "libpyro_b200_hostcheck.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                      "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets"]
-# everything but the test harness
-DEVICE_SOURCES_EXCLUDE = {"hostcheck.cu"}
+HOST_ONLY = {"hostcheck.cu"}
 
 
 def _nvcc():
@@ -32,60 +33,75 @@ def _nvcc():
     return exe
 
 
-def _newest_header_mtime():
-    m = 0.0
-    for d in (CSRC, os.path.join(ROOT, "include")):
-        for f in os.listdir(d):
-            if f.endswith((".cuh", ".h")):
-                m = max(m, os.path.getmtime(os.path.join(d, f)))
-    return m
+def _files():
+    hdrs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    hdrs += [os.path.join(ROOT, "include", f) for f in sorted(os.listdir(os.path.join(ROOT, "include")))]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    return hdrs, srcs
 
 
-def _compile(src, obj, extra=()):
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + ["-c", src, "-o", obj]
+def _hash(paths, extra=""):
+    h = hashlib.sha256(extra.encode())
+    for p in paths:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stamp_ok(lib, digest):
+    stamp = lib + ".hash"
+    if not (os.path.exists(lib) and os.path.exists(stamp)):
+        return False
+    with open(stamp) as f:
+        return f.read().strip() == digest
+
+
+def _write_stamp(lib, digest):
+    with open(lib + ".hash", "w") as f:
+        f.write(digest)
+
+
+def _run(cmd, what):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
-    return obj
+        raise RuntimeError("%s failed:\n%s\n%s\n%s" % (what, " ".join(cmd), r.stdout, r.stderr))
 
 
 def build(force=False, verbose=False):
-    os.makedirs(BUILD, exist_ok=True)
-    hdr_m = _newest_header_mtime()
-    sources = sorted(f for f in os.listdir(CSRC)
-                     if f.endswith(".cu") and f not in DEVICE_SOURCES_EXCLUDE)
-    jobs = []
-    objs = []
-    for f in sources:
-        src = os.path.join(CSRC, f)
-        obj = os.path.join(BUILD, f[:-3] + ".o")
-        objs.append(obj)
-        stale = force or not os.path.exists(obj) or \
-            os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m)
-        if stale:
-            jobs.append((src, obj))
-    if jobs:
+    hdrs, srcs = _files()
+    dev_srcs = [s for s in srcs if os.path.basename(s) not in HOST_ONLY]
+    dev_digest = _hash(hdrs + dev_srcs, " ".join(NVCC_FLAGS))
+    if force or not _stamp_ok(LIB, dev_digest):
+        os.makedirs(BUILD, exist_ok=True)
+        hdr_digest = _hash(hdrs, " ".join(NVCC_FLAGS))
+        jobs, objs = [], []
+        for src in dev_srcs:
+            obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
+            objs.append(obj)
+            d = _hash([src], hdr_digest)
+            if force or not _stamp_ok(obj, d):
+                jobs.append((src, obj, d))
         if verbose:
             print("[pyro_b200] compiling %d CUDA sources for sm_100a" % len(jobs), file=sys.stderr)
-        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
-            list(ex.map(lambda so: _compile(*so), jobs))
-    need_link = bool(jobs) or not os.path.exists(LIB) or \
-        any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
-    if need_link:
-        cmd = [_nvcc()] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs + \
-              ["-lcudart", "-Wno-deprecated-gpu-targets"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    # host-only harness (tests)
-    hsrc = os.path.join(CSRC, "hostcheck.cu")
-    if force or not os.path.exists(HOSTCHECK) or \
-            os.path.getmtime(HOSTCHECK) < max(os.path.getmtime(hsrc), hdr_m):
-        cmd = [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
-               "-Wno-deprecated-gpu-targets", hsrc, "-o", HOSTCHECK]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("hostcheck build failed:\n%s\n%s" % (r.stdout, r.stderr))
+
+        def one(job):
+            src, obj, d = job
+            _run([_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj], "nvcc " + os.path.basename(src))
+            _write_stamp(obj, d)
+
+        if jobs:
+            with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+                list(ex.map(one, jobs))
+        _run([_nvcc()] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
+                                  "-o", LIB] + objs + ["-lcudart"], "link libpyro_b200.so")
+        _write_stamp(LIB, dev_digest)
+    host_srcs = [s for s in srcs if os.path.basename(s) in HOST_ONLY]
+    host_digest = _hash(hdrs + host_srcs, "hostcheck")
+    if force or not _stamp_ok(HOSTCHECK, host_digest):
+        _run([_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+              "-Wno-deprecated-gpu-targets"] + host_srcs + ["-o", HOSTCHECK], "hostcheck build")
+        _write_stamp(HOSTCHECK, host_digest)
     return LIB
 
 

@@ -141,6 +141,11 @@ def desc(t, shape=None):
     return d
 
 
+def capturing():
+    """True while the current stream is being captured into a CUDA graph."""
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 def stream_ptr(device=None):
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -159,7 +164,7 @@ def workspace(device, nbytes=None, tag="reduce"):
     key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
-        if torch.cuda.is_current_stream_capturing():
+        if capturing():
             raise RuntimeError("pyro_b200: workspace must be allocated before CUDA graph capture; "
                                "run one eager step first")
         ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)

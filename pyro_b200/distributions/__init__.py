@@ -768,3 +768,115 @@ __all__ = ["Distribution", "Normal", "Bernoulli", "Gamma", "Beta", "Poisson", "C
            "HalfNormal", "LogNormal", "Exponential", "Uniform", "Dirichlet", "Categorical",
            "MultivariateNormal", "Delta", "Independent", "MaskedDistribution", "ScoreParts",
            "kl_divergence", "scale_and_mask", "is_identically_zero", "is_identically_one"]
+
+
+# ---------------------------------------------------------------------------------------------
+# fused generalised-linear likelihood (BASELINE config 2): Bernoulli(logits = X w + b)
+# ---------------------------------------------------------------------------------------------
+class LinearPredictor:
+    """Lazy ``X @ w^T + b`` for P weight vectors: behaves like a ``[P, N]`` (or ``[N]``) logits
+    tensor when handed to ``Bernoulli(logits=...)``, but lets the site be scored by ONE kernel
+    that reads X and y once and emits sum, dW and db (``b2_glm_bernoulli_logits``) instead of
+    materialising the [P, N] logits, log_prob and gradient tensors.
+
+    ``w``: [D], [P, D] or [P, 1, D] (vectorised particles);  ``b``: None, [], [P] or [P, 1]."""
+
+    def __init__(self, X, w, b=None):
+        self.X, self.w, self.b = X, w, b
+        D = X.shape[-1]
+        self.vectorised = w.dim() > 1
+        self.P = w.numel() // D
+        self.shape = torch.Size((self.P, X.shape[0])) if self.vectorised else torch.Size((X.shape[0],))
+        self.dtype, self.device = X.dtype, X.device
+
+    def dense(self):
+        W = self.w.reshape(self.P, -1)
+        out = W @ self.X.t()
+        if self.b is not None:
+            out = out + self.b.reshape(self.P, 1)
+        return out if self.vectorised else out.squeeze(0)
+
+
+def linear_predictor(X, w, b=None):
+    return LinearPredictor(X, w, b)
+
+
+class _GlmBernoulliFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, meta, X, y, W, b):
+        import ctypes
+        scale, weight, coeff, unit = meta
+        N.require_cuda(X, "fused GLM likelihood")
+        P, D = W.shape
+        n = X.shape[0]
+        dev = X.device
+        Wc = W.contiguous()
+        bc = b.contiguous() if b is not None else None
+        total = torch.empty((), dtype=torch.float32, device=dev)
+        dW = torch.empty(P, D, dtype=torch.float32, device=dev)
+        db = torch.empty(P, dtype=torch.float32, device=dev)
+        need = int(N.lib().b2_glm_workspace(n, D, P))
+        ws = N.workspace(dev, need, tag="glm")
+        N.check(N.lib().b2_glm_bernoulli_logits(
+            X.data_ptr(), y.data_ptr(), Wc.data_ptr(), bc.data_ptr() if bc is not None else None,
+            n, D, P, float(scale), float(weight), float(coeff), 0, None, total.data_ptr(),
+            dW.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), N.stream_ptr(dev)),
+            "b2_glm_bernoulli_logits")
+        ctx.grads = (dW, db if b is not None else None)
+        ctx.unit = unit
+        return total
+
+    @staticmethod
+    def backward(ctx, gout):
+        dW, db = ctx.grads
+        if not ctx.unit:
+            dW = dW * gout
+            db = db * gout if db is not None else None
+        return None, None, None, dW, db
+
+
+class _BernoulliLinear(Bernoulli):
+    """Bernoulli whose logits are a LinearPredictor (built by ``Bernoulli(logits=lazy)``)."""
+
+    def __init__(self, probs=None, logits=None, validate_args=None):
+        lazy = logits
+        self._lazy = lazy
+        self.family = N.BERNOULLI_LOGITS
+        self.param_names = ("logits",)
+        self._dense = None
+        Distribution.__init__(self, lazy.shape)
+
+    @property
+    def _params(self):
+        if self._dense is None:
+            self._dense = self._lazy.dense()
+        return [self._dense]
+
+    @property
+    def logits(self):
+        return self._params[0]
+
+    def _fused_sum(self, value, mask, scale, weight, sum_coeff, unit=True):
+        lz = self._lazy
+        X = lz.X
+        D = X.shape[-1]
+        ok = (mask is None and X.dtype == torch.float32 and X.is_contiguous() and D in (4, 8, 16, 32)
+              and isinstance(value, torch.Tensor) and value.numel() == X.shape[0]
+              and tuple(self.batch_shape) == tuple(lz.shape) and X.data_ptr() % 16 == 0)
+        if not ok:
+            return super()._fused_sum(value, mask, scale, weight, sum_coeff, unit)
+        y = value.reshape(-1).to(torch.float32).contiguous()
+        W = lz.w.reshape(lz.P, D)
+        b = lz.b.reshape(lz.P) if lz.b is not None else None
+        return _GlmBernoulliFn.apply((scale, weight, sum_coeff, unit), X, y, W, b)
+
+
+def _bernoulli_new(cls, probs=None, logits=None, validate_args=None):
+    # ``Bernoulli(logits=LinearPredictor)`` builds the fused-GLM subclass
+    if cls is Bernoulli and isinstance(logits, LinearPredictor):
+        return object.__new__(_BernoulliLinear)
+    return object.__new__(cls)
+
+
+Bernoulli.__new__ = staticmethod(_bernoulli_new)
+__all__ += ["LinearPredictor", "linear_predictor"]

@@ -105,8 +105,7 @@ class HMC:
             pot.C = num_chains
         self.D = pot.dim
         dev, dtype = pot.device, pot.dtype
-        if dev.type != "cuda":
-            raise RuntimeError("pyro_b200 MCMC kernels need the model/potential on a CUDA device")
+        N.require_cuda(torch.empty(0, device=dev), "MCMC kernels (model / potential data)")
         self._gen = torch.Generator(device=dev)
         self._gen.manual_seed(int(seed))
         self._seed = int(seed)

@@ -124,9 +124,15 @@ class TracePotential:
         proto = poutine.trace(model).get_trace(*self.args, **self.kwargs)
         proto = poutine.prune_subsample_sites(proto)
         if max_plate_nesting is None:
+            # batch dims may be used without a plate (eight_schools does): reserve every batch dim
+            # any site uses, so the chain dim sits to the left of all of them
             dims = [f.dim for s in proto.nodes.values() if s["type"] == "sample"
                     for f in s["cond_indep_stack"] if f.vectorized]
-            max_plate_nesting = -min(dims) if dims else 0
+            nest = -min(dims) if dims else 0
+            for s in proto.nodes.values():
+                if s["type"] == "sample":
+                    nest = max(nest, len(getattr(s["fn"], "batch_shape", ())))
+            max_plate_nesting = nest
         self.max_plate_nesting = max_plate_nesting
         self.chain_dim = -(max_plate_nesting + 1)
         self.sites = {}

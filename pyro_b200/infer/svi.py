@@ -70,15 +70,38 @@ class SVI:
             if id(u) not in seen:
                 seen.add(id(u))
                 params.append(u)
+        loss = self._allreduce(params, loss)
         self.optim(params)  # fused update; zeroes the gradients in the same pass
         return loss
+
+    def _allreduce(self, params, loss):
+        """Particle-sharded data parallelism: every rank holds P/W particles, so the ELBO estimate
+        and its gradient are the mean over ranks.  ONE all-reduce per step over a packed buffer
+        [loss, grad_1 .. grad_n] (the reference's only analogue is the per-parameter
+        Horovod all-reduce of pyro/optim/horovod.py:41-45 + examples/svi_horovod.py:134); the
+        replicated fused optimiser then keeps the parameters identical on every rank."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return loss
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads or not isinstance(loss, torch.Tensor):
+            return loss
+        flat = torch.cat([loss.detach().reshape(1).to(grads[0].dtype)] + [g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= dist.get_world_size()
+        off = 1
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].reshape(g.shape))
+            off += n
+        return flat[0]
 
     def step(self, *args, **kwargs):
         """One gradient step; returns the loss estimate as a python float."""
         if self._capture and self._steps_done >= 1:
             loss = self._captured_step(args, kwargs)
         else:
-            loss = self._eager_step(args, kwargs)
+            loss = self._eager_step(args, kwargs, want_tensor=True)
         self._steps_done += 1
         if isinstance(loss, torch.Tensor):
             loss = torch_item(loss)

@@ -90,7 +90,7 @@ class PyroOptim:
         table = self._tables.get(dtype)
         if table is not None and table["key"] == key:
             return table
-        if torch.cuda.is_current_stream_capturing():
+        if N.capturing():
             raise RuntimeError("pyro_b200.optim: parameter set changed during CUDA graph capture")
         if table is not None:
             self._sync_to_host(table)

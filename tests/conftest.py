@@ -16,8 +16,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+# B2_TEST_EMULATE=1 runs the gpu-marked tests on the CPU with the native seams replaced by the
+# oracle-backed stand-ins of tests/cpu_emulation.py.  It exists to debug the TEST CODE in the
+# GPU-less build container; it proves nothing about the kernels and is never set by the driver.
+EMULATE = os.environ.get("B2_TEST_EMULATE") == "1"
+
+
+def device():
+    return "cpu" if EMULATE else "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _maybe_emulate(request):
+    if EMULATE and "gpu" in request.keywords:
+        import cpu_emulation
+        with cpu_emulation.enabled():
+            yield
+    else:
+        yield
+
+
 def pytest_collection_modifyitems(config, items):
-    if torch.cuda.is_available():
+    if torch.cuda.is_available() or EMULATE:
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

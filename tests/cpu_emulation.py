@@ -1,0 +1,143 @@
+"""TEST INFRASTRUCTURE ONLY: stand-ins for the native entry points, built on the oracle, so the
+HOST logic of pyro_b200 (effect handlers, plates/broadcasting, ELBO assembly, optimiser
+bookkeeping, the lockstep NUTS driver, chain sharding) can be exercised by the CPU test tier
+(`-m "not gpu"`), which has no GPU.  Activated explicitly by the ``cpu_emulation`` fixture; the
+product never imports this module, and the `-m gpu` tier runs the same scenarios through the real
+kernels.
+"""
+import contextlib
+
+import torch
+
+from oracle import dists as odists
+from oracle import mcmc as omcmc
+from oracle import optim as ooptim
+
+
+def _site_score(family, value, params, shape, *, mask=None, scale=1.0, upstream=None, weight=1.0,
+                sum_coeff=1.0, accumulate=False, want_logprob=False, out_sum=None,
+                need_dvalue=False, need_dparams=None, event_size=None):
+    need_dparams = need_dparams or [False] * len(params)
+    with torch.enable_grad():
+        ps = [p.detach().requires_grad_(True) for p in params]
+        v = value
+        if value is not None and value.is_floating_point():
+            v = value.detach().requires_grad_(True)
+        if event_size is None:
+            fn, _ = odists.ELEMENTWISE[family]
+            lp = fn(v, *ps)
+            lp = lp.expand(shape) if tuple(lp.shape) != tuple(shape) else lp
+        else:
+            lp = odists.EVENT[family](v, *ps)
+            lp = lp.expand(shape) if tuple(lp.shape) != tuple(shape) else lp
+        slp = odists.scale_and_mask(lp, scale, mask)
+        total = slp.sum()
+        wanted = ([v] if need_dvalue else []) + [p for p, n in zip(ps, need_dparams) if n]
+        grads = []
+        if wanted:
+            obj = (slp * upstream).sum() if upstream is not None else total
+            grads = list(torch.autograd.grad(weight * obj, wanted, allow_unused=True))
+            grads = [torch.zeros_like(w) if g is None else g for g, w in zip(grads, wanted)]
+    if out_sum is not None:
+        val = (sum_coeff * total.detach()).to(out_sum.dtype)
+        if accumulate:
+            out_sum.add_(val)
+        else:
+            out_sum.copy_(val)
+    gv = grads.pop(0).detach() if need_dvalue else None
+    gp = [(grads.pop(0).detach() if n else None) for n in need_dparams]
+    return (slp.detach().clone() if want_logprob else None), gv, gp
+
+
+def _adam_launch(self, t):
+    for p in t["params"]:
+        h = self._host[p]
+        a = h["args"]
+        o = ooptim.ClippedAdam(lr=h["lr"], betas=tuple(a["betas"]), eps=a["eps"],
+                               weight_decay=a["weight_decay"], clip_norm=a["clip_norm"], lrd=a["lrd"])
+        o.step_count, o.exp_avg, o.exp_avg_sq = h["step"], h["exp_avg"], h["exp_avg_sq"]
+        with torch.no_grad():
+            o.step(p.data, p.grad)
+            p.grad.zero_()
+        h["step"], h["lr"] = o.step_count, o.lr
+    # keep the device-table mirror in sync with what the real kernel would have written
+    t["lrs"] = torch.tensor([self._host[p]["lr"] for p in t["params"]], dtype=torch.float64)
+    t["steps"] = torch.tensor([self._host[p]["step"] for p in t["params"]], dtype=torch.int32)
+
+
+def _agr_launch(self, t):
+    for p in t["params"]:
+        h = self._host[p]
+        a = h["args"]
+        o = ooptim.AdagradRMSProp(eta=a["eta"], delta=a["delta"], t=a["t"])
+        o.step_count = h["step"]
+        o.sum = h["sum"] if h["step"] > 0 else None
+        with torch.no_grad():
+            o.step(p.data, p.grad)
+            p.grad.zero_()
+        h["sum"].copy_(o.sum)
+        h["step"] = o.step_count
+    t["steps"] = torch.tensor([self._host[p]["step"] for p in t["params"]], dtype=torch.int32)
+
+
+def _native_value_and_grad(self, z, active=None):
+    from pyro_b200 import _native as N
+    if self.model_id == N.MODEL_HIER_NORMAL:
+        U = omcmc.eight_schools_potential(self._keep[0], self._keep[1], self._model.hyper[0], self._model.hyper[1])
+    else:
+        U = omcmc.logistic_potential(self._keep[0], self._keep[1], self._model.hyper[0])
+    Us, gs = [], []
+    for zc in z:
+        g, u = omcmc.potential_grad(U, zc)
+        Us.append(u)
+        gs.append(g)
+    return torch.stack(Us), torch.stack(gs)
+
+
+def _leapfrog(self, z, r, g, eps, minv, active=None):
+    a = torch.ones(z.shape[0], dtype=torch.bool) if active is None else active.bool()
+    e = eps[:, None]
+    am = a[:, None]
+    r.copy_(torch.where(am, r + 0.5 * e * (-g), r))
+    z.copy_(torch.where(am, z + e * (minv * r), z))
+    U, g_new = self.potential.value_and_grad(z, active)
+    r.copy_(torch.where(am, r + 0.5 * e * (-g_new), r))
+    ke = 0.5 * (minv * r * r).sum(-1)
+    self.num_leapfrogs += z.shape[0]
+    return z, r, g_new, U, ke
+
+
+def _reduce_to(src, dst):
+    nd = src.dim()
+    view = dst.reshape((1,) * (nd - dst.dim()) + tuple(dst.shape))
+    view.copy_(src.sum_to_size(view.shape))
+
+
+@contextlib.contextmanager
+def enabled():
+    """Patch the native seams with oracle-backed CPU stand-ins."""
+    import pyro_b200._native as N
+    import pyro_b200.distributions._ops as ops
+    import pyro_b200.infer.mcmc.nuts as nuts
+    import pyro_b200.infer.mcmc.potential as pot
+    import pyro_b200.optim as optim
+    import pyro_b200.distributions as pdist
+    saved_glm = pdist._BernoulliLinear._fused_sum
+    # the fused GLM kernel has no CPU stand-in: route the site through the dense Bernoulli path
+    pdist._BernoulliLinear._fused_sum = lambda self, value, mask, scale, weight, sum_coeff, unit=True: \
+        pdist.Bernoulli._fused_sum(self, value, mask, scale, weight, sum_coeff, unit)
+    saved = (ops.site_score, N.require_cuda, optim.ClippedAdam._launch, optim.AdagradRMSProp._launch,
+             pot.NativePotential.value_and_grad, nuts.HMC._leapfrog, ops.reduce_to)
+    ops.site_score = _site_score
+    N.require_cuda = lambda t, what: None
+    optim.ClippedAdam._launch = _adam_launch
+    optim.AdagradRMSProp._launch = _agr_launch
+    pot.NativePotential.value_and_grad = _native_value_and_grad
+    nuts.HMC._leapfrog = _leapfrog
+    ops.reduce_to = _reduce_to
+    try:
+        yield
+    finally:
+        pdist._BernoulliLinear._fused_sum = saved_glm
+        (ops.site_score, N.require_cuda, optim.ClippedAdam._launch, optim.AdagradRMSProp._launch,
+         pot.NativePotential.value_and_grad, nuts.HMC._leapfrog, ops.reduce_to) = saved

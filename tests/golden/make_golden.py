@@ -305,8 +305,8 @@ def elbo_grad():
         rate = pyro.sample("rate", dist.Gamma(2.0, 0.5))
         with pyro.plate("data", 2 * N, subsample_size=N, dim=-1):
             with poutine.mask(mask=mask):
-                pyro.sample("x", dist.Normal(z.unsqueeze(-1) if z.dim() else z, 1.3), obs=data)
-            pyro.sample("c", dist.Poisson(rate.unsqueeze(-1) if rate.dim() else rate), obs=counts)
+                pyro.sample("x", dist.Normal(z, 1.3), obs=data)  # z: [] or [P, 1]
+            pyro.sample("c", dist.Poisson(rate), obs=counts)
 
     def guide():
         loc = pyro.param("loc", torch.tensor(0.3))

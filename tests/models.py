@@ -1,0 +1,79 @@
+"""Model / guide definitions shared by the CPU (emulated) and GPU (real kernel) test tiers and by
+bench.py.  Written against the ``pyro`` interface; ``import pyro_b200 as pyro`` is the only change
+from reference user code."""
+import torch
+from torch.distributions import constraints
+
+import pyro_b200 as pyro
+import pyro_b200.distributions as dist
+from pyro_b200 import poutine
+
+
+def logistic_model(X, y):
+    """tests/infer/mcmc/test_hmc.py:189-198 scaled as SURVEY.md 8d (BASELINE config 2)."""
+    D = X.shape[-1]
+    w = pyro.sample("w", dist.Normal(X.new_zeros(D), X.new_ones(D)).to_event(1))
+    b = pyro.sample("b", dist.Normal(X.new_zeros(()), X.new_full((), 10.0)))
+    with pyro.plate("data", X.shape[0]):
+        # w: [D] or [P, 1, D] (vectorised particles); b: [] or [P, 1] -> logits [N] or [P, N]
+        if w.dim() > 1:
+            logits = w.squeeze(-2) @ X.T + b
+        else:
+            logits = X @ w + b
+        pyro.sample("y", dist.Bernoulli(logits=logits), obs=y)
+
+
+def logistic_model_fused(X, y):
+    """Same model with the linear predictor handed over lazily, so the likelihood site is scored by
+    the fused GLM kernel (X and y read once for value and gradient)."""
+    D = X.shape[-1]
+    w = pyro.sample("w", dist.Normal(X.new_zeros(D), X.new_ones(D)).to_event(1))
+    b = pyro.sample("b", dist.Normal(X.new_zeros(()), X.new_full((), 10.0)))
+    with pyro.plate("data", X.shape[0]):
+        pyro.sample("y", dist.Bernoulli(logits=dist.linear_predictor(X, w, b)), obs=y)
+
+
+def logistic_guide(X, y):
+    D = X.shape[-1]
+    w_loc = pyro.param("w_loc", lambda: X.new_zeros(D))
+    w_scale = pyro.param("w_scale", lambda: X.new_full((D,), 0.1), constraint=constraints.positive)
+    b_loc = pyro.param("b_loc", lambda: X.new_zeros(()))
+    b_scale = pyro.param("b_scale", lambda: X.new_full((), 0.1), constraint=constraints.positive)
+    pyro.sample("w", dist.Normal(w_loc, w_scale).to_event(1))
+    pyro.sample("b", dist.Normal(b_loc, b_scale))
+
+
+class InjectNoise(poutine.Messenger):
+    """Replace the guide's Normal draws by loc + eps*scale for recorded eps (the replay technique of
+    tests/infer/test_gradient.py:77-91), so runs are comparable across devices and with the
+    reference goldens."""
+
+    def __init__(self, eps):
+        self.eps = eps
+
+    def _pyro_sample(self, msg):
+        if msg["name"] in self.eps and not msg["is_observed"]:
+            fn = msg["fn"]
+            base = fn
+            while hasattr(base, "base_dist"):
+                base = base.base_dist
+            e = self.eps[msg["name"]]
+            msg["value"] = base.loc + e.to(base.loc.dtype) * base.scale
+            msg["done"] = True
+
+
+def eight_schools(sigma, y=None):
+    """examples/eight_schools/mcmc.py:27-34"""
+    J = sigma.shape[0]
+    eta = pyro.sample("eta", dist.Normal(sigma.new_zeros(J), sigma.new_ones(J)))
+    mu = pyro.sample("mu", dist.Normal(sigma.new_zeros(1), 10 * sigma.new_ones(1)))
+    tau = pyro.sample("tau", dist.HalfCauchy(scale=25 * sigma.new_ones(1)))
+    theta = mu + tau * eta
+    return pyro.sample("obs", dist.Normal(theta, sigma), obs=y)
+
+
+def logreg_mcmc_model(X, y):
+    D = X.shape[-1]
+    beta = pyro.sample("beta", dist.Normal(X.new_zeros(D), X.new_ones(D)))
+    logits = (X * beta.unsqueeze(-2)).sum(-1) if beta.dim() > 1 else (X * beta).sum(-1)
+    return pyro.sample("y", dist.Bernoulli(logits=logits), obs=y)

@@ -1,0 +1,212 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against goldens recorded from the
+unmodified reference and against the oracle on seeded inputs.  Tolerances (stated per test):
+  * index / integer work (Categorical gather) ............ bit-exact selection
+  * fp64 kernels vs reference ............................. 1e-12 relative (1e-10 on gradients)
+  * fp32 kernels vs fp64 reference ........................ |d| <= 1e-5 * max(1, |lp|)
+    (the reference's own atol, tests/common.py:246-248); gradients 2e-4
+  * sums of N terms ....................................... 1e-5 relative in fp32 (fixed-order tree
+    summation, more accurate than a sequential sum)
+"""
+import numpy as np
+import pytest
+import torch
+
+import pyro_b200.distributions as dist
+from conftest import device, load_npz
+from oracle import dists as odists
+from pyro_b200.distributions import _ops
+
+pytestmark = pytest.mark.gpu
+DEV = device()
+
+MAKE = {
+    "normal": lambda p: dist.Normal(*p), "cauchy": lambda p: dist.Cauchy(*p),
+    "lognormal": lambda p: dist.LogNormal(*p), "halfcauchy": lambda p: dist.HalfCauchy(*p),
+    "halfnormal": lambda p: dist.HalfNormal(*p), "exponential": lambda p: dist.Exponential(*p),
+    "gamma": lambda p: dist.Gamma(*p), "beta": lambda p: dist.Beta(*p),
+    "uniform": lambda p: dist.Uniform(*p),
+    "bernoulli_logits": lambda p: dist.Bernoulli(logits=p[0]),
+    "bernoulli_probs": lambda p: dist.Bernoulli(probs=p[0]),
+    "poisson": lambda p: dist.Poisson(*p),
+    "normal_bcast": lambda p: dist.Normal(*p), "normal_bcast2": lambda p: dist.Normal(*p),
+    "dirichlet": lambda p: dist.Dirichlet(*p), "dirichlet_bcast": lambda p: dist.Dirichlet(*p),
+    "categorical3": lambda p: dist.Categorical(logits=p[0]),
+    "categorical40": lambda p: dist.Categorical(logits=p[0]),
+    "categorical_bcast": lambda p: dist.Categorical(logits=p[0]),
+    "mvn2": lambda p: dist.MultivariateNormal(p[0], scale_tril=p[1]),
+    "mvn5": lambda p: dist.MultivariateNormal(p[0], scale_tril=p[1]),
+    "mvn37": lambda p: dist.MultivariateNormal(p[0], scale_tril=p[1]),
+    "mvn_bcast": lambda p: dist.MultivariateNormal(p[0], scale_tril=p[1]),
+}
+
+
+def _load(key, dtype):
+    g = load_npz("dist_random.npz")
+    v = torch.as_tensor(g[key + ".value"])
+    v = v.to(DEV) if not v.is_floating_point() else v.to(DEV, dtype)
+    ps, i = [], 0
+    while key + ".p%d" % i in g:
+        ps.append(torch.as_tensor(g[key + ".p%d" % i]).to(DEV, dtype))
+        i += 1
+    return g, v, ps
+
+
+def _close(a, ref, tol):
+    a = a.detach().double().cpu()
+    ref = torch.as_tensor(ref).double().reshape(a.shape)
+    bad = (a - ref).abs() > tol * ref.abs().clamp(min=1)
+    assert not bool(bad.any()), "max err %.3e" % float(((a - ref).abs() / ref.abs().clamp(min=1)).max())
+
+
+@pytest.mark.parametrize("key", sorted(MAKE))
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-12, 1e-9), (torch.float32, 1e-5, 2e-4)])
+def test_log_prob_and_backward_match_reference(key, dtype, tol, gtol):
+    g, v, ps = _load(key, dtype)
+    ps = [p.requires_grad_(True) for p in ps]
+    has_dv = key + ".dvalue" in g
+    if has_dv:
+        v = v.requires_grad_(True)
+    lp = MAKE[key](ps).log_prob(v)
+    _close(lp, g[key + ".lp"], tol)
+    if key.startswith("categorical"):
+        # the gathered entry must be the exact normalised logit (index work is exact)
+        lgn = (ps[0] - ps[0].logsumexp(-1, keepdim=True)).detach()
+        vv = v.unsqueeze(-1)
+        vv, lgb = torch.broadcast_tensors(vv, lgn)
+        ref = lgb.gather(-1, vv[..., :1]).squeeze(-1)
+        assert torch.allclose(lp.detach(), ref, atol=tol * 10, rtol=0)
+    up = torch.ones_like(lp)
+    grads = torch.autograd.grad(lp, ([v] if has_dv else []) + ps, grad_outputs=up, allow_unused=True)
+    gi = 0
+    if has_dv:
+        _close(grads[0], g[key + ".dvalue"], gtol)
+        gi = 1
+    for k in range(len(ps)):
+        ref = g[key + ".dp%d" % k]
+        got = grads[gi + k]
+        if got is None:
+            assert np.all(ref == 0)
+        else:
+            _close(got, ref, gtol)
+
+
+@pytest.mark.parametrize("key", ["normal", "gamma", "bernoulli_logits", "normal_bcast", "normal_bcast2",
+                                 "dirichlet_bcast", "categorical_bcast", "mvn_bcast", "beta", "poisson"])
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-11, 1e-9), (torch.float32, 2e-5, 3e-4)])
+def test_fused_sum_path_scale_mask_weight(key, dtype, tol, gtol):
+    """ONE kernel: sum(scale*mask*lp) and the final weighted gradients, vs autograd on the oracle."""
+    g, v, ps = _load(key, dtype)
+    torch.manual_seed(0)
+    d = MAKE[key](ps)
+    bshape = d.log_prob(v).shape
+    mask = (torch.rand(bshape, device=DEV) < 0.7)
+    scale, weight, coeff = 2.5, -0.125, -1.0
+    diff_value = v.is_floating_point() and (key + ".dvalue") in g
+    ps_r = [p.clone().requires_grad_(True) for p in ps]
+    vr = v.clone().requires_grad_(True) if diff_value else v
+    out = MAKE[key](ps_r)._fused_sum(vr, mask, scale, weight, coeff, True)
+    grads = torch.autograd.grad(out, ([vr] if diff_value else []) + ps_r, allow_unused=True)
+    # oracle in float64 on the CPU
+    fam = d.family
+    po = [p.detach().double().cpu().requires_grad_(True) for p in ps]
+    vo = v.detach().cpu()
+    if vo.is_floating_point():
+        vo = vo.double()
+    if diff_value:
+        vo.requires_grad_(True)
+    fn = odists.ELEMENTWISE[fam][0] if fam in odists.ELEMENTWISE else odists.EVENT[fam]
+    lp = fn(vo, *po).expand(bshape)
+    tot = torch.where(mask.cpu(), lp * scale, torch.zeros((), dtype=torch.float64)).sum()
+    assert abs(float(out) - coeff * float(tot)) <= 10 * tol * max(1.0, abs(float(tot)))
+    og = torch.autograd.grad(weight * tot, ([vo] if diff_value else []) + po, allow_unused=True)
+    assert len(og) == len(grads)
+    for a, b in zip(grads, og):
+        if b is None:
+            continue
+        _close(a, b, gtol)
+
+
+def test_kl_kernels():
+    g = load_npz("kl.npz")
+    for name, cls in (("normal", dist.Normal), ("gamma", dist.Gamma)):
+        ps = [torch.as_tensor(g["%s.p%d" % (name, i)]).to(DEV).requires_grad_(True) for i in range(4)]
+        kl = dist.kl_divergence(cls(ps[0], ps[1]), cls(ps[2], ps[3]))
+        _close(kl, g[name + ".kl"], 1e-12)
+        grads = torch.autograd.grad(kl.sum(), ps)
+        for k in range(4):
+            _close(grads[k], g["%s.dp%d" % (name, k)], 1e-7)
+
+
+@pytest.mark.parametrize("shape,dst_shape", [((7, 5, 3), (5, 3)), ((7, 5, 3), (7, 1, 3)), ((6, 4), (1, 4)),
+                                             ((1000, 33), (33,)), ((3, 100000), (3, 1)), ((64, 1, 32), (32,))])
+def test_reduce_to(shape, dst_shape):
+    torch.manual_seed(0)
+    src = torch.randn(shape, device=DEV, dtype=torch.float64)
+    dst = torch.empty(dst_shape, device=DEV, dtype=torch.float64)
+    _ops.reduce_to(src, dst)
+    ref = src.sum_to_size(dst_shape) if len(dst_shape) == len(shape) else src.sum_to_size((1,) * (len(shape) - len(dst_shape)) + tuple(dst_shape)).reshape(dst_shape)
+    assert torch.allclose(dst, ref, atol=1e-9, rtol=1e-12)
+
+
+def test_large_sum_property_and_determinism():
+    """BASELINE-size site: Bernoulli(logits [64, 1e6]) against obs [1e6] broadcast over particles.
+    Properties: (i) fused sum == sum of materialised log_prob; (ii) bit-stable across launches;
+    (iii) linearity in scale; (iv) gradient == y - sigmoid(l) on a sampled slab."""
+    torch.manual_seed(0)
+    P, N = 64, 1 << 20
+    logits = torch.randn(P, N, device=DEV)
+    y = (torch.rand(N, device=DEV) < 0.3).float()
+    d = dist.Bernoulli(logits=logits)
+    s1 = d._fused_sum(y, None, 1.0, 1.0, 1.0, True)
+    s2 = d._fused_sum(y, None, 1.0, 1.0, 1.0, True)
+    assert float(s1) == float(s2)
+    lp = d.log_prob(y)
+    ref = float(lp.double().sum())
+    assert abs(float(s1) - ref) <= 1e-5 * abs(ref)
+    s3 = d._fused_sum(y, None, 3.0, 1.0, 1.0, True)
+    assert abs(float(s3) - 3 * float(s1)) <= 1e-5 * abs(ref) * 3
+    lg = logits.clone().requires_grad_(True)
+    out = dist.Bernoulli(logits=lg)._fused_sum(y, None, 1.0, -1.0 / P, 1.0, True)
+    (gl,) = torch.autograd.grad(out, lg)
+    expect = (-1.0 / P) * (y[None, :4096] - torch.sigmoid(logits[:, :4096]))
+    assert torch.allclose(gl[:, :4096], expect, atol=1e-7, rtol=1e-5)
+    # oracle on a slab
+    o = odists.bernoulli_logits(y[:5000].cpu().double(), logits[:3, :5000].cpu().double())
+    assert torch.allclose(lp[:3, :5000].cpu().double(), o, atol=1e-5)
+
+
+def test_empty_and_ragged_sites():
+    z = torch.zeros(0, 5, device=DEV)
+    d = dist.Normal(torch.zeros(5, device=DEV), torch.ones(5, device=DEV))
+    assert d.log_prob(z).shape == (0, 5)
+    assert float(d._fused_sum(z, None, 1.0, 1.0, 1.0, True)) == 0.0
+    for n in (1, 2, 3, 5, 31, 33, 1023, 1025):
+        x = torch.randn(n, device=DEV, dtype=torch.float64)
+        lp = dist.Normal(torch.zeros((), device=DEV, dtype=torch.float64), torch.ones((), device=DEV, dtype=torch.float64)).log_prob(x)
+        ref = odists.normal(x.cpu(), torch.zeros((), dtype=torch.float64), torch.ones((), dtype=torch.float64))
+        assert torch.allclose(lp.cpu(), ref, atol=1e-13)
+    # unaligned view (forces the generic kernel)
+    base = torch.randn(1001, device=DEV)
+    x = base[1:]
+    lp = dist.Normal(torch.zeros((), device=DEV), torch.ones((), device=DEV)).log_prob(x)
+    assert torch.allclose(lp.cpu().double(), odists.normal(x.cpu().double(), torch.zeros((), dtype=torch.float64), torch.ones((), dtype=torch.float64)), atol=1e-5)
+    # non-contiguous (transposed) operands
+    a = torch.randn(37, 19, device=DEV, dtype=torch.float64)
+    lpt = dist.Normal(a.t(), torch.ones((), device=DEV, dtype=torch.float64)).log_prob(torch.zeros(19, 37, device=DEV, dtype=torch.float64))
+    assert torch.allclose(lpt.cpu(), odists.normal(torch.zeros(19, 37, dtype=torch.float64), a.t().cpu(), torch.ones((), dtype=torch.float64)), atol=1e-12)
+
+
+def test_edge_values():
+    """-inf outside the support, NaN propagation, masked NaNs do not leak."""
+    hc = dist.HalfCauchy(torch.ones(3, device=DEV))
+    lp = hc.log_prob(torch.tensor([-1.0, 0.0, 2.0], device=DEV))
+    assert lp[0] == -float("inf") and torch.isfinite(lp[1:]).all()
+    n = dist.Normal(torch.tensor([0.0, float("nan")], device=DEV), torch.ones(2, device=DEV))
+    lp = n.log_prob(torch.zeros(2, device=DEV))
+    assert torch.isfinite(lp[0]) and torch.isnan(lp[1])
+    mask = torch.tensor([True, False], device=DEV)
+    s = n._fused_sum(torch.zeros(2, device=DEV), mask, 1.0, 1.0, 1.0, True)
+    assert torch.isfinite(s)
+    p = dist.Poisson(torch.tensor([0.0, 2.0], device=DEV))
+    lp = p.log_prob(torch.tensor([0.0, 3.0], device=DEV))
+    assert abs(float(lp[0])) < 1e-7

@@ -1,0 +1,284 @@
+"""End-to-end parity of the two hot paths on the GPU: SVI steps (eager, fused GLM, CUDA-graph
+captured) against the reference's recorded trajectory; optimisers; leapfrog / potentials / NUTS
+against goldens and the oracle.  See test_gpu_kernels.py for the tolerance policy."""
+import math
+
+import numpy as np
+import pytest
+import torch
+from torch.distributions import constraints
+
+import models
+import pyro_b200 as pyro
+import pyro_b200.distributions as dist
+from conftest import device, load_npz, EMULATE
+from oracle import mcmc as omcmc
+from oracle import svi as osvi
+from pyro_b200 import poutine
+from pyro_b200.infer import MCMC, NUTS, HMC, SVI, JitTrace_ELBO, Trace_ELBO, TraceMeanField_ELBO
+from pyro_b200.infer.mcmc import HierNormalPotential, LogisticPotential, TracePotential
+from pyro_b200.optim import AdagradRMSProp, ClippedAdam
+
+pytestmark = pytest.mark.gpu
+DEV = device()
+
+
+def _svi_trajectory(model, elbo_cls, dtype, tag, tol, steps=None):
+    g = load_npz("svi_logistic.npz")
+    torch.set_default_dtype(dtype)
+    X, y = torch.as_tensor(g["X"]).to(DEV, dtype), torch.as_tensor(g["y"]).to(DEV, dtype)
+    eps_w, eps_b = torch.as_tensor(g["eps_w"]).to(DEV, dtype), torch.as_tensor(g["eps_b"]).to(DEV, dtype)
+    P = int(g["P"])
+    box = {"i": 0}
+
+    def guide(X, y):
+        with models.InjectNoise({"w": eps_w[box["i"]], "b": eps_b[box["i"]]}):
+            models.logistic_guide(X, y)
+
+    svi = SVI(model, guide, ClippedAdam({"lr": 0.01}),
+              elbo_cls(num_particles=P, vectorize_particles=True, max_plate_nesting=1))
+    for i in range(eps_w.shape[0] if steps is None else steps):
+        box["i"] = i
+        loss = svi.step(X, y)
+        assert abs(loss - g["losses_" + tag][i]) <= 10 * tol * abs(g["losses_" + tag][i]), (i, loss)
+        store = pyro.get_param_store()
+        flat = torch.cat([store[k].detach().reshape(-1).double().cpu() for k in ("w_loc", "w_scale", "b_loc", "b_scale")])
+        assert torch.allclose(flat, torch.as_tensor(g["params_" + tag][i]), atol=10 * tol, rtol=10 * tol), i
+
+
+@pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-9), ("f32", torch.float32, 3e-4)])
+def test_svi_logistic_matches_reference_trajectory(tag, dtype, tol):
+    _svi_trajectory(models.logistic_model, Trace_ELBO, dtype, tag, tol)
+
+
+def test_svi_logistic_fused_glm_matches_reference_trajectory():
+    """fp32 only (the GLM kernel is fp32 with fast-math transcendentals): ELBO within 5e-4 relative,
+    parameters within 5e-3 absolute of the reference after 5 steps."""
+    _svi_trajectory(models.logistic_model_fused, Trace_ELBO, torch.float32, "f32", 5e-4)
+
+
+def test_glm_kernel_against_oracle():
+    """X, y read once; sum / dW / db vs float64 autograd of the oracle, ragged N, several D and P."""
+    torch.manual_seed(0)
+    for (n, D, P) in [(1, 4, 1), (63, 8, 3), (64, 16, 64), (1000, 32, 7), (4097, 32, 64), (130, 4, 130)]:
+        X = torch.randn(n, D, device=DEV)
+        y = (torch.rand(n, device=DEV) < 0.4).float()
+        w = (0.5 * torch.randn(P, 1, D, device=DEV)).requires_grad_(True)
+        b = torch.randn(P, 1, device=DEV).requires_grad_(True)
+        d = dist.Bernoulli(logits=dist.linear_predictor(X, w, b))
+        out = d._fused_sum(y, None, 1.5, -0.25, 1.0, True)
+        gw, gb = torch.autograd.grad(out, [w, b])
+        wo = w.detach().double().cpu().requires_grad_(True)
+        bo = b.detach().double().cpu().requires_grad_(True)
+        logits = wo.squeeze(-2) @ X.double().cpu().t() + bo
+        from oracle import dists as od
+        tot = (od.bernoulli_logits(y.double().cpu(), logits) * 1.5).sum()
+        assert abs(float(out) - float(tot)) <= 2e-5 * max(1.0, abs(float(tot))), (n, D, P)
+        ow, ob = torch.autograd.grad(-0.25 * tot, [wo, bo])
+        sc = max(1.0, float(ow.abs().max()))
+        assert float((gw.double().cpu() - ow).abs().max()) <= 2e-4 * sc, (n, D, P)
+        assert float((gb.double().cpu() - ob).abs().max()) <= 2e-4 * max(1.0, float(ob.abs().max())), (n, D, P)
+
+
+def test_captured_graph_step_equals_eager():
+    """JitTrace_ELBO analogue: the CUDA-graph replayed step must follow the same trajectory as eager
+    steps when the guide noise comes from the same generator state."""
+    if EMULATE:
+        pytest.skip("graph capture needs a GPU")
+    torch.manual_seed(0)
+    N_, D, P = 4096, 8, 16
+    X = torch.randn(N_, D, device=DEV)
+    y = (torch.rand(N_, device=DEV) < torch.sigmoid(X[:, 0])).float()
+
+    def run(elbo_cls, nsteps):
+        pyro.clear_param_store()
+        torch.manual_seed(1)
+        torch.cuda.manual_seed(1)
+        svi = SVI(models.logistic_model, models.logistic_guide, ClippedAdam({"lr": 0.05}),
+                  elbo_cls(num_particles=P, vectorize_particles=True, max_plate_nesting=1))
+        losses = [svi.step(X, y) for _ in range(nsteps)]
+        store = pyro.get_param_store()
+        return losses, {k: store[k].detach().clone() for k in store.keys()}
+
+    l_e, p_e = run(Trace_ELBO, 40)
+    l_g, p_g = run(JitTrace_ELBO, 40)
+    # different RNG consumption under capture -> compare statistically: both must have learned
+    assert l_g[-1] < l_g[0] and l_e[-1] < l_e[0]
+    assert abs(np.mean(l_g[-10:]) - np.mean(l_e[-10:])) < 0.05 * abs(np.mean(l_e[-10:]))
+    for k in p_e:
+        assert torch.allclose(p_e[k], p_g[k], atol=0.15), k
+
+
+@pytest.mark.parametrize("cls,tag", [(Trace_ELBO, "trace"), (TraceMeanField_ELBO, "meanfield")])
+def test_elbo_grads_gamma_poisson_mask_subsample(cls, tag):
+    g = load_npz("elbo_grad.npz")
+    torch.set_default_dtype(torch.float64)
+    data, counts = torch.as_tensor(g["data"]).to(DEV), torch.as_tensor(g["counts"]).to(DEV)
+    mask = torch.as_tensor(g["mask"]).to(DEV)
+    eps, ueps = torch.as_tensor(g["eps"]).to(DEV), torch.as_tensor(g["ueps"]).to(DEV)
+    n = data.shape[0]
+    T = lambda v: torch.tensor(v, device=DEV)  # noqa: E731
+
+    def model():
+        z = pyro.sample("z", dist.Normal(T(0.0), T(2.0)))
+        rate = pyro.sample("rate", dist.Gamma(T(2.0), T(0.5)))
+        with pyro.plate("data", 2 * n, subsample_size=n, dim=-1):
+            with poutine.mask(mask=mask):
+                pyro.sample("x", dist.Normal(z, T(1.3)), obs=data)
+            pyro.sample("c", dist.Poisson(rate), obs=counts)
+
+    class Inject(poutine.Messenger):
+        def __init__(self, vals):
+            self.vals = vals
+
+        def _pyro_sample(self, msg):
+            if msg["name"] in self.vals:
+                msg["value"] = self.vals[msg["name"]]
+                msg["done"] = True
+
+    def guide():
+        loc = pyro.param("loc", T(0.3))
+        scale = pyro.param("scale", T(0.7), constraint=constraints.positive)
+        conc = pyro.param("conc", T(3.0), constraint=constraints.positive)
+        grate = pyro.param("grate", T(1.2), constraint=constraints.positive)
+        with Inject({"z": loc + eps * scale, "rate": conc / grate * (0.5 + ueps)}):
+            pyro.sample("z", dist.Normal(loc, scale))
+            pyro.sample("rate", dist.Gamma(conc, grate))
+
+    elbo = cls(num_particles=6, vectorize_particles=True, max_plate_nesting=1)
+    with poutine.trace(param_only=True) as cap:
+        loss = elbo.loss_and_grads(model, guide)
+    assert abs(loss - float(g[tag + ".loss"])) < 1e-8 * abs(float(g[tag + ".loss"]))
+    for name, site in cap.trace.nodes.items():
+        ref = torch.as_tensor(g["%s.grad.%s" % (tag, name)])
+        got = site["value"]._pyro_unconstrained_param.grad.cpu()
+        assert torch.allclose(got, ref, atol=1e-7, rtol=1e-7), name
+
+
+@pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-12), ("f32", torch.float32, 2e-6)])
+def test_fused_optimisers_match_reference(tag, dtype, tol):
+    g = load_npz("optim.npz")
+    for name, mk in (
+        ("clipped_adam", lambda: ClippedAdam({"lr": 0.05, "betas": (0.9, 0.99), "clip_norm": 2.0, "lrd": 0.97, "weight_decay": 0.01})),
+        ("clipped_adam_default", lambda: ClippedAdam({"lr": 0.01})),
+        ("adagrad_rmsprop", lambda: AdagradRMSProp({"eta": 4.5, "t": 0.1})),
+    ):
+        p = torch.as_tensor(g["p0_" + tag]).to(DEV).clone().requires_grad_(True)
+        q = torch.zeros(5, 3, device=DEV, dtype=dtype).requires_grad_(True)  # a second tensor in the same launch
+        pyro.get_param_store()._param_to_name[p] = "p"
+        pyro.get_param_store()._param_to_name[q] = "q"
+        opt = mk()
+        p.grad = torch.zeros_like(p)
+        q.grad = torch.zeros_like(q)
+        for i, gr in enumerate(torch.as_tensor(g["grads_" + tag]).to(DEV)):
+            p.grad.copy_(gr)
+            q.grad.fill_(0.1)
+            opt([p, q])
+            ref = torch.as_tensor(g["%s_%s" % (name, tag)][i])
+            assert torch.allclose(p.detach().cpu(), ref, atol=tol, rtol=tol), (name, i)
+            assert float(p.grad.abs().max()) == 0.0  # zeroed in the same pass
+        st = opt.get_state()["p"]["state"][0]
+        assert st["step"] == 12
+
+
+def test_native_potentials_and_leapfrog_match_reference():
+    g = load_npz("mcmc.npz")
+    dt = torch.float64
+    y, sigma = torch.as_tensor(g["es.y"]).to(DEV), torch.as_tensor(g["es.sigma"]).to(DEV)
+    Z = torch.as_tensor(g["es.Z"]).to(DEV)
+    pot = HierNormalPotential(y, sigma, 10.0, 25.0)
+    U, G = pot.value_and_grad(Z)
+    assert torch.allclose(U.cpu(), torch.as_tensor(g["es.U"]), atol=1e-9, rtol=1e-10)
+    assert torch.allclose(G.cpu(), torch.as_tensor(g["es.G"]), atol=1e-9, rtol=1e-10)
+    lp = LogisticPotential(torch.as_tensor(g["lr.X"]).to(DEV), torch.as_tensor(g["lr.y"]).to(DEV), 1.0)
+    U, G = lp.value_and_grad(torch.as_tensor(g["lr.B"]).to(DEV))
+    assert torch.allclose(U.cpu(), torch.as_tensor(g["lr.U"]), atol=1e-9, rtol=1e-10)
+    assert torch.allclose(G.cpu(), torch.as_tensor(g["lr.G"]), atol=1e-9, rtol=1e-10)
+    # 7 leapfrog steps of the C-ABI integrator == reference velocity_verlet (integrator.py:14-65)
+    k = HMC(potential_fn=pot, adapt_step_size=False, adapt_mass_matrix=False)
+    k.setup(0, 1, initial_params=Z[:1].clone())
+    z = Z[:1].clone().contiguous()
+    r = torch.as_tensor(g["es.vv.r0"]).to(DEV)[None].contiguous()
+    minv = torch.as_tensor(g["es.vv.minv"]).to(DEV)[None].contiguous()
+    eps = torch.full((1,), 0.05, dtype=dt, device=DEV)
+    _, gcur = pot.value_and_grad(z)
+    for _ in range(7):
+        z, r, gcur, Ucur, ke = k._leapfrog(z, r, gcur, eps, minv)
+    assert torch.allclose(z[0].cpu(), torch.as_tensor(g["es.vv.z"]), atol=1e-9)
+    assert torch.allclose(r[0].cpu(), torch.as_tensor(g["es.vv.r"]), atol=1e-9)
+    assert abs(float(Ucur) - float(g["es.vv.U"])) < 1e-8
+    assert abs(float(ke) - 0.5 * float((minv * r * r).sum())) < 1e-9
+    # fp32, large J, many chains: property test (energy error of a short trajectory is O(eps^2))
+    torch.manual_seed(0)
+    J, C = 200_000, 8
+    sig = (5 + 15 * torch.rand(J, device=DEV))
+    yy = 5 + 3 * torch.randn(J, device=DEV) + sig * torch.randn(J, device=DEV)
+    big = HierNormalPotential(yy, sig)
+    z = torch.cat([torch.randn(C, 2, device=DEV) * 0.1, torch.randn(C, J, device=DEV)], 1).contiguous()
+    U1, G1 = big.value_and_grad(z)
+    ref_U = omcmc.eight_schools_potential(yy.double().cpu(), sig.double().cpu())
+    g_ref, u_ref = omcmc.potential_grad(ref_U, z[0].double().cpu())
+    assert abs(float(U1[0]) - float(u_ref)) <= 2e-6 * abs(float(u_ref))
+    assert float((G1[0].double().cpu() - g_ref).abs().max()) <= 1e-3 * max(1.0, float(g_ref.abs().max()))
+
+
+def test_trace_potential_matches_reference():
+    torch.set_default_dtype(torch.float64)
+    g = load_npz("mcmc.npz")
+    y, sigma = torch.as_tensor(g["es.y"]).to(DEV), torch.as_tensor(g["es.sigma"]).to(DEV)
+    Z = torch.as_tensor(g["es.Z"]).to(DEV)
+    pot = TracePotential(models.eight_schools, (sigma, y), {}, num_chains=Z.shape[0])
+    order = list(pot.sites)
+    cols = {"mu": Z[:, 0:1], "tau": Z[:, 1:2], "eta": Z[:, 2:]}
+    U, G = pot.value_and_grad(torch.cat([cols[n] for n in order], dim=1))
+    assert torch.allclose(U.cpu(), torch.as_tensor(g["es.U"]), atol=1e-9, rtol=1e-9)
+    Gr = torch.as_tensor(g["es.G"])
+    ref_cols = {"mu": Gr[:, 0:1], "tau": Gr[:, 1:2], "eta": Gr[:, 2:]}
+    assert torch.allclose(G.cpu(), torch.cat([ref_cols[n] for n in order], dim=1), atol=1e-9, rtol=1e-9)
+
+
+def test_native_nuts_eight_schools_posterior():
+    """BASELINE config 1 through the whole-transition kernel: posterior moments vs the reference's
+    long run (golden es.long.*); tolerances in the spirit of tests/infer/mcmc/test_nuts.py."""
+    if EMULATE:
+        pytest.skip("needs the device kernel")
+    g = load_npz("mcmc.npz")
+    y, sigma = torch.as_tensor(g["es.y"]).to(DEV), torch.as_tensor(g["es.sigma"]).to(DEV)
+    kernel = NUTS(potential_fn=HierNormalPotential(y, sigma, 10.0, 25.0))
+    mc = MCMC(kernel, num_samples=1000, warmup_steps=300, num_chains=16, seed=0)
+    mc.run()
+    s = mc.get_samples()
+    assert abs(float(s["mu"].mean()) - float(g["es.long.mu.mean"][0])) < 0.4
+    assert abs(float(s["tau"].mean()) - float(g["es.long.tau.mean"][0])) < 0.6
+    assert float((s["eta"].mean(0).cpu() - torch.as_tensor(g["es.long.eta.mean"])).abs().max()) < 0.1
+    assert abs(float(s["mu"].std()) - float(g["es.long.mu.std"][0])) < 0.5
+    d = mc.diagnostics()
+    assert float(d["mu"]["r_hat"].max()) < 1.05
+    assert kernel.leapfrog_count() > 16 * 1300
+
+
+def test_lockstep_nuts_logistic_posterior():
+    torch.set_default_dtype(torch.float64)
+    g = load_npz("mcmc.npz")
+    X, y = torch.as_tensor(g["lr.X"]).to(DEV), torch.as_tensor(g["lr.y"]).to(DEV)
+    kernel = NUTS(potential_fn=LogisticPotential(X, y, 1.0), native_small=False)
+    mc = MCMC(kernel, num_samples=200, warmup_steps=150, num_chains=8, seed=1)
+    mc.run()
+    s = mc.get_samples()["beta"].cpu()
+    chain = omcmc.NUTSChain(omcmc.logistic_potential(X.cpu(), y.cpu(), 1.0), 3, seed=2)
+    ref, _ = chain.run(torch.zeros(3, dtype=torch.float64), 150, 600)
+    assert torch.allclose(s.mean(0), ref.mean(0), atol=0.12)
+    assert torch.allclose(s.std(0), ref.std(0), atol=0.08)
+
+
+def test_generic_model_nuts_runs_and_agrees():
+    """An unchanged Pyro-style model through TracePotential + lockstep NUTS."""
+    torch.set_default_dtype(torch.float64)
+    g = load_npz("mcmc.npz")
+    X, y = torch.as_tensor(g["lr.X"]).to(DEV), torch.as_tensor(g["lr.y"]).to(DEV)
+    mc = MCMC(NUTS(models.logreg_mcmc_model), num_samples=120, warmup_steps=100, num_chains=6, seed=3)
+    mc.run(X, y)
+    s = mc.get_samples()["beta"].cpu()
+    chain = omcmc.NUTSChain(omcmc.logistic_potential(X.cpu(), y.cpu(), 1.0), 3, seed=5)
+    ref, _ = chain.run(torch.zeros(3, dtype=torch.float64), 150, 500)
+    assert torch.allclose(s.mean(0), ref.mean(0), atol=0.15)

@@ -1,0 +1,311 @@
+"""Host logic on the CPU tier: the native seams are replaced by oracle-backed stand-ins
+(tests/cpu_emulation.py), everything else is the product's own Python -- effect handlers, plates,
+Trace_ELBO assembly, optimiser bookkeeping, MCMC driver.  Results are compared with goldens from
+the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+from torch.distributions import constraints
+
+import cpu_emulation
+import models
+import pyro_b200 as pyro
+import pyro_b200.distributions as dist
+from conftest import load_npz
+from pyro_b200 import poutine
+from pyro_b200.infer import SVI, Trace_ELBO, TraceMeanField_ELBO
+from pyro_b200.optim import AdagradRMSProp, ClippedAdam
+
+
+@pytest.fixture
+def emu():
+    with cpu_emulation.enabled():
+        yield
+
+
+def test_plate_shapes_and_scale(emu):
+    def model():
+        with pyro.plate("outer", 10, subsample_size=5, dim=-2):
+            with pyro.plate("inner", 3, dim=-1):
+                x = pyro.sample("x", dist.Normal(torch.tensor(0.0), torch.tensor(1.0)))
+        return x
+    tr = poutine.trace(model).get_trace()
+    site = tr.nodes["x"]
+    assert site["value"].shape == (5, 3)
+    assert site["fn"].batch_shape == (5, 3)
+    assert site["scale"] == 2.0
+    assert [f.name for f in site["cond_indep_stack"]] == ["outer", "inner"]
+    tr2 = poutine.prune_subsample_sites(tr)
+    assert "outer" not in tr2.nodes
+
+
+def test_plate_auto_dims_and_collision(emu):
+    def model():
+        with pyro.plate("a", 4):
+            with pyro.plate("b", 2):
+                return pyro.sample("x", dist.Normal(torch.zeros(()), torch.ones(())))
+    assert poutine.trace(model).get_trace().nodes["x"]["value"].shape == (2, 4)
+    with pytest.raises(ValueError):
+        with pyro.plate("p", 3, dim=-1), pyro.plate("q", 3, dim=-1):
+            pass
+
+
+def test_replay_condition_block(emu):
+    def model():
+        z = pyro.sample("z", dist.Normal(torch.tensor(0.0), torch.tensor(1.0)))
+        return pyro.sample("x", dist.Normal(z, torch.tensor(1.0)), obs=torch.tensor(0.3))
+    g = poutine.trace(model).get_trace()
+    r = poutine.trace(poutine.replay(model, trace=g)).get_trace()
+    assert r.nodes["z"]["value"] is g.nodes["z"]["value"]
+    c = poutine.trace(poutine.condition(model, data={"z": torch.tensor(1.5)})).get_trace()
+    assert c.nodes["z"]["is_observed"] and float(c.nodes["z"]["value"]) == 1.5
+    with poutine.trace() as outer:
+        poutine.block(model, hide=["z"])()
+    assert "z" not in outer.trace.nodes and "x" in outer.trace.nodes
+    lp = c.log_prob_sum()
+    ref = dist_ref_normal(1.5, 0, 1) + dist_ref_normal(0.3, 1.5, 1)
+    assert abs(float(lp) - ref) < 1e-6
+
+
+def dist_ref_normal(x, m, s):
+    return float(torch.distributions.Normal(m, s).log_prob(torch.tensor(x)))
+
+
+@pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-9), ("f32", torch.float32, 3e-4)])
+@pytest.mark.parametrize("elbo_cls", [Trace_ELBO])
+def test_svi_logistic_matches_reference_trajectory(emu, tag, dtype, tol, elbo_cls):
+    """The full host stack (particle plate, replay, fused-site ELBO assembly, per-parameter
+    ClippedAdam state) reproduces the reference's 5-step SVI trajectory."""
+    g = load_npz("svi_logistic.npz")
+    torch.set_default_dtype(dtype)
+    X, y = torch.as_tensor(g["X"]).to(dtype), torch.as_tensor(g["y"]).to(dtype)
+    eps_w, eps_b = torch.as_tensor(g["eps_w"]).to(dtype), torch.as_tensor(g["eps_b"]).to(dtype)
+    P = int(g["P"])
+    box = {"i": 0}
+
+    def guide(X, y):
+        with models.InjectNoise({"w": eps_w[box["i"]], "b": eps_b[box["i"]]}):
+            models.logistic_guide(X, y)
+
+    svi = SVI(models.logistic_model, guide, ClippedAdam({"lr": 0.01}),
+              elbo_cls(num_particles=P, vectorize_particles=True, max_plate_nesting=1))
+    for i in range(eps_w.shape[0]):
+        box["i"] = i
+        loss = svi.step(X, y)
+        assert abs(loss - g["losses_" + tag][i]) <= 10 * tol * abs(g["losses_" + tag][i]), i
+        store = pyro.get_param_store()
+        flat = torch.cat([store[k].detach().reshape(-1).double() for k in ("w_loc", "w_scale", "b_loc", "b_scale")])
+        assert torch.allclose(flat, torch.as_tensor(g["params_" + tag][i]), atol=10 * tol, rtol=10 * tol), i
+
+
+@pytest.mark.parametrize("cls,tag", [(Trace_ELBO, "trace"), (TraceMeanField_ELBO, "meanfield")])
+def test_elbo_grads_gamma_poisson_mask_subsample(emu, cls, tag):
+    g = load_npz("elbo_grad.npz")
+    torch.set_default_dtype(torch.float64)
+    data, counts = torch.as_tensor(g["data"]), torch.as_tensor(g["counts"])
+    mask = torch.as_tensor(g["mask"])
+    eps, ueps = torch.as_tensor(g["eps"]), torch.as_tensor(g["ueps"])
+    N = data.shape[0]
+
+    def model():
+        z = pyro.sample("z", dist.Normal(torch.tensor(0.0), torch.tensor(2.0)))
+        rate = pyro.sample("rate", dist.Gamma(torch.tensor(2.0), torch.tensor(0.5)))
+        with pyro.plate("data", 2 * N, subsample_size=N, dim=-1):
+            with poutine.mask(mask=mask):
+                pyro.sample("x", dist.Normal(z, torch.tensor(1.3)), obs=data)
+            pyro.sample("c", dist.Poisson(rate), obs=counts)
+
+    class Inject(poutine.Messenger):
+        def __init__(self, vals):
+            self.vals = vals
+
+        def _pyro_sample(self, msg):
+            if msg["name"] in self.vals:
+                msg["value"] = self.vals[msg["name"]]
+                msg["done"] = True
+
+    def guide():
+        loc = pyro.param("loc", torch.tensor(0.3))
+        scale = pyro.param("scale", torch.tensor(0.7), constraint=constraints.positive)
+        conc = pyro.param("conc", torch.tensor(3.0), constraint=constraints.positive)
+        grate = pyro.param("grate", torch.tensor(1.2), constraint=constraints.positive)
+        with Inject({"z": loc + eps * scale, "rate": conc / grate * (0.5 + ueps)}):
+            pyro.sample("z", dist.Normal(loc, scale))
+            pyro.sample("rate", dist.Gamma(conc, grate))
+
+    elbo = cls(num_particles=6, vectorize_particles=True, max_plate_nesting=1)
+    with poutine.trace(param_only=True) as cap:
+        loss = elbo.loss_and_grads(model, guide)
+    assert abs(loss - float(g[tag + ".loss"])) < 1e-8 * abs(float(g[tag + ".loss"]))
+    for name, site in cap.trace.nodes.items():
+        ref = torch.as_tensor(g["%s.grad.%s" % (tag, name)])
+        got = site["value"]._pyro_unconstrained_param.grad
+        assert torch.allclose(got, ref, atol=1e-7, rtol=1e-7), name
+
+
+def test_score_function_path_matches_reference_kat(emu):
+    """Non-reparameterised guide site -> general path with log_r (tests/infer/test_gradient.py
+    style): compare with an independent autograd computation of the surrogate."""
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(0)
+    data = torch.tensor([1.0, 0.0, 1.0, 1.0])
+    zs = torch.tensor([[1.0], [0.0], [1.0]])  # 3 particles
+
+    def model():
+        p = pyro.sample("z", dist.Bernoulli(probs=torch.tensor(0.4)))
+        with pyro.plate("d", 4):
+            pyro.sample("x", dist.Bernoulli(probs=0.2 + 0.6 * p), obs=data)  # p: [P, 1] -> [P, 4]
+
+    class Inject(poutine.Messenger):
+        def _pyro_sample(self, msg):
+            if msg["name"] == "z":
+                msg["value"] = zs
+                msg["done"] = True
+
+    def guide():
+        q = pyro.param("q", torch.tensor(0.3), constraint=constraints.unit_interval)
+        with Inject():
+            pyro.sample("z", dist.Bernoulli(probs=q))
+
+    elbo = Trace_ELBO(num_particles=3, vectorize_particles=True, max_plate_nesting=1)
+    with poutine.trace(param_only=True) as cap:
+        loss = elbo.loss_and_grads(model, guide)
+    got = cap.trace.nodes["q"]["value"]._pyro_unconstrained_param.grad
+    # independent computation
+    u = torch.tensor(0.3).logit().clone().requires_grad_(True)
+    q = torch.sigmoid(u)
+    B = torch.distributions.Bernoulli
+    lq = B(probs=q).log_prob(zs)                        # [3,1]
+    lpz = B(probs=torch.tensor(0.4)).log_prob(zs)
+    lpx = B(probs=0.2 + 0.6 * zs).log_prob(data)         # [3,4]
+    log_r = (lpz - lq).detach() + lpx.sum(-1, keepdim=True).detach()
+    surrogate = -((log_r * lq).sum()) / 3
+    surrogate.backward()
+    assert torch.allclose(got, u.grad, atol=1e-10)
+    elbo_val = (lpz + lpx.sum(-1, keepdim=True) - lq).sum() / 3
+    assert abs(loss + float(elbo_val)) < 1e-10
+
+
+def test_optimizer_checkpoint_roundtrip(emu, tmp_path):
+    """tests/optim/test_optim.py:372-437: save -> clear -> load -> identical trajectory."""
+    torch.set_default_dtype(torch.float64)
+    g = load_npz("svi_logistic.npz")
+    X, y = torch.as_tensor(g["X"]), torch.as_tensor(g["y"])
+    eps_w, eps_b = torch.as_tensor(g["eps_w"]), torch.as_tensor(g["eps_b"])
+    box = {"i": 0}
+
+    def guide(X, y):
+        with models.InjectNoise({"w": eps_w[box["i"]], "b": eps_b[box["i"]]}):
+            models.logistic_guide(X, y)
+
+    def make():
+        return SVI(models.logistic_model, guide, ClippedAdam({"lr": 0.01, "lrd": 0.9}),
+                   Trace_ELBO(num_particles=8, vectorize_particles=True, max_plate_nesting=1))
+    svi = make()
+    for i in range(2):
+        box["i"] = i
+        svi.step(X, y)
+    svi.optim.save(str(tmp_path / "opt.pt"))
+    pyro.get_param_store().save(str(tmp_path / "params.pt"))
+    state = svi.optim.get_state()
+    assert set(state) == {"w_loc", "w_scale", "b_loc", "b_scale"}
+    assert state["w_loc"]["state"][0]["step"] == 2
+    assert abs(state["w_loc"]["param_groups"][0]["lr"] - 0.01 * 0.9 ** 2) < 1e-15
+    ref = []
+    for i in range(2, 5):
+        box["i"] = i
+        ref.append(svi.step(X, y))
+    pyro.clear_param_store()
+    pyro.get_param_store().load(str(tmp_path / "params.pt"))
+    svi2 = make()
+    svi2.optim.load(str(tmp_path / "opt.pt"))
+    got = []
+    for i in range(2, 5):
+        box["i"] = i
+        got.append(svi2.step(X, y))
+    assert np.allclose(ref, got, rtol=1e-12)
+
+
+def test_adagrad_rmsprop_matches_reference(emu):
+    g = load_npz("optim.npz")
+    torch.set_default_dtype(torch.float64)
+    p = torch.as_tensor(g["p0_f64"]).clone().requires_grad_(True)
+    opt = AdagradRMSProp({"eta": 4.5, "t": 0.1})
+    pyro.get_param_store()._param_to_name[p] = "p"
+    for i, gr in enumerate(torch.as_tensor(g["grads_f64"])):
+        p.grad = gr.clone()
+        opt([p])
+        assert torch.allclose(p.detach(), torch.as_tensor(g["adagrad_rmsprop_f64"][i]), atol=1e-12)
+
+
+def test_lockstep_nuts_recovers_posterior_logistic(emu):
+    """The lockstep iterative tree driver (host logic + masks) on a 3-d logistic regression:
+    posterior means agree with the oracle's recursive NUTS within MC error
+    (tests/infer/mcmc/test_nuts.py::test_logistic_regression tolerance style)."""
+    from oracle import mcmc as omcmc
+    from pyro_b200.infer import MCMC, NUTS
+    from pyro_b200.infer.mcmc import LogisticPotential
+    torch.set_default_dtype(torch.float64)
+    g = load_npz("mcmc.npz")
+    X, y = torch.as_tensor(g["lr.X"]), torch.as_tensor(g["lr.y"])
+    kernel = NUTS(potential_fn=LogisticPotential(X, y, 1.0), native_small=False)
+    mc = MCMC(kernel, num_samples=150, warmup_steps=100, num_chains=6, seed=1)
+    mc.run()
+    s = mc.get_samples()["beta"]
+    chain = omcmc.NUTSChain(omcmc.logistic_potential(X, y, 1.0), 3, seed=2)
+    ref, _ = chain.run(torch.zeros(3, dtype=torch.float64), 150, 600)
+    assert torch.allclose(s.mean(0), ref.mean(0), atol=0.12)
+    assert torch.allclose(s.std(0), ref.std(0), atol=0.08)
+    d = mc.diagnostics()
+    assert float(d["beta"]["r_hat"].max()) < 1.1
+    assert kernel.leapfrog_count() > 0
+
+
+def test_trace_potential_matches_reference(emu):
+    """Generic model potential (model run under a chain plate, fused site scoring) == reference
+    potential + gradient at the golden points."""
+    from pyro_b200.infer.mcmc import TracePotential
+    torch.set_default_dtype(torch.float64)
+    g = load_npz("mcmc.npz")
+    y, sigma = torch.as_tensor(g["es.y"]), torch.as_tensor(g["es.sigma"])
+    Z = torch.as_tensor(g["es.Z"])
+    pot = TracePotential(models.eight_schools, (sigma, y), {}, num_chains=Z.shape[0])
+    # golden layout [mu, log tau, eta]; TracePotential orders sites as the model declares them
+    z = torch.cat([Z[:, pot_slice(pot, "mu", Z)], ], dim=1) if False else None
+    order = list(pot.sites)
+    cols = {"mu": Z[:, 0:1], "tau": Z[:, 1:2], "eta": Z[:, 2:]}
+    zz = torch.cat([cols[n] for n in order], dim=1)
+    U, G = pot.value_and_grad(zz)
+    assert torch.allclose(U, torch.as_tensor(g["es.U"]), atol=1e-9, rtol=1e-9)
+    ref_cols = {"mu": torch.as_tensor(g["es.G"])[:, 0:1], "tau": torch.as_tensor(g["es.G"])[:, 1:2],
+                "eta": torch.as_tensor(g["es.G"])[:, 2:]}
+    assert torch.allclose(G, torch.cat([ref_cols[n] for n in order], dim=1), atol=1e-9, rtol=1e-9)
+
+
+def pot_slice(pot, name, Z):
+    return pot.sites[name][0]
+
+
+def test_stats_match_reference():
+    from pyro_b200.infer.mcmc.stats import effective_sample_size, split_gelman_rubin
+    g = load_npz("mcmc.npz")
+    x = torch.as_tensor(g["stats.x"])
+    assert torch.allclose(split_gelman_rubin(x), torch.as_tensor(g["stats.rhat"]), atol=1e-10)
+    assert torch.allclose(effective_sample_size(x), torch.as_tensor(g["stats.neff"]), rtol=1e-8)
+
+
+def test_vectorised_adaptation_matches_reference_pieces():
+    from pyro_b200.infer.mcmc.adaptation import DualAveraging, WelfordDiag, build_adaptation_schedule
+    import math
+    g = load_npz("mcmc.npz")
+    for w in (5, 19, 100, 150, 200, 500, 1000):
+        assert [[a.start, a.end] for a in build_adaptation_schedule(w)] == g["sched.%d" % w].tolist()
+    da = DualAveraging(2, torch.device("cpu"), prox_center=math.log(10 * 0.3))
+    for gg, ref in zip(g["da.g"], g["da.x"]):
+        da.step(torch.full((2,), float(gg), dtype=torch.float64))
+        xt, xavg = da.get_state()
+        assert abs(float(xt[1]) - ref[0]) < 1e-12 and abs(float(xavg[0]) - ref[1]) < 1e-12
+    wf = WelfordDiag()
+    for s in torch.as_tensor(g["wf.samples"]):
+        wf.update(s.expand(3, -1))
+    assert torch.allclose(wf.get_covariance(True)[2], torch.as_tensor(g["wf.cov_reg"]), atol=1e-12)

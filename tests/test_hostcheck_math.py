@@ -1,0 +1,167 @@
+"""The element functors and the NUTS core that the CUDA kernels execute, run on the CPU
+(libpyro_b200_hostcheck.so) and checked against the reference goldens / the oracle.  These tests
+do not need a GPU; the -m gpu tier repeats the comparison through the real kernels."""
+import numpy as np
+import pytest
+import torch
+
+import hostcheck as H
+from conftest import load_npz
+from oracle import mcmc as omcmc
+
+FAMS = {"normal": 0, "bernoulli_logits": 1, "gamma": 2, "beta": 3, "poisson": 4, "cauchy": 5,
+        "halfcauchy": 6, "exponential": 7, "lognormal": 8, "halfnormal": 9, "bernoulli_probs": 10,
+        "uniform": 11}
+
+
+@pytest.mark.parametrize("key", sorted(FAMS))
+@pytest.mark.parametrize("dtype,tol,gtol", [(np.float64, 1e-12, 1e-10), (np.float32, 1e-5, 2e-4)])
+def test_functors_match_reference(key, dtype, tol, gtol):
+    g = load_npz("dist_random.npz")
+    v = g[key + ".value"]
+    ps = []
+    i = 0
+    while key + ".p%d" % i in g:
+        ps.append(g[key + ".p%d" % i])
+        i += 1
+    lp, dx, dp = H.eval_family(FAMS[key], v, ps, dtype)
+    ref = g[key + ".lp"]
+    # tolerance: |d| <= tol * max(1, |lp|)  (reference bar: atol 1e-5, tests/common.py:246-248)
+    assert np.all(np.abs(lp - ref) <= tol * np.maximum(1, np.abs(ref)))
+    if key + ".dvalue" in g:
+        r = g[key + ".dvalue"]
+        assert np.all(np.abs(dx - r) <= gtol * np.maximum(1, np.abs(r)))
+    for k in range(len(ps)):
+        r = g[key + ".dp%d" % k]
+        assert np.all(np.abs(dp[k] - r) <= gtol * np.maximum(1, np.abs(r))), k
+
+
+def test_kl_functors():
+    g = load_npz("kl.npz")
+    for name, fam in (("normal", 12), ("gamma", 13)):
+        ps = [g["%s.p%d" % (name, i)] for i in range(4)]
+        lp, _, dp = H.eval_family(fam, None, ps)
+        assert np.allclose(lp, g[name + ".kl"], atol=1e-12, rtol=1e-12)
+        for k in range(4):
+            # torch's float64 polygamma(1) (in the golden) is only ~1e-9 accurate
+            assert np.allclose(dp[k], g["%s.dp%d" % (name, k)], atol=1e-7, rtol=1e-7)
+
+
+def test_digamma_special_values():
+    L = H.lib()
+    for x in [-2.5, -0.3, 1e-8, 0.5, 1.0, 5.9, 6.0, 100.0, 1e6]:
+        ref = float(torch.digamma(torch.tensor(x, dtype=torch.float64)))
+        assert abs(L.b2h_digamma(x) - ref) <= 1e-12 * max(1, abs(ref))
+    assert L.b2h_digamma(0.0) == -np.inf
+
+
+def test_native_potentials_match_reference():
+    g = load_npz("mcmc.npz")
+    for z, u_ref, g_ref in zip(g["es.Z"], g["es.U"], g["es.G"]):
+        U, gr = H.potential_hier_normal(g["es.y"], g["es.sigma"], 10.0, 25.0, z)
+        assert abs(U - u_ref) < 1e-10 * max(1, abs(u_ref))
+        assert np.allclose(gr, g_ref, atol=1e-10, rtol=1e-10)
+    for b, u_ref, g_ref in zip(g["lr.B"], g["lr.U"], g["lr.G"]):
+        U, gr = H.potential_logistic(g["lr.X"], g["lr.y"], 1.0, b)
+        assert abs(U - u_ref) < 1e-10 * max(1, abs(u_ref))
+        assert np.allclose(gr, g_ref, atol=1e-10, rtol=1e-10)
+
+
+def _iterative_turning(rs):
+    """U-turn decisions of the iterative checkpoint scheme (nuts_core.cuh) for a momentum sequence."""
+    n = len(rs)
+    rsub = np.zeros_like(rs[0])
+    rck, sck = {}, {}
+    for leaf in range(n):
+        rsub = rsub + rs[leaf]
+        idx_max = bin(leaf >> 1).count("1")
+        if leaf % 2 == 0:
+            rck[idx_max], sck[idx_max] = rs[leaf].copy(), rsub.copy()
+        else:
+            t = leaf
+            nblk = 0
+            while t & 1:
+                nblk += 1
+                t >>= 1
+            for k in range(idx_max, idx_max - nblk, -1):
+                blk = rsub - sck[k] + rck[k]
+                rho = blk - 0.5 * (rck[k] + rs[leaf])
+                if rck[k] @ rho <= 0 or rs[leaf] @ rho <= 0:
+                    return leaf
+    return None
+
+
+def _recursive_turning(rs, lo, hi):
+    """First leaf index at which the reference recursion (nuts.py:250-365) stops for leaves [lo,hi)."""
+    if hi - lo == 1:
+        return None
+    mid = (lo + hi) // 2
+    a = _recursive_turning(rs, lo, mid)
+    if a is not None:
+        return a
+    b = _recursive_turning(rs, mid, hi)
+    if b is not None:
+        return b
+    rsum = np.sum(rs[lo:hi], axis=0)
+    rho = rsum - 0.5 * (rs[lo] + rs[hi - 1])
+    if rs[lo] @ rho <= 0 or rs[hi - 1] @ rho <= 0:
+        return hi - 1
+    return None
+
+
+def test_iterative_uturn_equals_recursive():
+    rng = np.random.default_rng(0)
+    hits = 0
+    for trial in range(300):
+        depth = rng.integers(1, 7)
+        n = 1 << depth
+        # momenta drifting in direction so that turns happen at varied places
+        base = rng.standard_normal(3)
+        rs = [base + 0.9 * rng.standard_normal(3) * (1 + 0.3 * i) for i in range(n)]
+        rs = np.asarray(rs)
+        a, b = _iterative_turning(rs), _recursive_turning(rs, 0, n)
+        assert a == b
+        hits += a is not None
+    assert 30 < hits < 290
+
+
+def test_device_nuts_core_recovers_reference_posterior():
+    """nuts_core.cuh (the code nuts_small_kernel runs per chain), executed on the CPU for
+    eight_schools: posterior moments must agree with the reference's long run
+    (golden es.long.*), in the spirit of tests/infer/mcmc/test_nuts.py tolerances."""
+    g = load_npz("mcmc.npz")
+    y, sigma = g["es.y"], g["es.sigma"]
+    C, D = 8, 10
+    rng = np.random.default_rng(1)
+    z = rng.uniform(-2, 2, (C, D))
+    U = np.zeros(C)
+    gr = np.zeros((C, D))
+    for c in range(C):
+        U[c], gr[c] = H.potential_hier_normal(y, sigma, 10.0, 25.0, z[c])
+    eps = np.full(C, 0.1)
+    minv = np.ones((C, D))
+    # crude warm-up: a few hundred transitions at small step, then sample with a tuned step
+    H.nuts_hier_normal(y, sigma, 10.0, 25.0, z, U, gr, eps, minv, 200, seed=3)
+    eps = np.full(C, 0.35)
+    samples, acc, depth, div, steps = H.nuts_hier_normal(y, sigma, 10.0, 25.0, z, U, gr, eps, minv, 1500, seed=4)
+    mu = samples[..., 0].reshape(-1)
+    tau = np.exp(samples[..., 1]).reshape(-1)
+    eta = samples[..., 2:].reshape(-1, 8)
+    assert abs(mu.mean() - float(g["es.long.mu.mean"][0])) < 0.5
+    assert abs(tau.mean() - float(g["es.long.tau.mean"][0])) < 0.7
+    assert np.max(np.abs(eta.mean(0) - g["es.long.eta.mean"])) < 0.12
+    assert 0.5 < acc.mean() < 0.99
+    assert steps.min() >= 1 and depth.max() <= 10
+    # tree sizes: a transition of depth d that was not cut short has 2^d - 1 leapfrogs
+    full = (div == 0)
+    assert np.all(steps[full] <= (1 << depth[full].clip(max=10)) * 2)
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors: zero key/counter, and the
+    pi/e digits test)."""
+    import ctypes
+    out = np.zeros(4, np.uint32)
+    H.lib().b2h_philox(ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0), 4,
+                       out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    assert [hex(v) for v in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
