@@ -83,14 +83,22 @@ __global__ void __launch_bounds__(256) glm_bernoulli_kernel(const float* __restr
     for (int r = rg; r < rows; r += kGlmRowGroups) {
       const float4* xr = reinterpret_cast<const float4*>(xt + r * D);
       float xv[D];
-      float l = bias;
 #pragma unroll
       for (int q = 0; q < D / 4; ++q) {
         const float4 v = xr[q];
         xv[4 * q + 0] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
       }
+      // four independent partial dot products: a single accumulator is a chain of D dependent
+      // FMAs (4 cycles each), which 4 resident warps per scheduler cannot hide
+      float l0 = bias, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-      for (int d = 0; d < D; ++d) l = fmaf(xv[d], w[d], l);
+      for (int d = 0; d < D; d += 4) {
+        l0 = fmaf(xv[d + 0], w[d + 0], l0);
+        l1 = fmaf(xv[d + 1], w[d + 1], l1);
+        l2 = fmaf(xv[d + 2], w[d + 2], l2);
+        l3 = fmaf(xv[d + 3], w[d + 3], l3);
+      }
+      const float l = (l0 + l1) + (l2 + l3);
       const float yn = ys[buf][r];
       // softplus / sigmoid sharing one exp (fast intrinsics: ex2.approx / lg2.approx / rcp)
       const float e = __expf(-fabsf(l));

@@ -408,6 +408,18 @@ class Bernoulli(_Elementwise):
 # ---------------------------------------------------------------------------------------------
 # event families
 # ---------------------------------------------------------------------------------------------
+def _event_contiguous(t, event_ndim):
+    """The event kernels index the trailing event dims as one dense row-major block."""
+    if t is None or event_ndim == 0:
+        return t
+    expect = 1
+    for d in range(1, event_ndim + 1):
+        if t.shape[-d] != 1 and t.stride(-d) != expect:
+            return t.contiguous()
+        expect *= t.shape[-d]
+    return t
+
+
 class _EventFamily(Distribution):
     family = None
 
@@ -433,6 +445,7 @@ class Dirichlet(_EventFamily):
     has_rsample = True
 
     def __init__(self, concentration, validate_args=None):
+        concentration = _event_contiguous(concentration, 1)
         self.concentration = concentration
         super().__init__(concentration.shape[:-1], concentration.shape[-1:])
 
@@ -441,11 +454,13 @@ class Dirichlet(_EventFamily):
         return torch.distributions.Dirichlet(c, validate_args=False)
 
     def log_prob(self, value):
+        value = _event_contiguous(value, 1)
         bshape = torch.broadcast_shapes(self.batch_shape, value.shape[:-1])
         return _ops.log_prob_op(self.family, value, [self.concentration], bshape,
                                 event_size=self.event_shape[0])
 
     def _fused_sum(self, value, mask, scale, weight, sum_coeff, unit=True):
+        value = _event_contiguous(value, 1)
         bshape = torch.broadcast_shapes(self.batch_shape, value.shape[:-1])
         return _ops.fused_site_sum(self.family, value, [self.concentration], bshape, mask=mask,
                                    scale=scale, weight=weight, sum_coeff=sum_coeff,
@@ -466,6 +481,7 @@ class Categorical(_EventFamily):
             # normalised, clamped probabilities.  The kernel normalises logits itself.
             eps = torch.finfo(probs.dtype).eps
             logits = torch.log((probs / probs.sum(-1, keepdim=True)).clamp(min=eps, max=1 - eps))
+        logits = _event_contiguous(logits, 1)
         self._logits_raw = logits
         self._num_events = logits.shape[-1]
         super().__init__(logits.shape[:-1])
@@ -534,8 +550,8 @@ class MultivariateNormal(_EventFamily):
             Id = torch.eye(precision_matrix.shape[-1], dtype=precision_matrix.dtype,
                            device=precision_matrix.device)
             scale_tril = torch.linalg.solve_triangular(L_inv, Id, upper=False)
-        self.loc = loc
-        self.scale_tril = scale_tril
+        self.loc = _event_contiguous(loc, 1)
+        self.scale_tril = _event_contiguous(scale_tril, 2)
         batch = torch.broadcast_shapes(loc.shape[:-1], scale_tril.shape[:-2])
         super().__init__(batch, loc.shape[-1:])
 
@@ -546,11 +562,13 @@ class MultivariateNormal(_EventFamily):
             validate_args=False)
 
     def log_prob(self, value):
+        value = _event_contiguous(value, 1)
         bshape = torch.broadcast_shapes(self.batch_shape, value.shape[:-1])
         return _ops.log_prob_op(self.family, value, [self.loc, self.scale_tril], bshape,
                                 event_size=self.event_shape[0])
 
     def _fused_sum(self, value, mask, scale, weight, sum_coeff, unit=True):
+        value = _event_contiguous(value, 1)
         bshape = torch.broadcast_shapes(self.batch_shape, value.shape[:-1])
         return _ops.fused_site_sum(self.family, value, [self.loc, self.scale_tril], bshape,
                                    mask=mask, scale=scale, weight=weight, sum_coeff=sum_coeff,
