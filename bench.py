@@ -129,10 +129,15 @@ def time_steps(svi, args, steps, warmup, device, flush, sync_each=True):
 
 
 def kernel_time_ms(fn, iters, flush):
-    """Average device time of one launch sequence ``fn`` (CUDA events on the launching stream)."""
+    """Average device time of one launch sequence ``fn``: CUDA events on the launching stream
+    around a replay of the sequence captured in a CUDA graph (so the Python wrapper cost of the
+    call is not inside the interval); L2 flushed between replays, outside the interval."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
     tot = 0.0
     for _ in range(iters):
         if flush is not None:
@@ -140,7 +145,7 @@ def kernel_time_ms(fn, iters, flush):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        graph.replay()
         e1.record()
         e1.synchronize()
         tot += e0.elapsed_time(e1)
@@ -193,6 +198,70 @@ def cpu_reference(steps, warmup, threads=None, n=N_ROWS):
     return steps / dt, dt / steps * 1e3, threads, loss
 
 
+def nuts_section(dev, quick=False):
+    """NUTS leapfrog-steps/s (second half of BASELINE.json's metric), reported as extra keys:
+    config 1 (eight_schools, 4 chains, 200+200) and the same model with 1024 vectorised chains
+    through the whole-transition kernel; config 4's model (hierarchical Normal, J=1e6) through the
+    lockstep tree driver with the fused potential; and the oracle's CPU restatement of the
+    reference sampler for config 1 as the CPU baseline."""
+    import numpy as np
+    from oracle import mcmc as omcmc
+    from pyro_b200.infer import MCMC, NUTS
+    from pyro_b200.infer.mcmc import HierNormalPotential
+    out = {}
+    y = torch.tensor([28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0], device=dev)
+    sigma = torch.tensor([15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0], device=dev)
+    for chains in (4, 1024):
+        k = NUTS(potential_fn=HierNormalPotential(y, sigma, 10.0, 25.0))
+        mc = MCMC(k, num_samples=200, warmup_steps=200, num_chains=chains, seed=0)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mc.run()
+        e1.record()
+        e1.synchronize()
+        n = k.leapfrog_count()
+        s = mc.get_samples()
+        out["eight_schools_%dchains" % chains] = {
+            "leapfrogs": n, "seconds": round(e0.elapsed_time(e1) * 1e-3, 4),
+            "leapfrog_per_sec": round(n / (e0.elapsed_time(e1) * 1e-3), 1),
+            "mu_mean": round(float(s["mu"].mean()), 3), "tau_mean": round(float(s["tau"].mean()), 3),
+            "path": "b2_nuts_small: whole transitions on device, 1 thread per chain; warm-up adaptation between launches"}
+    # config 4 model at J = 1e6
+    J, C = 1_000_000, (8 if quick else 32)
+    g = torch.Generator().manual_seed(0)
+    sig = (5 + 15 * torch.rand(J, generator=g)).to(dev)
+    yy = (5 + 3 * torch.randn(J, generator=g)).to(dev) + sig * torch.randn(J, generator=g).to(dev)
+    k = NUTS(potential_fn=HierNormalPotential(yy, sig, 10.0, 25.0), native_small=False, max_tree_depth=6)
+    mc = MCMC(k, num_samples=4, warmup_steps=6, num_chains=C, seed=0)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mc.run()
+    e1.record()
+    e1.synchronize()
+    n = k.leapfrog_count()
+    out["hier_normal_J1e6_%dchains" % C] = {
+        "leapfrogs": n, "seconds": round(e0.elapsed_time(e1) * 1e-3, 3),
+        "leapfrog_per_sec": round(n / (e0.elapsed_time(e1) * 1e-3), 1),
+        "algorithmic_GBps": round(n * 16e6 / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1),
+        "path": "lockstep iterative tree (torch glue) + b2_potential_grad + b2_leapfrog_* kernels; "
+                "10 transitions, max_tree_depth 6 (bounded sample of config 4)"}
+    # CPU baseline: oracle restatement of the reference sampler, config 1, one chain
+    torch.set_num_threads(1)
+    U = omcmc.eight_schools_potential(y.double().cpu(), sigma.double().cpu())
+    chain = omcmc.NUTSChain(U, 10, seed=0)
+    t0 = time.perf_counter()
+    chain.run(torch.zeros(10, dtype=torch.float64), 100, 100)
+    dt = time.perf_counter() - t0
+    out["cpu_baseline"] = {"leapfrog_per_sec": round(chain.num_leapfrogs / dt, 1), "cores": 1, "kind": "port",
+                           "sample": "eight_schools, 1 chain, 100 warm-up + 100 samples, oracle/mcmc.py NUTSChain "
+                                     "(reference Pyro itself measured 522-541 leapfrog/s in the build container, "
+                                     "tests/golden/make_golden.py)"}
+    torch.set_num_threads(os.cpu_count())
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,6 +272,7 @@ def main():
                     help="ours: site | site+graph | glm | glm+graph (default)")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-nuts", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -338,6 +408,11 @@ def main():
                                "sample": "%d full-size steps (N=1e6, P=64) of oracle/svi.py LogisticSVIMatmul "
                                          "(CPU restatement of reference SVI.step, torch CPU ops, all host threads)" % a.cpu_steps,
                                "ms_per_step": round(cms, 2)}
+        if not a.no_nuts:
+            try:
+                out["nuts"] = nuts_section(dev)
+            except Exception as e:  # pragma: no cover
+                out["nuts"] = {"error": repr(e)[:300]}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

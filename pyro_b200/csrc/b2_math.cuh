@@ -135,7 +135,9 @@ B2_HD float fast_log(float x) {
 B2_HD double fast_log(double x) { return log(x); }
 B2_HD float fast_rcp(float x) {
 #ifdef __CUDA_ARCH__
-  return __frcp_rn(x);
+  float r;  // MUFU.RCP (1 ulp); __frcp_rn would add a Newton step and a denormal slow path
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #else
   return 1.0f / x;
 #endif

@@ -134,15 +134,21 @@ __global__ void __launch_bounds__(256) glm_bernoulli_kernel(const float* __restr
 }
 
 // second stage: fixed-order sum over the CTAs' partials; applies weight / scale.
-// One thread per entry of the [P, D+2] table; consecutive threads read consecutive addresses.
-__global__ void glm_finish_kernel(const float* __restrict__ partials, int nblocks, int P, int D,
-                                  double scale, double weight, float* __restrict__ sum_p,
-                                  float* __restrict__ out_dW, float* __restrict__ out_db) {
+// One WARP per entry of the [P, D+2] table: lanes stride over the CTAs (L2-resident partials),
+// then a shuffle tree -- a thread-per-entry loop over ~300 dependent loads took 35 us.
+__global__ void __launch_bounds__(256) glm_finish_kernel(const float* __restrict__ partials,
+                                                         int nblocks, int P, int D, double scale,
+                                                         double weight, float* __restrict__ sum_p,
+                                                         float* __restrict__ out_dW,
+                                                         float* __restrict__ out_db) {
   const int total = P * (D + 2);
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (e >= total) return;
   double s = 0.0;
-  for (int bl = 0; bl < nblocks; ++bl) s += (double)partials[(int64_t)bl * total + e];
+  for (int bl = lane; bl < nblocks; bl += 32) s += (double)partials[(int64_t)bl * total + e];
+  s = warp_sum(s);
+  if (lane != 0) return;
   const int p = e / (D + 2), d = e - p * (D + 2);
   if (d < D) {
     if (out_dW) out_dW[(int64_t)p * D + d] = (float)(weight * scale * s);
@@ -207,7 +213,7 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   }
   float* sum_p = out_sum_p ? out_sum_p : partials + (size_t)gx * P * (D + 2);
   const int total = P * (D + 2);
-  glm_finish_kernel<<<(total + 127) / 128, 128, 0, s>>>(partials, gx, P, D, scale, weight, sum_p,
+  glm_finish_kernel<<<(total + 7) / 8, 256, 0, s>>>(partials, gx, P, D, scale, weight, sum_p,
                                                         out_dW, out_db);
   int nl = 2;
   if (out_total) {

@@ -65,13 +65,177 @@ __device__ __forceinline__ void finish_outputs(const SiteArgs& a, int k, double 
 // ------------------------------------------------------------------------------------------------
 // Vector kernel.  Block = 256 threads arranged TX x TY (TX = 1 << tx_log2 column-vector lanes,
 // TY rows).  grid.x tiles column vectors, grid.y tiles rows; both grid-strided.
+// Inner loop: U vectors per operand are loaded back to back (no predicates, no per-element
+// branches), then evaluated, then stored; a one-vector tail loop handles the remainder.
+// An operand is either a vector along the columns (column stride 1) or one scalar per row
+// (column stride 0, loaded once per row).  MASKUP adds the optional mask / upstream operands.
 // ------------------------------------------------------------------------------------------------
-template <int FAM, typename T, bool GRAD>
-__global__ void __launch_bounds__(256) site_vec_kernel(const SiteArgs a) {
+template <int FAM, typename T, bool GRAD, bool MASKUP, int NVEC>
+struct VecBody {
+  static constexpr int NP = FamilyTraits<FAM>::kNumParams;
+  static constexpr bool HASV = FamilyTraits<FAM>::kHasValue;
+  static constexpr int V = VecOf<T>::N;
+  static constexpr int NRED = GRAD ? 2 + NP : 1;
+
+  // operand classes, fixed for the launch: vector along columns (column stride 1) or one scalar
+  // per row; row-invariant (row stride 0) vectors are loaded once per column chunk and reused
+  // for every row (e.g. the observations y[N] scored against logits[P, N])
+  bool x_vec, p_vec[NP], x_inv, p_inv[NP];
+  T scale, f0;
+  // per-row state
+  const T* xr;
+  const T* pr[NP];
+  const T* ur;
+  const uint8_t* mr;
+  T* lpr;
+  T* gxr;
+  T* gpr[NP];
+  T xs, ps[NP], us;
+  bool u_vec, m_vec;
+  // operand registers (invariant ones persist across rows)
+  Pack<T> xv[NVEC], pv[NVEC][NP];
+
+  __device__ __forceinline__ void load_invariant(const T* xbase, const T* const (&pbase)[NP],
+                                                 int64_t cv, int64_t cstep) {
+#pragma unroll
+    for (int u = 0; u < NVEC; ++u) {
+      const int64_t c = (cv + u * cstep) * V;
+      if (HASV && x_vec && x_inv) xv[u] = ld_keep(xbase + c);
+#pragma unroll
+      for (int k = 0; k < NP; ++k)
+        if (p_vec[k] && p_inv[k]) pv[u][k] = ld_keep(pbase[k] + c);
+    }
+  }
+
+  __device__ __forceinline__ void run(int64_t cv, int64_t cstep, T (&acc)[NRED]) {
+    Pack<T> uv[NVEC];
+    uint32_t mbits[NVEC];
+#pragma unroll
+    for (int u = 0; u < NVEC; ++u) {
+      const int64_t c = (cv + u * cstep) * V;
+      if (HASV && x_vec && !x_inv) xv[u] = ld_stream(xr + c);
+#pragma unroll
+      for (int k = 0; k < NP; ++k)
+        if (p_vec[k] && !p_inv[k]) pv[u][k] = ld_stream(pr[k] + c);
+      if (MASKUP) {
+        if (ur && u_vec) uv[u] = ld_stream(ur + c);
+        mbits[u] = 0xffffffffu;
+        if (mr) {
+          mbits[u] = 0;
+#pragma unroll
+          for (int j = 0; j < V; ++j) mbits[u] |= (mr[m_vec ? c + j : 0] != 0 ? 1u : 0u) << j;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NVEC; ++u) {
+      const int64_t c = (cv + u * cstep) * V;
+      Pack<T> lpv, gxv, gpv[NP];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        T pl[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) pl[k] = p_vec[k] ? pv[u][k].v[j] : ps[k];
+        const T xe = HASV ? (x_vec ? xv[u].v[j] : xs) : (T)0;
+        ElemOut<T> o;
+        Eval<FAM, T, GRAD>::run(xe, pl, o);
+        T slp = o.lp * scale;
+        T f = f0;
+        if (MASKUP) {
+          const bool m = (mbits[u] >> j) & 1u;
+          slp = m ? slp : (T)0;
+          f = m ? f0 : (T)0;
+          if (ur) f *= u_vec ? uv[u].v[j] : us;
+        }
+        lpv.v[j] = slp;
+        acc[0] += slp;
+        if (GRAD) {
+          T gxe = f * o.dx;
+          if (MASKUP) gxe = (f == (T)0) ? (T)0 : gxe;  // masked-out NaNs must not leak
+          gxv.v[j] = gxe;
+          acc[1] += gxe;
+#pragma unroll
+          for (int k = 0; k < NP; ++k) {
+            T g = f * o.dp[k];
+            if (MASKUP) g = (f == (T)0) ? (T)0 : g;
+            gpv[k].v[j] = g;
+            acc[2 + k] += g;
+          }
+        }
+      }
+      if (lpr) st_stream(lpr + c, lpv);
+      if (GRAD) {
+        if (gxr) st_stream(gxr + c, gxv);
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+          if (gpr[k]) st_stream(gpr[k] + c, gpv[k]);
+      }
+    }
+  }
+
+  // all rows of this thread for one column chunk
+  __device__ __forceinline__ void chunk(const SiteArgs& a, int64_t cv, int64_t cstep, int ty, int TY,
+                                        T (&acc)[NRED]) {
+    const T* xbase = HASV ? reinterpret_cast<const T*>(a.x.ptr) : nullptr;
+    const T* pbase[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) pbase[k] = reinterpret_cast<const T*>(a.p[k].ptr);
+    load_invariant(xbase, pbase, cv, cstep);
+    for (int64_t r = (int64_t)blockIdx.y * TY + ty; r < a.R; r += (int64_t)gridDim.y * TY) {
+      xr = HASV ? xbase + r * a.x.st[0] : nullptr;
+      xs = (HASV && !x_vec) ? __ldg(xr) : (T)0;
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        pr[k] = pbase[k] + r * a.p[k].st[0];
+        ps[k] = p_vec[k] ? (T)0 : __ldg(pr[k]);
+      }
+      if (MASKUP) {
+        ur = a.up.ptr ? reinterpret_cast<const T*>(a.up.ptr) + r * a.up.st[0] : nullptr;
+        us = (ur && !u_vec) ? __ldg(ur) : (T)1;
+        mr = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr) + r * a.mask.st[0] : nullptr;
+      }
+      lpr = a.lp.mode == 1 ? reinterpret_cast<T*>(a.lp.ptr) + r * a.lp.st[0] : nullptr;
+      gxr = (GRAD && a.gx.mode == 1) ? reinterpret_cast<T*>(a.gx.ptr) + r * a.gx.st[0] : nullptr;
+#pragma unroll
+      for (int k = 0; k < NP; ++k)
+        gpr[k] = (GRAD && a.gp[k].mode == 1) ? reinterpret_cast<T*>(a.gp[k].ptr) + r * a.gp[k].st[0] : nullptr;
+      run(cv, cstep, acc);
+    }
+  }
+
+  __device__ __forceinline__ void init(const SiteArgs& a) {
+    x_vec = a.x.st[1] == 1;
+    x_inv = a.x.st[0] == 0 && a.R > 1;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      p_vec[k] = a.p[k].st[1] == 1;
+      p_inv[k] = a.p[k].st[0] == 0 && a.R > 1;
+    }
+    scale = (T)a.scale;
+    f0 = (T)(a.weight * a.scale);
+    ur = nullptr;
+    mr = nullptr;
+    us = (T)1;
+    u_vec = MASKUP && a.up.st[1] == 1;
+    m_vec = MASKUP && a.mask.st[1] == 1;
+  }
+};
+
+// Vectors in flight per operand per thread.  Forward-only fp32 kernels are pure streams: 4 vectors
+// (measured 87% of the HBM copy peak for Normal).  Kernels that also write gradients carry more
+// live registers; 2 vectors keep them at 3 resident CTAs per SM.
+template <typename T, bool GRAD>
+struct VecUnroll {
+  static constexpr int U = (sizeof(T) == 4 && !GRAD) ? 4 : 2;
+  static constexpr int kMinBlocks = (sizeof(T) == 8 && GRAD) ? 2 : 3;
+};
+
+// Loop nest: column chunks outermost (U vectors per thread, then a one-vector tail), rows inside.
+template <int FAM, typename T, bool GRAD, bool MASKUP>
+__global__ void __launch_bounds__(256, VecUnroll<T, GRAD>::kMinBlocks) site_vec_kernel(const SiteArgs a) {
   constexpr int NP = FamilyTraits<FAM>::kNumParams;
-  constexpr bool HASV = FamilyTraits<FAM>::kHasValue;
   constexpr int V = VecOf<T>::N;
-  constexpr int U = 2;  // vectors in flight per operand
+  constexpr int U = VecUnroll<T, GRAD>::U;
   constexpr int NRED = GRAD ? 2 + NP : 1;
 
   const int TX = 1 << a.tx_log2;
@@ -81,112 +245,20 @@ __global__ void __launch_bounds__(256) site_vec_kernel(const SiteArgs a) {
   const int64_t CV = a.C / V;
   const int64_t cstep = (int64_t)gridDim.x * TX;
 
-  const T* __restrict__ xp = reinterpret_cast<const T*>(a.x.ptr);
-  const T* __restrict__ up = reinterpret_cast<const T*>(a.up.ptr);
-  const uint8_t* __restrict__ mp = reinterpret_cast<const uint8_t*>(a.mask.ptr);
-  T* __restrict__ lpo = reinterpret_cast<T*>(a.lp.ptr);
-  const bool want_lp = a.lp.mode == 1;
-  const T f0 = (T)(a.weight * a.scale);
-  const T scale = (T)a.scale;
-
   T acc[NRED];
 #pragma unroll
   for (int k = 0; k < NRED; ++k) acc[k] = (T)0;
 
-  for (int64_t r = (int64_t)blockIdx.y * TY + ty; r < a.R; r += (int64_t)gridDim.y * TY) {
-    // per-row bases
-    const T* xr = HASV ? xp + r * a.x.st[0] : nullptr;
-    const T* pr[NP];
-#pragma unroll
-    for (int k = 0; k < NP; ++k) pr[k] = reinterpret_cast<const T*>(a.p[k].ptr) + r * a.p[k].st[0];
-    const T* ur = up ? up + r * a.up.st[0] : nullptr;
-    const uint8_t* mr = mp ? mp + r * a.mask.st[0] : nullptr;
-
-    for (int64_t cv0 = (int64_t)blockIdx.x * TX + tx; cv0 < CV; cv0 += cstep * U) {
-      Pack<T> xv[U], pv[U][NP], uv[U];
-      uint8_t mv[U][V];
-      bool ok[U];
-      // ---- issue every load first -----------------------------------------------------------
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t c = (cv0 + u * cstep) * V;
-        ok[u] = (cv0 + u * cstep) < CV;
-        if (ok[u]) {
-          if (HASV) {
-            if (a.x.st[1] == 1) {
-              xv[u] = (a.x.st[0] != 0 || a.R == 1) ? ld_stream(xr + c) : ld_keep(xr + c);
-            } else {
-              const T s = __ldg(xr);
-#pragma unroll
-              for (int j = 0; j < V; ++j) xv[u].v[j] = s;
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < NP; ++k) {
-            if (a.p[k].st[1] == 1) {
-              pv[u][k] = (a.p[k].st[0] != 0 || a.R == 1) ? ld_stream(pr[k] + c) : ld_keep(pr[k] + c);
-            } else {
-              const T s = __ldg(pr[k]);
-#pragma unroll
-              for (int j = 0; j < V; ++j) pv[u][k].v[j] = s;
-            }
-          }
-          if (ur) {
-            if (a.up.st[1] == 1) {
-              uv[u] = ld_stream(ur + c);
-            } else {
-              const T s = __ldg(ur);
-#pragma unroll
-              for (int j = 0; j < V; ++j) uv[u].v[j] = s;
-            }
-          }
-          if (mr) {
-#pragma unroll
-            for (int j = 0; j < V; ++j) mv[u][j] = mr[a.mask.st[1] == 1 ? c + j : 0];
-          }
-        }
-      }
-      // ---- compute + store ------------------------------------------------------------------
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!ok[u]) continue;
-        const int64_t c = (cv0 + u * cstep) * V;
-        Pack<T> lpv, gxv, gpv[NP];
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-          T pl[NP > 0 ? NP : 1];
-#pragma unroll
-          for (int k = 0; k < NP; ++k) pl[k] = pv[u][k].v[j];
-          ElemOut<T> o;
-          Eval<FAM, T, GRAD>::run(HASV ? xv[u].v[j] : (T)0, pl, o);
-          const bool m = mr ? (mv[u][j] != 0) : true;
-          const T slp = m ? o.lp * scale : (T)0;
-          lpv.v[j] = slp;
-          acc[0] += slp;
-          if (GRAD) {
-            T f = m ? f0 : (T)0;
-            if (ur) f *= uv[u].v[j];
-            const T gxe = m ? f * o.dx : (T)0;
-            gxv.v[j] = gxe;
-            acc[1] += gxe;
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-              const T g = m ? f * o.dp[k] : (T)0;
-              gpv[k].v[j] = g;
-              acc[2 + k] += g;
-            }
-          }
-        }
-        if (want_lp) st_stream(lpo + r * a.lp.st[0] + c, lpv);
-        if (GRAD) {
-          if (a.gx.mode == 1) st_stream(reinterpret_cast<T*>(a.gx.ptr) + r * a.gx.st[0] + c, gxv);
-#pragma unroll
-          for (int k = 0; k < NP; ++k)
-            if (a.gp[k].mode == 1)
-              st_stream(reinterpret_cast<T*>(a.gp[k].ptr) + r * a.gp[k].st[0] + c, gpv[k]);
-        }
-      }
-    }
+  int64_t cv = (int64_t)blockIdx.x * TX + tx;
+  {
+    VecBody<FAM, T, GRAD, MASKUP, U> body;
+    body.init(a);
+    for (; cv + (U - 1) * cstep < CV; cv += U * cstep) body.chunk(a, cv, cstep, ty, TY, acc);
+  }
+  {
+    VecBody<FAM, T, GRAD, MASKUP, 1> tail;
+    tail.init(a);
+    for (; cv < CV; cv += cstep) tail.chunk(a, cv, cstep, ty, TY, acc);
   }
 
   __shared__ double smem[NRED * 32];
@@ -270,18 +342,23 @@ template <int FAM, typename T, bool GRAD>
 int launch_site(const SiteArgs& a, bool vec, cudaStream_t stream) {
   if (vec) {
     constexpr int V = VecOf<T>::N;
+    constexpr int U = VecUnroll<T, GRAD>::U;
     const int64_t CV = a.C / V;
     const int TX = 1 << a.tx_log2, TY = 256 / TX;
-    int64_t gx = (CV + (int64_t)TX * 2 - 1) / ((int64_t)TX * 2);
+    // enough CTAs for ~4 waves of resident blocks; each thread then owns >= U vectors per row
+    int64_t gx = (CV + (int64_t)TX * U - 1) / ((int64_t)TX * U);
     int64_t gy = (a.R + TY - 1) / TY;
-    const int64_t target = (int64_t)kNumSMs * 8;
+    const int64_t target = (int64_t)kNumSMs * 12;
     if (gx > target) gx = target;
     int64_t gy_cap = target / gx;
     if (gy_cap < 1) gy_cap = 1;
     if (gy > gy_cap) gy = gy_cap;
     if (gy > 65535) gy = 65535;
     dim3 grid((unsigned)gx, (unsigned)gy, 1);
-    site_vec_kernel<FAM, T, GRAD><<<grid, 256, 0, stream>>>(a);
+    if (a.mask.ptr || a.up.ptr)
+      site_vec_kernel<FAM, T, GRAD, true><<<grid, 256, 0, stream>>>(a);
+    else
+      site_vec_kernel<FAM, T, GRAD, false><<<grid, 256, 0, stream>>>(a);
   } else {
     int64_t blocks = (a.n + 255) / 256;
     const int64_t target = (int64_t)kNumSMs * 8;
