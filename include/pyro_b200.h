@@ -87,6 +87,8 @@ typedef struct {
 
 /* flags for b2_site_score */
 #define B2_FLAG_ACCUMULATE_SUM 1 /* out_sum += coeff*sum instead of out_sum = coeff*sum */
+#define B2_FLAG_GLM_FP32 2       /* b2_glm_bernoulli_logits: fp32 SIMT contractions instead of the
+                                    TF32 tensor-core path */
 
 /*
  * b2_site_score -- fused log_prob + score of one sample site for an elementwise family.
@@ -159,6 +161,8 @@ int b2_reduce_to(const b2_tensor* src, b2_tensor* dst, void* workspace, size_t w
  * X: [N,D] row-major fp32 (16-byte aligned), D in {4, 8, 16, 32}; W: [P,D]; b: [P] (nullable);
  * y: [N] fp32.
  * out_total (nullable): scalar, (=|+=) sum_coeff * scale * SUM_p sum_p[p].
+ * For D == 32 the two contractions run on the tensor cores (TF32 operands, fp32 accumulate,
+ * logits perturbed by ~1e-3 relative, unbiased); pass B2_FLAG_GLM_FP32 for the fp32 SIMT kernel.
  */
 int b2_glm_bernoulli_logits(const float* X, const float* y, const float* W, const float* b,
                             int64_t N, int D, int P, double scale, double weight, double sum_coeff,

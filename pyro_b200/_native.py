@@ -18,6 +18,7 @@ B2_MAX_DIMS = 8
 B2_MAX_PARAMS = 4
 B2_F32, B2_F64, B2_I64, B2_U8 = 0, 1, 2, 3
 B2_FLAG_ACCUMULATE_SUM = 1
+B2_FLAG_GLM_FP32 = 2
 B2_ERR_UNSUPPORTED_REDUCTION = -6
 
 # family ids (include/pyro_b200.h)

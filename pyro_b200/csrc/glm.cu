@@ -173,6 +173,11 @@ __global__ void glm_total_kernel(const float* __restrict__ sum_p, int P, double 
   }
 }
 
+// tensor-core variant (glm_mma.cu)
+int glm_mma_grid_x(int64_t N);
+void launch_glm_mma(const float* X, const float* y, const float* W, const float* b, int64_t N, int P,
+                    float* partials, int gx, cudaStream_t s);
+
 inline int glm_grid_x(int64_t N) {
   const int64_t ntiles = (N + kGlmTileRows - 1) / kGlmTileRows;
   int64_t gx = (int64_t)kNumSMs * 2;  // two 256-thread CTAs per SM (register-limited)
@@ -201,9 +206,13 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   if (reinterpret_cast<uintptr_t>(X) % 16 != 0) return B2_ERR_BAD_SHAPE;
   if (!workspace || workspace_bytes < b2_glm_workspace(N, D, P)) return B2_ERR_WORKSPACE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int gx = glm_grid_x(N);
+  const bool use_mma = (D == 32) && !(flags & B2_FLAG_GLM_FP32);
+  const int gx = use_mma ? glm_mma_grid_x(N) : glm_grid_x(N);
   dim3 grid((unsigned)gx, (unsigned)((P + kGlmParticles - 1) / kGlmParticles), 1);
   float* partials = reinterpret_cast<float*>(workspace);
+  if (use_mma) {
+    launch_glm_mma(X, y, W, b, N, P, partials, gx, s);
+  } else
   switch (D) {
     case 4: glm_bernoulli_kernel<4><<<grid, 256, 0, s>>>(X, y, W, b, N, P, partials); break;
     case 8: glm_bernoulli_kernel<8><<<grid, 256, 0, s>>>(X, y, W, b, N, P, partials); break;

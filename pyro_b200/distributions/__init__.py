@@ -799,8 +799,9 @@ class LinearPredictor:
 
     ``w``: [D], [P, D] or [P, 1, D] (vectorised particles);  ``b``: None, [], [P] or [P, 1]."""
 
-    def __init__(self, X, w, b=None):
+    def __init__(self, X, w, b=None, tensor_cores=True):
         self.X, self.w, self.b = X, w, b
+        self.tensor_cores = tensor_cores  # False: fp32 SIMT contractions (B2_FLAG_GLM_FP32)
         D = X.shape[-1]
         self.vectorised = w.dim() > 1
         self.P = w.numel() // D
@@ -815,15 +816,15 @@ class LinearPredictor:
         return out if self.vectorised else out.squeeze(0)
 
 
-def linear_predictor(X, w, b=None):
-    return LinearPredictor(X, w, b)
+def linear_predictor(X, w, b=None, tensor_cores=True):
+    return LinearPredictor(X, w, b, tensor_cores)
 
 
 class _GlmBernoulliFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, X, y, W, b):
         import ctypes
-        scale, weight, coeff, unit = meta
+        scale, weight, coeff, unit, flags = meta
         N.require_cuda(X, "fused GLM likelihood")
         P, D = W.shape
         n = X.shape[0]
@@ -837,7 +838,7 @@ class _GlmBernoulliFn(torch.autograd.Function):
         ws = N.workspace(dev, need, tag="glm")
         N.check(N.lib().b2_glm_bernoulli_logits(
             X.data_ptr(), y.data_ptr(), Wc.data_ptr(), bc.data_ptr() if bc is not None else None,
-            n, D, P, float(scale), float(weight), float(coeff), 0, None, total.data_ptr(),
+            n, D, P, float(scale), float(weight), float(coeff), int(flags), None, total.data_ptr(),
             dW.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), N.stream_ptr(dev)),
             "b2_glm_bernoulli_logits")
         ctx.grads = (dW, db if b is not None else None)
@@ -886,7 +887,8 @@ class _BernoulliLinear(Bernoulli):
         y = value.reshape(-1).to(torch.float32).contiguous()
         W = lz.w.reshape(lz.P, D)
         b = lz.b.reshape(lz.P) if lz.b is not None else None
-        return _GlmBernoulliFn.apply((scale, weight, sum_coeff, unit), X, y, W, b)
+        flags = 0 if getattr(lz, "tensor_cores", True) else N.B2_FLAG_GLM_FP32
+        return _GlmBernoulliFn.apply((scale, weight, sum_coeff, unit, flags), X, y, W, b)
 
 
 def _bernoulli_new(cls, probs=None, logits=None, validate_args=None):
