@@ -76,161 +76,130 @@ struct VecBody {
   static constexpr bool HASV = FamilyTraits<FAM>::kHasValue;
   static constexpr int V = VecOf<T>::N;
   static constexpr int NRED = GRAD ? 2 + NP : 1;
-  // two rows at once only where the register budget allows it without spilling: fp32 families
-  // with a single parameter (Bernoulli, Poisson, Exponential, Half*): the [particles, N] sites
-  static constexpr bool kTwoRows = sizeof(T) == 4 && NP == 1 && !MASKUP && NVEC <= 2;
 
   // operand classes, fixed for the launch: vector along columns (column stride 1) or one scalar
   // per row; row-invariant (row stride 0) vectors are loaded once per column chunk and reused
   // for every row (e.g. the observations y[N] scored against logits[P, N])
   bool x_vec, p_vec[NP], x_inv, p_inv[NP];
-  bool u_vec, m_vec;
   T scale, f0;
-  // operand registers: slot [q] belongs to the q-th row in flight; row-invariant operands are
-  // loaded once per column chunk into slot 0 and read from there by every row
-  static constexpr int NRMAX = kTwoRows ? 2 : 1;
-  Pack<T> xv[NRMAX][NVEC], pv[NRMAX][NVEC][NP];
+  // per-row state
+  const T* xr;
+  const T* pr[NP];
+  const T* ur;
+  const uint8_t* mr;
+  T* lpr;
+  T* gxr;
+  T* gpr[NP];
+  T xs, ps[NP], us;
+  bool u_vec, m_vec;
+  // operand registers (invariant ones persist across rows)
+  Pack<T> xv[NVEC], pv[NVEC][NP];
 
-  struct Row {
-    const T* xr;
-    const T* pr[NP];
-    const T* ur;
-    const uint8_t* mr;
-    T* lpr;
-    T* gxr;
-    T* gpr[NP];
-    T xs, ps[NP], us;
-  };
-
-  __device__ __forceinline__ void setup_row(const SiteArgs& a, int64_t r, Row& w) const {
-    w.xr = HASV ? reinterpret_cast<const T*>(a.x.ptr) + r * a.x.st[0] : nullptr;
-    w.xs = (HASV && !x_vec) ? __ldg(w.xr) : (T)0;
-#pragma unroll
-    for (int k = 0; k < NP; ++k) {
-      w.pr[k] = reinterpret_cast<const T*>(a.p[k].ptr) + r * a.p[k].st[0];
-      w.ps[k] = p_vec[k] ? (T)0 : __ldg(w.pr[k]);
-    }
-    w.ur = nullptr;
-    w.mr = nullptr;
-    w.us = (T)1;
-    if (MASKUP) {
-      w.ur = a.up.ptr ? reinterpret_cast<const T*>(a.up.ptr) + r * a.up.st[0] : nullptr;
-      w.us = (w.ur && !u_vec) ? __ldg(w.ur) : (T)1;
-      w.mr = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr) + r * a.mask.st[0] : nullptr;
-    }
-    w.lpr = a.lp.mode == 1 ? reinterpret_cast<T*>(a.lp.ptr) + r * a.lp.st[0] : nullptr;
-    w.gxr = (GRAD && a.gx.mode == 1) ? reinterpret_cast<T*>(a.gx.ptr) + r * a.gx.st[0] : nullptr;
-#pragma unroll
-    for (int k = 0; k < NP; ++k)
-      w.gpr[k] = (GRAD && a.gp[k].mode == 1) ? reinterpret_cast<T*>(a.gp[k].ptr) + r * a.gp[k].st[0] : nullptr;
-  }
-
-  __device__ __forceinline__ void load_invariant(const SiteArgs& a, int64_t cv, int64_t cstep) {
+  __device__ __forceinline__ void load_invariant(const T* xbase, const T* const (&pbase)[NP],
+                                                 int64_t cv, int64_t cstep) {
 #pragma unroll
     for (int u = 0; u < NVEC; ++u) {
       const int64_t c = (cv + u * cstep) * V;
-      if (HASV && x_vec && x_inv) xv[0][u] = ld_keep(reinterpret_cast<const T*>(a.x.ptr) + c);
+      if (HASV && x_vec && x_inv) xv[u] = ld_keep(xbase + c);
 #pragma unroll
       for (int k = 0; k < NP; ++k)
-        if (p_vec[k] && p_inv[k]) pv[0][u][k] = ld_keep(reinterpret_cast<const T*>(a.p[k].ptr) + c);
+        if (p_vec[k] && p_inv[k]) pv[u][k] = ld_keep(pbase[k] + c);
     }
   }
 
-  // NR rows at once: all their loads are issued before any arithmetic
-  template <int NR>
-  __device__ __forceinline__ void run(const Row (&w)[NR], int64_t cv, int64_t cstep, T (&acc)[NRED]) {
-    Pack<T> uv[NR][NVEC];
-    uint32_t mbits[NR][NVEC];
+  __device__ __forceinline__ void run(int64_t cv, int64_t cstep, T (&acc)[NRED]) {
+    Pack<T> uv[NVEC];
+    uint32_t mbits[NVEC];
 #pragma unroll
-    for (int q = 0; q < NR; ++q) {
+    for (int u = 0; u < NVEC; ++u) {
+      const int64_t c = (cv + u * cstep) * V;
+      if (HASV && x_vec && !x_inv) xv[u] = ld_stream(xr + c);
 #pragma unroll
-      for (int u = 0; u < NVEC; ++u) {
-        const int64_t c = (cv + u * cstep) * V;
-        if (HASV && x_vec && !x_inv) xv[q][u] = ld_stream(w[q].xr + c);
+      for (int k = 0; k < NP; ++k)
+        if (p_vec[k] && !p_inv[k]) pv[u][k] = ld_stream(pr[k] + c);
+      if (MASKUP) {
+        if (ur && u_vec) uv[u] = ld_stream(ur + c);
+        mbits[u] = 0xffffffffu;
+        if (mr) {
+          mbits[u] = 0;
+#pragma unroll
+          for (int j = 0; j < V; ++j) mbits[u] |= (mr[m_vec ? c + j : 0] != 0 ? 1u : 0u) << j;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NVEC; ++u) {
+      const int64_t c = (cv + u * cstep) * V;
+      Pack<T> lpv, gxv, gpv[NP];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        T pl[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) pl[k] = p_vec[k] ? pv[u][k].v[j] : ps[k];
+        const T xe = HASV ? (x_vec ? xv[u].v[j] : xs) : (T)0;
+        ElemOut<T> o;
+        Eval<FAM, T, GRAD>::run(xe, pl, o);
+        T slp = o.lp * scale;
+        T f = f0;
+        if (MASKUP) {
+          const bool m = (mbits[u] >> j) & 1u;
+          slp = m ? slp : (T)0;
+          f = m ? f0 : (T)0;
+          if (ur) f *= u_vec ? uv[u].v[j] : us;
+        }
+        lpv.v[j] = slp;
+        acc[0] += slp;
+        if (GRAD) {
+          T gxe = f * o.dx;
+          if (MASKUP) gxe = (f == (T)0) ? (T)0 : gxe;  // masked-out NaNs must not leak
+          gxv.v[j] = gxe;
+          acc[1] += gxe;
+#pragma unroll
+          for (int k = 0; k < NP; ++k) {
+            T g = f * o.dp[k];
+            if (MASKUP) g = (f == (T)0) ? (T)0 : g;
+            gpv[k].v[j] = g;
+            acc[2 + k] += g;
+          }
+        }
+      }
+      if (lpr) st_stream(lpr + c, lpv);
+      if (GRAD) {
+        if (gxr) st_stream(gxr + c, gxv);
 #pragma unroll
         for (int k = 0; k < NP; ++k)
-          if (p_vec[k] && !p_inv[k]) pv[q][u][k] = ld_stream(w[q].pr[k] + c);
-        if (MASKUP) {
-          if (w[q].ur && u_vec) uv[q][u] = ld_stream(w[q].ur + c);
-          mbits[q][u] = 0xffffffffu;
-          if (w[q].mr) {
-            mbits[q][u] = 0;
-#pragma unroll
-            for (int j = 0; j < V; ++j)
-              mbits[q][u] |= (w[q].mr[m_vec ? c + j : 0] != 0 ? 1u : 0u) << j;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < NR; ++q) {
-#pragma unroll
-      for (int u = 0; u < NVEC; ++u) {
-        const int64_t c = (cv + u * cstep) * V;
-        Pack<T> lpv, gxv, gpv[NP];
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-          T pl[NP];
-#pragma unroll
-          for (int k = 0; k < NP; ++k)
-            pl[k] = p_vec[k] ? ((q > 0 && p_inv[k]) ? pv[0][u][k].v[j] : pv[q][u][k].v[j]) : w[q].ps[k];
-          const T xe = HASV ? (x_vec ? ((q > 0 && x_inv) ? xv[0][u].v[j] : xv[q][u].v[j]) : w[q].xs) : (T)0;
-          ElemOut<T> o;
-          Eval<FAM, T, GRAD>::run(xe, pl, o);
-          T slp = o.lp * scale;
-          T f = f0;
-          if (MASKUP) {
-            const bool m = (mbits[q][u] >> j) & 1u;
-            slp = m ? slp : (T)0;
-            f = m ? f0 : (T)0;
-            if (w[q].ur) f *= u_vec ? uv[q][u].v[j] : w[q].us;
-          }
-          lpv.v[j] = slp;
-          acc[0] += slp;
-          if (GRAD) {
-            T gxe = f * o.dx;
-            if (MASKUP) gxe = (f == (T)0) ? (T)0 : gxe;  // masked-out NaNs must not leak
-            gxv.v[j] = gxe;
-            acc[1] += gxe;
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-              T g = f * o.dp[k];
-              if (MASKUP) g = (f == (T)0) ? (T)0 : g;
-              gpv[k].v[j] = g;
-              acc[2 + k] += g;
-            }
-          }
-        }
-        if (w[q].lpr) st_stream(w[q].lpr + c, lpv);
-        if (GRAD) {
-          if (w[q].gxr) st_stream(w[q].gxr + c, gxv);
-#pragma unroll
-          for (int k = 0; k < NP; ++k)
-            if (w[q].gpr[k]) st_stream(w[q].gpr[k] + c, gpv[k]);
-        }
+          if (gpr[k]) st_stream(gpr[k] + c, gpv[k]);
       }
     }
   }
 
-  // all rows of this thread for one column chunk; rows are taken two at a time so that twice the
-  // bytes are in flight per thread (the row loop is where a [P, N] site spends its time)
+  // all rows of this thread for one column chunk
   __device__ __forceinline__ void chunk(const SiteArgs& a, int64_t cv, int64_t cstep, int ty, int TY,
                                         T (&acc)[NRED]) {
-    load_invariant(a, cv, cstep);
-    const int64_t rstep = (int64_t)gridDim.y * TY;
-    int64_t r = (int64_t)blockIdx.y * TY + ty;
-    if (kTwoRows) {
-      for (; r + rstep < a.R; r += 2 * rstep) {
-        Row w[2];
-        setup_row(a, r, w[0]);
-        setup_row(a, r + rstep, w[1]);
-        run<2>(w, cv, cstep, acc);
+    const T* xbase = HASV ? reinterpret_cast<const T*>(a.x.ptr) : nullptr;
+    const T* pbase[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) pbase[k] = reinterpret_cast<const T*>(a.p[k].ptr);
+    load_invariant(xbase, pbase, cv, cstep);
+    for (int64_t r = (int64_t)blockIdx.y * TY + ty; r < a.R; r += (int64_t)gridDim.y * TY) {
+      xr = HASV ? xbase + r * a.x.st[0] : nullptr;
+      xs = (HASV && !x_vec) ? __ldg(xr) : (T)0;
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        pr[k] = pbase[k] + r * a.p[k].st[0];
+        ps[k] = p_vec[k] ? (T)0 : __ldg(pr[k]);
       }
-    }
-    for (; r < a.R; r += rstep) {
-      Row w[1];
-      setup_row(a, r, w[0]);
-      run<1>(w, cv, cstep, acc);
+      if (MASKUP) {
+        ur = a.up.ptr ? reinterpret_cast<const T*>(a.up.ptr) + r * a.up.st[0] : nullptr;
+        us = (ur && !u_vec) ? __ldg(ur) : (T)1;
+        mr = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr) + r * a.mask.st[0] : nullptr;
+      }
+      lpr = a.lp.mode == 1 ? reinterpret_cast<T*>(a.lp.ptr) + r * a.lp.st[0] : nullptr;
+      gxr = (GRAD && a.gx.mode == 1) ? reinterpret_cast<T*>(a.gx.ptr) + r * a.gx.st[0] : nullptr;
+#pragma unroll
+      for (int k = 0; k < NP; ++k)
+        gpr[k] = (GRAD && a.gp[k].mode == 1) ? reinterpret_cast<T*>(a.gp[k].ptr) + r * a.gp[k].st[0] : nullptr;
+      run(cv, cstep, acc);
     }
   }
 
@@ -244,6 +213,9 @@ struct VecBody {
     }
     scale = (T)a.scale;
     f0 = (T)(a.weight * a.scale);
+    ur = nullptr;
+    mr = nullptr;
+    us = (T)1;
     u_vec = MASKUP && a.up.st[1] == 1;
     m_vec = MASKUP && a.mask.st[1] == 1;
   }
@@ -252,23 +224,18 @@ struct VecBody {
 // Vectors in flight per operand per thread.  Forward-only fp32 kernels are pure streams: 4 vectors
 // (measured 87% of the HBM copy peak for Normal).  Kernels that also write gradients carry more
 // live registers; 2 vectors keep them at 3 resident CTAs per SM.
-template <int FAM, typename T, bool GRAD>
+template <typename T, bool GRAD>
 struct VecUnroll {
   static constexpr int U = (sizeof(T) == 4 && !GRAD) ? 4 : 2;
-  // families without lgamma/digamma are streams: keep 3 CTAs per SM resident (<= 80 registers,
-  // no spills measured with ptxas -v); the special-function families are issue-bound and get the
-  // full 128-register budget instead of spilling
-  static constexpr bool kLight = FAM == kNormal || FAM == kCauchy || FAM == kHalfCauchy ||
-                                 FAM == kExponential || FAM == kHalfNormal || FAM == kUniform;
-  static constexpr int kMinBlocks = (sizeof(T) == 4 && !GRAD && kLight) ? 3 : 2;
+  static constexpr int kMinBlocks = (sizeof(T) == 8 && GRAD) ? 2 : 3;
 };
 
 // Loop nest: column chunks outermost (U vectors per thread, then a one-vector tail), rows inside.
 template <int FAM, typename T, bool GRAD, bool MASKUP>
-__global__ void __launch_bounds__(256, VecUnroll<FAM, T, GRAD>::kMinBlocks) site_vec_kernel(const SiteArgs a) {
+__global__ void __launch_bounds__(256, VecUnroll<T, GRAD>::kMinBlocks) site_vec_kernel(const SiteArgs a) {
   constexpr int NP = FamilyTraits<FAM>::kNumParams;
   constexpr int V = VecOf<T>::N;
-  constexpr int U = VecUnroll<FAM, T, GRAD>::U;
+  constexpr int U = VecUnroll<T, GRAD>::U;
   constexpr int NRED = GRAD ? 2 + NP : 1;
 
   const int TX = 1 << a.tx_log2;
@@ -375,7 +342,7 @@ template <int FAM, typename T, bool GRAD>
 int launch_site(const SiteArgs& a, bool vec, cudaStream_t stream) {
   if (vec) {
     constexpr int V = VecOf<T>::N;
-    constexpr int U = VecUnroll<FAM, T, GRAD>::U;
+    constexpr int U = VecUnroll<T, GRAD>::U;
     const int64_t CV = a.C / V;
     const int TX = 1 << a.tx_log2, TY = 256 / TX;
     // enough CTAs for ~4 waves of resident blocks; each thread then owns >= U vectors per row
