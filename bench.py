@@ -166,7 +166,7 @@ def roofline_for(path, X, y, particles, flush):
             dist.Bernoulli(logits=dist.linear_predictor(X, w, b))._fused_sum(y, None, 1.0, -1.0 / P, 1.0, True)
         ms = kernel_time_ms(fn, 20, flush)
         alg = n * D_FEAT * 4 + n * 4  # X and y once, for value AND gradient
-        name = "glm_bernoulli_kernel<32> (+2 finish kernels)"
+        name = "glm_bernoulli_mma_kernel (+2 finish kernels)"
     else:
         logits = torch.randn(P, n, device=dev).requires_grad_(True)
 
@@ -176,9 +176,22 @@ def roofline_for(path, X, y, particles, flush):
         alg = P * n * 4 + n * 4 + P * n * 4  # read logits + y, write d/dlogits (full shape)
         name = "site_vec_kernel<BernoulliLogits,float,GRAD>"
     ach = alg / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": name, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(ach / peak, 4), "traffic": None, "ms_per_launch": round(ms, 4),
-            "algorithmic_bytes": alg, "peak_source": how}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram read+write per launch, from ncu --set full
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(name.split(" ")[0].split("<")[0])
+    out = {"bound": "hbm", "kernel": name, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+           "frac": round(ach / peak, 4), "traffic": traffic, "ms_per_launch": round(ms, 4),
+           "algorithmic_bytes": alg, "peak_source": how}
+    if "glm" in path:
+        # this kernel is not HBM-bound: 3 SFU ops per (row, particle) at 16/clk/SM
+        sfu_us = 3.0 * n * P / (148 * 16 * 1.965e9) * 1e6
+        out["note"] = ("SFU-bound kernel: MUFU floor %.0f us, HBM floor %.0f us, measured %.0f us; "
+                       "4*N*D*P = %.1f GFLOP on the tensor pipe (TF32 mma.sync) = %.0f TFLOP/s"
+                       % (sfu_us, alg / peak / 1e3, ms * 1e3, 4.0 * n * D_FEAT * P / 1e9,
+                          4.0 * n * D_FEAT * P / (ms * 1e-3) / 1e12))
+    return out
 
 
 def cpu_reference(steps, warmup, threads=None, n=N_ROWS):
