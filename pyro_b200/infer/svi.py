@@ -52,7 +52,8 @@ class SVI:
             return loss if isinstance(loss, float) else torch_item(loss)
 
     # ---- one eager step -----------------------------------------------------------------------------
-    def _eager_step(self, args, kwargs, want_tensor=False):
+    def _grads(self, args, kwargs, want_tensor=True):
+        """Phase 1: loss + gradients.  Returns (loss, [unconstrained parameters touched])."""
         with poutine.trace(param_only=True) as param_capture:
             if want_tensor and self._loss_and_grads_tensor is not None:
                 loss = self._loss_and_grads_tensor(self.model, self.guide, *args, **kwargs)
@@ -70,31 +71,52 @@ class SVI:
             if id(u) not in seen:
                 seen.add(id(u))
                 params.append(u)
+        return loss, params
+
+    @staticmethod
+    def _world():
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size()
+        return 1
+
+    def _pack(self, params, loss):
+        grads = [p.grad for p in params if p.grad is not None]
+        return torch.cat([loss.detach().reshape(1).to(grads[0].dtype)] + [g.reshape(-1) for g in grads])
+
+    def _unpack(self, params, flat):
+        off = 1
+        for p in params:
+            if p.grad is None:
+                continue
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].reshape(p.grad.shape))
+            off += n
+        return flat[0]
+
+    def _eager_step(self, args, kwargs, want_tensor=False):
+        loss, params = self._grads(args, kwargs, want_tensor)
         loss = self._allreduce(params, loss)
         self.optim(params)  # fused update; zeroes the gradients in the same pass
         return loss
 
     def _allreduce(self, params, loss):
-        """Particle-sharded data parallelism: every rank holds P/W particles, so the ELBO estimate
-        and its gradient are the mean over ranks.  ONE all-reduce per step over a packed buffer
-        [loss, grad_1 .. grad_n] (the reference's only analogue is the per-parameter
-        Horovod all-reduce of pyro/optim/horovod.py:41-45 + examples/svi_horovod.py:134); the
-        replicated fused optimiser then keeps the parameters identical on every rank."""
+        """Data parallelism: every rank scores a shard (of the particle plate, or of a data plate
+        whose ``size/subsample_size`` rescaling keeps each rank's ELBO unbiased), so the ELBO
+        estimate and its gradient are the MEAN over ranks.  ONE all-reduce per step over a packed
+        buffer [loss, grad_1 .. grad_n] (the reference's only analogue is the
+        per-parameter Horovod all-reduce of pyro/optim/horovod.py:41-45 +
+        examples/svi_horovod.py:134); the replicated fused optimiser then keeps the parameters
+        identical on every rank."""
         import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        if self._world() == 1:
             return loss
-        grads = [p.grad for p in params if p.grad is not None]
-        if not grads or not isinstance(loss, torch.Tensor):
+        if not isinstance(loss, torch.Tensor) or not any(p.grad is not None for p in params):
             return loss
-        flat = torch.cat([loss.detach().reshape(1).to(grads[0].dtype)] + [g.reshape(-1) for g in grads])
+        flat = self._pack(params, loss)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         flat /= dist.get_world_size()
-        off = 1
-        for g in grads:
-            n = g.numel()
-            g.copy_(flat[off:off + n].reshape(g.shape))
-            off += n
-        return flat[0]
+        return self._unpack(params, flat)
 
     def step(self, *args, **kwargs):
         """One gradient step; returns the loss estimate as a python float."""
@@ -134,7 +156,14 @@ class SVI:
                     s.copy_(a, non_blocking=True)
             elif a != s:
                 raise ValueError("non-tensor argument of a graph-captured SVI step changed")
+        if st.get("graph_b") is None:
+            self._graph.replay()
+            return st["loss"]
+        # multi-rank: [graph A: loss + grads + pack] -> NCCL all-reduce (eager) -> [graph B: unpack + optimiser]
+        import torch.distributed as dist
         self._graph.replay()
+        dist.all_reduce(st["flat"], op=dist.ReduceOp.SUM)
+        st["graph_b"].replay()
         return st["loss"]
 
     def _capture_graph(self, args):
@@ -160,9 +189,23 @@ class SVI:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss = self._eager_step(tuple(static_args), {}, want_tensor=True)
-            loss = loss.reshape(()) if isinstance(loss, torch.Tensor) else torch.as_tensor(loss, device=dev)
-        self._graph = graph
-        self._graph_state = {"static_args": static_args, "loss": loss}
+        if self._world() == 1:
+            with torch.cuda.graph(graph):
+                loss = self._eager_step(tuple(static_args), {}, want_tensor=True)
+                loss = loss.reshape(()) if isinstance(loss, torch.Tensor) else torch.as_tensor(loss, device=dev)
+            self._graph = graph
+            self._graph_state = {"static_args": static_args, "loss": loss}
+        else:
+            # the collective stays outside the graphs: capture the two halves around it
+            world = self._world()
+            with torch.cuda.graph(graph):
+                loss, params = self._grads(tuple(static_args), {}, True)
+                flat = self._pack(params, loss)
+            graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_b, pool=graph.pool()):
+                flat /= world
+                out = self._unpack(params, flat).clone()
+                self.optim(params)
+            self._graph = graph
+            self._graph_state = {"static_args": static_args, "loss": out, "flat": flat, "graph_b": graph_b}
         self._steps_done += 1  # the warm-up step above was a real optimisation step

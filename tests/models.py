@@ -33,6 +33,22 @@ def logistic_model_fused(X, y):
         pyro.sample("y", dist.Bernoulli(logits=dist.linear_predictor(X, w, b)), obs=y)
 
 
+def logistic_model_sharded(X, y, idx, n_total):
+    """Data-parallel form: this rank holds rows ``idx`` of an ``n_total``-row data set.  The data
+    plate's ``size / subsample_size`` rescaling (pyro/poutine/subsample_messenger.py:159-174) makes
+    each rank's ELBO an unbiased estimate; SVI averages loss and gradients over ranks (the scheme of
+    examples/svi_horovod.py:94-134)."""
+    D = X.shape[-1]
+    w = pyro.sample("w", dist.Normal(X.new_zeros(D), X.new_ones(D)).to_event(1))
+    b = pyro.sample("b", dist.Normal(X.new_zeros(()), X.new_full((), 10.0)))
+    with pyro.plate("data", n_total, subsample=idx):
+        pyro.sample("y", dist.Bernoulli(logits=dist.linear_predictor(X, w, b)), obs=y)
+
+
+def logistic_guide_sharded(X, y, idx, n_total):
+    logistic_guide(X, y)
+
+
 def logistic_guide(X, y):
     D = X.shape[-1]
     w_loc = pyro.param("w_loc", lambda: X.new_zeros(D))

@@ -52,6 +52,30 @@ def _worker(rank, world, port, what, ret):
                     flat = torch.cat([store[k].detach().reshape(-1) for k in ("w_loc", "w_scale", "b_loc", "b_scale")])
                     out.append((loss, flat.numpy()))
                 ret[rank] = out
+            elif what == "svi_data":
+                # data-plate sharding: same particles on every rank, each rank scores its rows with
+                # the plate's size/subsample_size rescaling; mean over ranks == full-data ELBO
+                g = load_npz("svi_logistic.npz")
+                X, y = torch.as_tensor(g["X"]), torch.as_tensor(g["y"])
+                eps_w, eps_b = torch.as_tensor(g["eps_w"]), torch.as_tensor(g["eps_b"])
+                n = X.shape[0]
+                idx = torch.arange(rank * n // world, (rank + 1) * n // world)
+                box = {"i": 0}
+
+                def guide(X, y, idx, n_total):
+                    with models.InjectNoise({"w": eps_w[box["i"]], "b": eps_b[box["i"]]}):
+                        models.logistic_guide(X, y)
+
+                svi = SVI(models.logistic_model_sharded, guide, ClippedAdam({"lr": 0.01}),
+                          Trace_ELBO(num_particles=int(g["P"]), vectorize_particles=True, max_plate_nesting=1))
+                out = []
+                for i in range(eps_w.shape[0]):
+                    box["i"] = i
+                    loss = svi.step(X[idx], y[idx], idx, n)
+                    store = pyro.get_param_store()
+                    flat = torch.cat([store[k].detach().reshape(-1) for k in ("w_loc", "w_scale", "b_loc", "b_scale")])
+                    out.append((loss, flat.numpy()))
+                ret[rank] = out
             else:
                 g = load_npz("mcmc.npz")
                 X, y = torch.as_tensor(g["lr.X"]), torch.as_tensor(g["lr.y"])
@@ -77,6 +101,18 @@ def test_particle_sharded_svi_matches_reference_trajectory():
     from conftest import load_npz
     g = load_npz("svi_logistic.npz")
     ret = _spawn("svi")
+    for i, (ref_loss, ref_params) in enumerate(zip(g["losses_f64"], g["params_f64"])):
+        for rank in (0, 1):
+            loss, params = ret[rank][i]
+            assert abs(loss - ref_loss) <= 1e-8 * abs(ref_loss), (rank, i)
+            assert np.allclose(params, ref_params, atol=1e-8, rtol=1e-8), (rank, i)
+
+
+@pytest.mark.timeout(300)
+def test_data_sharded_svi_matches_reference_trajectory():
+    from conftest import load_npz
+    g = load_npz("svi_logistic.npz")
+    ret = _spawn("svi_data")
     for i, (ref_loss, ref_params) in enumerate(zip(g["losses_f64"], g["params_f64"])):
         for rank in (0, 1):
             loss, params = ret[rank][i]
