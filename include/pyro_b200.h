@@ -274,6 +274,21 @@ int b2_nuts_small(const b2_model* model, void* z, void* U, void* grad, const voi
                   void* samples_out, void* accept_prob_out, int32_t* depth_out,
                   int32_t* diverging_out, int32_t* num_steps_out, void* stream);
 
+/*
+ * b2_nuts_leaf_vector -- lockstep iterative NUTS (large latent dimension): everything a new leaf
+ * needs over the [C, D] state in ONE pass (pyro/infer/mcmc/nuts.py:197-248,285-342 restated
+ * iteratively): whitened momentum ru = r*sqrt(minv); rsub += ru; proposal copy zs,gs <- z,g where
+ * take[c]; on an even leaf the checkpoint store rck/sck[store_slot] (store_slot >= 0), on an odd
+ * leaf (store_slot < 0) the 2*nblk U-turn dot products of the blocks ending at this leaf
+ * (checkpoint slots idx_max, idx_max-1, ...), written to dots[c*2*nblk + 2j + {0,1}].
+ * rck/sck: [slots, C, D].  Chains with active[c]==0 are untouched.
+ */
+int b2_nuts_leaf_vector(const void* z, const void* r, const void* g, const void* minv,
+                        int64_t minv_chain_stride, const uint8_t* active, const uint8_t* take,
+                        void* rsub, void* zs, void* gs, void* rck, void* sck, int store_slot,
+                        int idx_max, int nblk, void* dots, int64_t C, int64_t D, int dtype,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 const char* b2_last_error(int code);
 int b2_version(void);

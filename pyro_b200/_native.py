@@ -68,6 +68,8 @@ SIGNATURES = {
     "b2_potential_workspace": (_sz, [_mp, _i64]),
     "b2_nuts_small": (_i32, [_mp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f64, ctypes.c_uint64,
                              _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2_nuts_leaf_vector": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                                   _i32, _vp, _i64, _i64, _i32, _vp, _sz, _vp]),
     "b2_last_error": (ctypes.c_char_p, [_i32]),
     "b2_version": (_i32, []),
     "b2_launch_count": (_i64, []),

@@ -456,3 +456,132 @@ extern "C" int b2_nuts_small(const b2_model* model, void* z, void* U, void* grad
 #undef B2_NUTS_ARGS
   return B2_ERR_BAD_DTYPE;
 }
+
+namespace b2 {
+
+// ---- lockstep NUTS: per-leaf vector bookkeeping in ONE pass over [C, D] ---------------------------
+// After a leapfrog (kick_drift, potential, kick) and the per-chain scalar decisions, every active
+// chain must (nuts.py:197-248, 285-342 restated iteratively, see nuts_core.cuh):
+//   ru = r * sqrt(minv)                       whitened momentum of the new leaf
+//   rsub += ru                                running momentum sum of the subtree
+//   if take[c]: zs = z, gs = g                progressive multinomial proposal
+//   even leaf:  rck[slot] = ru, sck[slot] = rsub            (checkpoint)
+//   odd leaf:   for each of the nblk blocks ending here, the two U-turn dot products
+//               a_first = <rck[k], rho>, a_last = <ru, rho>, rho = (rsub - sck[k] + rck[k]) - (rck[k] + ru)/2
+// grid = (bx, C); dot partials go to partials[(c * bx + blockIdx.x) * 2*nblk + ...], finished by
+// nuts_dots_finish_kernel into dots[c * 2*nblk + ...].
+constexpr int kNutsMaxBlocks = 12;
+template <typename T>
+__global__ void __launch_bounds__(256) nuts_leaf_vector_kernel(
+    const T* __restrict__ z, const T* __restrict__ r, const T* __restrict__ g, const T* __restrict__ minv,
+    int64_t minv_cs, const uint8_t* __restrict__ active, const uint8_t* __restrict__ take,
+    T* __restrict__ rsub, T* __restrict__ zs, T* __restrict__ gs, T* __restrict__ rck, T* __restrict__ sck,
+    int64_t ck_stride /* = C*D */, int store_slot /* >= 0: even leaf */, int idx_max, int nblk,
+    double* __restrict__ partials, int64_t C, int64_t D) {
+  __shared__ double smem[2 * kNutsMaxBlocks * 32];
+  for (int64_t c = blockIdx.y; c < C; c += gridDim.y) {
+    double acc[2 * kNutsMaxBlocks];
+#pragma unroll
+    for (int k = 0; k < 2 * kNutsMaxBlocks; ++k) acc[k] = 0.0;
+    const bool on = active[c] != 0;
+    if (on) {
+      const bool tk = take[c] != 0;
+      const T* mi = minv + c * minv_cs;
+      for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D;
+           d += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = c * D + d;
+        const T ru = r[i] * b2_sqrt(mi[d]);
+        const T rs = rsub[i] + ru;
+        rsub[i] = rs;
+        if (tk) {
+          zs[i] = z[i];
+          gs[i] = g[i];
+        }
+        if (store_slot >= 0) {
+          rck[(int64_t)store_slot * ck_stride + i] = ru;
+          sck[(int64_t)store_slot * ck_stride + i] = rs;
+        } else {
+          for (int j = 0; j < nblk; ++j) {
+            const int64_t o = (int64_t)(idx_max - j) * ck_stride + i;
+            const T rk = rck[o];
+            const T rho = (rs - sck[o] + rk) - (T)0.5 * (rk + ru);
+            acc[2 * j] += (double)(rk * rho);
+            acc[2 * j + 1] += (double)(ru * rho);
+          }
+        }
+      }
+    }
+    if (nblk > 0) {
+      // block reduce the 2*nblk sums
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      for (int k = 0; k < 2 * nblk; ++k) {
+        const double w = warp_sum(acc[k]);
+        if (lane == 0) smem[k * 32 + warp] = w;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        for (int k = 0; k < 2 * nblk; ++k) {
+          double w = (lane < (int)(blockDim.x >> 5)) ? smem[k * 32 + lane] : 0.0;
+          w = warp_sum(w);
+          if (lane == 0) partials[(c * gridDim.x + blockIdx.x) * 2 * nblk + k] = w;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <typename T>
+__global__ void nuts_dots_finish_kernel(const double* __restrict__ partials, int nb, int nvals,
+                                        T* __restrict__ dots, int64_t C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * nvals) return;
+  const int64_t c = i / nvals;
+  const int k = (int)(i - c * nvals);
+  double s = 0.0;
+  for (int b = 0; b < nb; ++b) s += partials[(c * nb + b) * nvals + k];
+  dots[i] = (T)s;
+}
+
+}  // namespace b2
+extern "C" int b2_nuts_leaf_vector(const void* z, const void* r, const void* g, const void* minv,
+                                   int64_t minv_chain_stride, const uint8_t* active,
+                                   const uint8_t* take, void* rsub, void* zs, void* gs, void* rck,
+                                   void* sck, int store_slot, int idx_max, int nblk, void* dots,
+                                   int64_t C, int64_t D, int dtype, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  using namespace b2;
+  if (!z || !r || !g || !minv || !active || !take || !rsub || !zs || !gs || !rck || !sck) return B2_ERR_NULL;
+  if (C <= 0 || D <= 0) return B2_OK;
+  if (C > 65535) return B2_ERR_TOO_LARGE;
+  if (nblk < 0 || nblk > kNutsMaxBlocks) return B2_ERR_BAD_SHAPE;
+  if (nblk > 0 && !dots) return B2_ERR_NULL;
+  const unsigned bx = bx_for(D, C);
+  if (nblk > 0 && (!workspace || workspace_bytes < (size_t)C * bx * 2 * nblk * sizeof(double)))
+    return B2_ERR_WORKSPACE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  double* partials = reinterpret_cast<double*>(workspace);
+  dim3 grid(bx, (unsigned)C, 1);
+  const int64_t cks = C * D;
+  if (dtype == B2_F32) {
+    nuts_leaf_vector_kernel<float><<<grid, 256, 0, s>>>(
+        (const float*)z, (const float*)r, (const float*)g, (const float*)minv, minv_chain_stride, active,
+        take, (float*)rsub, (float*)zs, (float*)gs, (float*)rck, (float*)sck, cks, store_slot, idx_max,
+        nblk, partials, C, D);
+    if (nblk > 0)
+      nuts_dots_finish_kernel<float><<<(unsigned)((C * 2 * nblk + 127) / 128), 128, 0, s>>>(
+          partials, (int)bx, 2 * nblk, (float*)dots, C);
+  } else if (dtype == B2_F64) {
+    nuts_leaf_vector_kernel<double><<<grid, 256, 0, s>>>(
+        (const double*)z, (const double*)r, (const double*)g, (const double*)minv, minv_chain_stride,
+        active, take, (double*)rsub, (double*)zs, (double*)gs, (double*)rck, (double*)sck, cks,
+        store_slot, idx_max, nblk, partials, C, D);
+    if (nblk > 0)
+      nuts_dots_finish_kernel<double><<<(unsigned)((C * 2 * nblk + 127) / 128), 128, 0, s>>>(
+          partials, (int)bx, 2 * nblk, (double*)dots, C);
+  } else {
+    return B2_ERR_BAD_DTYPE;
+  }
+  count_launch(nblk > 0 ? 2 : 1);
+  return check_launch();
+}

@@ -159,7 +159,11 @@ class HMC:
         N.check(lib.b2_leapfrog_half_kick_drift(z.data_ptr(), r.data_ptr(), g.data_ptr(),
                                                 eps.data_ptr(), minv.data_ptr(), D, act, C, D, dt,
                                                 N.stream_ptr(dev)), "b2_leapfrog_half_kick_drift")
-        U, g_new = self.potential.value_and_grad(z, active)
+        if isinstance(self.potential, NativePotential):
+            # native potentials write the new gradient over the old one (masked chains untouched)
+            U, g_new = self.potential.value_and_grad(z, active, out_grad=g)
+        else:
+            U, g_new = self.potential.value_and_grad(z, active)
         ke = torch.empty(C, dtype=z.dtype, device=dev)
         ws = N.workspace(dev, int(lib.b2_mcmc_workspace(C)), tag="mcmc")
         N.check(lib.b2_leapfrog_half_kick(r.data_ptr(), g_new.data_ptr(), eps.data_ptr(),
@@ -309,6 +313,27 @@ class NUTS(HMC):
             return self._z
         return self._sample_lockstep()
 
+    def _leaf_vector(self, z, rcur, g, minv, active8, take8, rsub, zs, gs, rck, sck, leaf):
+        """Everything a new leaf needs over the [C, D] state in one fused pass
+        (``b2_nuts_leaf_vector``).  Returns the U-turn flags [C] of the blocks ending at this leaf
+        (all False on even leaves)."""
+        C, D = z.shape
+        dev = z.device
+        idx_max = _popcount(leaf >> 1)
+        even = leaf % 2 == 0
+        nblk = 0 if even else _trailing_ones(leaf)
+        dots = torch.empty(C, max(2 * nblk, 1), dtype=z.dtype, device=dev)
+        lib = N.lib()
+        ws = N.workspace(dev, int(lib.b2_mcmc_workspace(C)), tag="mcmc")
+        N.check(lib.b2_nuts_leaf_vector(
+            z.data_ptr(), rcur.data_ptr(), g.data_ptr(), minv.data_ptr(), D, active8.data_ptr(),
+            take8.data_ptr(), rsub.data_ptr(), zs.data_ptr(), gs.data_ptr(), rck.data_ptr(),
+            sck.data_ptr(), idx_max if even else -1, idx_max, nblk, dots.data_ptr(), C, D,
+            N._DTYPES[z.dtype], ws.data_ptr(), ws.numel(), N.stream_ptr(dev)), "b2_nuts_leaf_vector")
+        if even:
+            return torch.zeros(C, dtype=torch.bool, device=dev)
+        return (dots[:, : 2 * nblk] <= 0).any(-1)
+
     def _sample_lockstep(self):
         C, D = self.C, self.D
         pot = self.potential
@@ -355,8 +380,8 @@ class NUTS(HMC):
                 z, rcur, g_new, U_new, ke = self._leapfrog(z, rcur, g, eps, minv, act8)
                 self.num_leapfrogs -= C  # recount only active chains below
                 self._leap_dev = active.sum() if self._leap_dev is None else self._leap_dev + active.sum()
-                g = torch.where(active[:, None], g_new, g)
-                ru_c = rcur * s
+                if g_new is not g:
+                    g = torch.where(active[:, None], g_new, g)
                 energy = U_new + ke
                 energy = torch.where(torch.isnan(energy), torch.full_like(energy, float("inf")), energy)
                 delta = energy - energy0
@@ -372,24 +397,10 @@ class NUTS(HMC):
                     nw = _logaddexp(logw_sub, w_leaf)
                     take = active & (self._rand(C) < torch.exp(w_leaf - nw))
                 logw_sub = torch.where(active, nw, logw_sub)
-                tk = take[:, None]
-                zs = torch.where(tk, z, zs)
-                gs = torch.where(tk, g, gs)
                 Us = torch.where(take, U_new, Us)
-                rsub = rsub + torch.where(active[:, None], ru_c, torch.zeros_like(ru_c))
-                turn_now = torch.zeros(C, dtype=torch.bool, device=dev)
-                idx_max = _popcount(leaf >> 1)
-                if leaf % 2 == 0:
-                    rck[idx_max] = ru_c
-                    sck[idx_max] = rsub
-                else:
-                    for k in range(idx_max, idx_max - _trailing_ones(leaf), -1):
-                        blk = rsub - sck[k] + rck[k]
-                        rho = blk - 0.5 * (rck[k] + ru_c)
-                        a_first = (rck[k] * rho).sum(-1)
-                        a_last = (ru_c * rho).sum(-1)
-                        turn_now = turn_now | (a_first <= 0) | (a_last <= 0)
-                    turn_now = turn_now & active & ~div_now
+                turn_now = self._leaf_vector(z, rcur, g, minv, act8, take.to(torch.uint8), rsub, zs, gs,
+                                             rck, sck, leaf)
+                turn_now = turn_now & active & ~div_now
                 diverged = diverged | div_now
                 done = done | div_now | turn_now
                 if (leaf & 15) == 15 and leaf + 1 < nleaves and bool(done.all()):

@@ -50,12 +50,12 @@ class NativePotential:
     def dim(self):
         return self.D
 
-    def value_and_grad(self, z, active=None):
+    def value_and_grad(self, z, active=None, out_grad=None):
         N.require_cuda(z, "NativePotential")
         C = z.shape[0]
         z = z.contiguous()
         U = torch.empty(C, dtype=self.dtype, device=z.device)
-        g = torch.empty_like(z)
+        g = out_grad if out_grad is not None else torch.empty_like(z)
         need = int(N.lib().b2_mcmc_workspace(C))
         ws = N.workspace(z.device, need, tag="mcmc")
         N.check(N.lib().b2_potential_grad(

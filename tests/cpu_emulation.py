@@ -80,7 +80,32 @@ def _agr_launch(self, t):
     t["steps"] = torch.tensor([self._host[p]["step"] for p in t["params"]], dtype=torch.int32)
 
 
-def _native_value_and_grad(self, z, active=None):
+def _leaf_vector(self, z, rcur, g, minv, active8, take8, rsub, zs, gs, rck, sck, leaf):
+    """torch stand-in for b2_nuts_leaf_vector (same contract, in-place on rsub/zs/gs/rck/sck)."""
+    active, take = active8.bool(), take8.bool()
+    ru = rcur * minv.sqrt()
+    rsub.add_(torch.where(active[:, None], ru, torch.zeros_like(ru)))
+    zs.copy_(torch.where((take & active)[:, None], z, zs))
+    gs.copy_(torch.where((take & active)[:, None], g, gs))
+    idx_max = bin(leaf >> 1).count("1")
+    turn = torch.zeros(z.shape[0], dtype=torch.bool)
+    if leaf % 2 == 0:
+        am = active[:, None]
+        rck[idx_max] = torch.where(am, ru, rck[idx_max])
+        sck[idx_max] = torch.where(am, rsub, sck[idx_max])
+    else:
+        t, nblk = leaf, 0
+        while t & 1:
+            nblk += 1
+            t >>= 1
+        for k in range(idx_max, idx_max - nblk, -1):
+            blk = rsub - sck[k] + rck[k]
+            rho = blk - 0.5 * (rck[k] + ru)
+            turn = turn | ((rck[k] * rho).sum(-1) <= 0) | ((ru * rho).sum(-1) <= 0)
+    return turn
+
+
+def _native_value_and_grad(self, z, active=None, out_grad=None):
     from pyro_b200 import _native as N
     if self.model_id == N.MODEL_HIER_NORMAL:
         U = omcmc.eight_schools_potential(self._keep[0], self._keep[1], self._model.hyper[0], self._model.hyper[1])
@@ -91,7 +116,12 @@ def _native_value_and_grad(self, z, active=None):
         g, u = omcmc.potential_grad(U, zc)
         Us.append(u)
         gs.append(g)
-    return torch.stack(Us), torch.stack(gs)
+    G = torch.stack(gs)
+    if out_grad is not None:
+        a = torch.ones(z.shape[0], dtype=torch.bool) if active is None else active.bool()
+        out_grad.copy_(torch.where(a[:, None], G, out_grad))
+        G = out_grad
+    return torch.stack(Us), G
 
 
 def _leapfrog(self, z, r, g, eps, minv, active=None):
@@ -100,7 +130,9 @@ def _leapfrog(self, z, r, g, eps, minv, active=None):
     am = a[:, None]
     r.copy_(torch.where(am, r + 0.5 * e * (-g), r))
     z.copy_(torch.where(am, z + e * (minv * r), z))
+    g_old = g.clone()
     U, g_new = self.potential.value_and_grad(z, active)
+    g_new = torch.where(am, g_new, g_old)
     r.copy_(torch.where(am, r + 0.5 * e * (-g_new), r))
     ke = 0.5 * (minv * r * r).sum(-1)
     self.num_leapfrogs += z.shape[0]
@@ -134,10 +166,13 @@ def enabled():
     optim.AdagradRMSProp._launch = _agr_launch
     pot.NativePotential.value_and_grad = _native_value_and_grad
     nuts.HMC._leapfrog = _leapfrog
+    saved_leaf = nuts.NUTS._leaf_vector
+    nuts.NUTS._leaf_vector = _leaf_vector
     ops.reduce_to = _reduce_to
     try:
         yield
     finally:
         pdist._BernoulliLinear._fused_sum = saved_glm
+        nuts.NUTS._leaf_vector = saved_leaf
         (ops.site_score, N.require_cuda, optim.ClippedAdam._launch, optim.AdagradRMSProp._launch,
          pot.NativePotential.value_and_grad, nuts.HMC._leapfrog, ops.reduce_to) = saved

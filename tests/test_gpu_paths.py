@@ -311,3 +311,33 @@ def test_generic_model_nuts_runs_and_agrees():
     chain = omcmc.NUTSChain(omcmc.logistic_potential(X.cpu(), y.cpu(), 1.0), 3, seed=5)
     ref, _ = chain.run(torch.zeros(3, dtype=torch.float64), 150, 500)
     assert torch.allclose(s.mean(0), ref.mean(0), atol=0.15)
+
+
+def test_nuts_leaf_vector_kernel_matches_torch_restatement():
+    """b2_nuts_leaf_vector (fused per-leaf bookkeeping of the lockstep tree) against the plain
+    torch restatement used by the CPU tier, on even (checkpoint store) and odd (U-turn dots) leaves."""
+    if EMULATE:
+        pytest.skip("needs the device kernel")
+    import cpu_emulation
+    from pyro_b200.infer.mcmc.nuts import NUTS as K
+    torch.manual_seed(0)
+    C, D, slots = 5, 1037, 6
+    for dtype in (torch.float64, torch.float32):
+        mk = lambda *s: torch.randn(*s, device=DEV, dtype=dtype)  # noqa: E731
+        z, r, g = mk(C, D), mk(C, D), mk(C, D)
+        minv = torch.rand(C, D, device=DEV, dtype=dtype) + 0.5
+        active = torch.tensor([1, 0, 1, 1, 1], device=DEV, dtype=torch.uint8)
+        take = torch.tensor([1, 1, 0, 1, 0], device=DEV, dtype=torch.uint8)
+        state = [mk(C, D), mk(C, D), mk(C, D), mk(slots, C, D), mk(slots, C, D)]
+        for leaf in (0, 2, 6, 1, 3, 7, 11):
+            a = [t.clone() for t in state]
+            b = [t.cpu().clone() for t in state]
+            kern = K.__new__(K)
+            turn_k = K._leaf_vector(kern, z, r, g, minv, active, take, *a, leaf)
+            turn_t = cpu_emulation._leaf_vector(None, z.cpu(), r.cpu(), g.cpu(), minv.cpu(), active.cpu(),
+                                                take.cpu(), *b, leaf)
+            tol = 1e-12 if dtype == torch.float64 else 1e-5
+            for x, y in zip(a, b):
+                assert torch.allclose(x.cpu(), y, atol=tol, rtol=tol), leaf
+            act = active.bool().cpu()
+            assert torch.equal(turn_k.cpu()[act], turn_t[act]), leaf
