@@ -69,7 +69,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -353,11 +353,11 @@ def main():
     torch.cuda.synchronize(dev)
     if rank == 0:
         sampler.start()
+        time.sleep(0.15)
     ms, loss = time_steps(svi, step_args, a.steps, a.warmup + 2, dev, flush)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -390,6 +390,7 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = e2e_n / (float(e2e_ms) * 1e-3)
     h2d = Xh.numel() * 4 + yh.numel() * 4
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:

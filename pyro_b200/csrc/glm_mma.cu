@@ -49,6 +49,17 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // D must be 32 (four k-steps / four n-tiles of 8).
 __global__ void __launch_bounds__(256, 2) glm_bernoulli_mma_kernel(const float* __restrict__ X,
                                                                    const float* __restrict__ y,
@@ -144,7 +155,8 @@ __global__ void __launch_bounds__(256, 2) glm_bernoulli_mma_kernel(const float* 
         xc[n][1] = to_tf32(xr2[kMmaPitch + n * 8 + g]);
       }
       const float y0 = ys[buf][r0 + 2 * t], y1 = ys[buf][r0 + 2 * t + 1];
-      const bool v0 = (r0 + 2 * t) < rows, v1 = (r0 + 2 * t + 1) < rows;
+      // rows beyond the end of the data (last tile only) are masked by a 0/1 weight
+      const float v0 = (r0 + 2 * t) < rows ? 1.f : 0.f, v1 = (r0 + 2 * t + 1) < rows ? 1.f : 0.f;
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
         // logits^T fragment: c0 = (p = g, r = 2t), c1 = (g, 2t+1), c2 = (g+8, 2t), c3 = (g+8, 2t+1)
@@ -156,14 +168,16 @@ __global__ void __launch_bounds__(256, 2) glm_bernoulli_mma_kernel(const float* 
         for (int i = 0; i < 4; ++i) {
           const float l = c[i];
           const float yy = (i & 1) ? y1 : y0;
-          const bool valid = (i & 1) ? v1 : v0;
-          const float e = __expf(-fabsf(l));
+          const float vw = (i & 1) ? v1 : v0;
+          // e = exp(-|l|) in (0, 1]; SFU ops issued directly (ftz forms: no denormal fix-up code)
+          const float e = ex2_ftz(-1.4426950408889634f * fabsf(l));
+          const float den = 1.f + e;
           float inv;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f + e));
-          const float sp = fmaxf(l, 0.f) + __logf(1.f + e);
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+          const float sp = fmaf(lg2_ftz(den), 0.6931471805599453f, fmaxf(l, 0.f));
           const float sg = (l >= 0.f) ? inv : e * inv;
-          const float lp = valid ? (yy * l - sp) : 0.f;
-          const float gg = valid ? (yy - sg) : 0.f;
+          const float lp = vw * fmaf(yy, l, -sp);
+          const float gg = vw * (yy - sg);
           sum[m][i >> 1] += lp;
           db[m][i >> 1] += gg;
           gv[i] = gg;

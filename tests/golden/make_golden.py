@@ -19,6 +19,8 @@ Files written
   svi_logistic.npz     5 SVI steps (Trace_ELBO, 8 vectorised particles, ClippedAdam) of Bayesian
                        logistic regression with recorded noise: losses and parameters per step
   optim.npz            ClippedAdam / AdagradRMSProp trajectories on given gradients
+  def_meanfield.npz    config-5 structure (sparse gamma DEF, TraceMeanField_ELBO, AdagradRMSProp): 6 losses
+                       and the final unconstrained parameters
   mcmc.npz             potentials + gradients, velocity_verlet trajectories, integrator KATs,
                        adaptation schedules, dual averaging / Welford sequences,
                        eight_schools NUTS posterior moments (4 chains, 200+200), stats (r_hat, ESS)
@@ -510,11 +512,45 @@ def mcmc_cases():
     print("mcmc ok; es long mu/tau mean:", out["es.long.mu.mean"], out["es.long.tau.mean"])
 
 
+def def_meanfield():
+    """BASELINE config 5 structure at reduced size through the reference: sparse gamma DEF model of
+    tests/models.py (the SAME source, with `pyro_b200` imports rewritten to `pyro`),
+    TraceMeanField_ELBO with 3 vectorised particles, AdagradRMSProp, latent values injected as a
+    deterministic function of the variational parameters."""
+    import re
+    import types
+    src = open(os.path.join(os.path.dirname(HERE), "models.py")).read()
+    src = src.replace("import pyro_b200 as pyro", "import pyro") \
+             .replace("import pyro_b200.distributions as dist", "import pyro.distributions as dist") \
+             .replace("from pyro_b200 import poutine", "from pyro import poutine") \
+             .replace("poutine.Messenger", "poutine.messenger.Messenger")
+    src = re.sub(r"def logistic_model_fused.*?\n\n\ndef ", "def ", src, flags=re.S)
+    src = re.sub(r"def logistic_model_sharded.*?\n\n\ndef logistic_guide_sharded", "def logistic_guide_sharded", src, flags=re.S)
+    mod = types.ModuleType("refmodels")
+    exec(compile(src, "refmodels", "exec"), mod.__dict__)
+    torch.manual_seed(0)
+    torch.set_default_dtype(torch.float64)
+    n, img, widths, P = 6, 32, (10, 6, 4), 3
+    x = torch.poisson(torch.full((n, img), 2.0))
+    inj = {s_: (lambda a, r, k=k: (a / r) * (0.6 + 0.1 * k)) for k, s_ in
+           enumerate(["w_top", "w_mid", "w_bottom", "z_top", "z_mid", "z_bottom"])}
+    pyro.clear_param_store()
+    m = mod.SparseGammaDEF(img, widths, dtype=torch.float64, inject=inj, particles=P)
+    svi = SVI(m.model, m.guide, pyro.optim.AdagradRMSProp({"eta": 0.5, "t": 0.1}),
+              TraceMeanField_ELBO(num_particles=P, vectorize_particles=True, max_plate_nesting=1))
+    losses = [svi.step(x) for _ in range(6)]
+    out = {"x": npy(x), "losses": np.asarray(losses), "P": P, "widths": np.asarray(widths)}
+    for k, v in pyro.get_param_store().named_parameters():
+        out["param." + k] = npy(v)
+    np.savez_compressed(os.path.join(HERE, "def_meanfield.npz"), **out)
+    print("def_meanfield ok", losses[:3])
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["dist_fixtures", "dist_random", "kl", "optim", "svi_logistic",
-                             "elbo_grad", "mcmc"]
+                             "elbo_grad", "mcmc", "def_meanfield"]
     fns = {"dist_fixtures": dist_fixtures, "dist_random": dist_random, "kl": kl_cases,
            "optim": optim_cases, "svi_logistic": svi_logistic, "elbo_grad": elbo_grad,
-           "mcmc": mcmc_cases}
+           "mcmc": mcmc_cases, "def_meanfield": def_meanfield}
     for w in which:
         fns[w]()

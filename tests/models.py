@@ -93,3 +93,81 @@ def logreg_mcmc_model(X, y):
     beta = pyro.sample("beta", dist.Normal(X.new_zeros(D), X.new_ones(D)))
     logits = (X * beta.unsqueeze(-2)).sum(-1) if beta.dim() > 1 else (X * beta).sum(-1)
     return pyro.sample("y", dist.Bernoulli(logits=logits), obs=y)
+
+
+class SparseGammaDEF:
+    """Sparse gamma deep exponential family (BASELINE config 5; structure of
+    examples/sparse_gamma_def.py:43-165): three layers of Gamma weights and per-datapoint Gamma
+    latents, Poisson likelihood, mean-field Gamma guide with softplus-parameterised shape/mean.
+    ``inject`` (optional) maps site name -> callable(alpha, rate) -> value, used by tests to make
+    the latent draws a deterministic function of the parameters on every device."""
+
+    def __init__(self, image_size=4096, widths=(100, 40, 15), device="cpu", dtype=torch.float32, inject=None,
+                 particles=1):
+        self.top, self.mid, self.bottom = widths
+        self.image_size = image_size
+        t = lambda v: torch.tensor(v, device=device, dtype=dtype)  # noqa: E731
+        self.alpha_z, self.beta_z, self.alpha_w, self.beta_w = t(0.1), t(0.1), t(0.1), t(0.3)
+        self.device, self.dtype = device, dtype
+        self.inject = inject
+        self.particles = particles  # only used to give injected values the particle dim
+
+    def model(self, x):
+        n = x.size(0)
+        shapes = {"top": (self.top, self.mid), "mid": (self.mid, self.bottom), "bottom": (self.bottom, self.image_size)}
+        w = {}
+        for name, (a, b) in shapes.items():
+            with pyro.plate("w_%s_plate" % name, a * b):
+                v = pyro.sample("w_%s" % name, dist.Gamma(self.alpha_w, self.beta_w))
+            w[name] = v.reshape(a, b) if v.dim() == 1 else v.reshape(-1, a, b)
+        with pyro.plate("data", n):
+            z = pyro.sample("z_top", dist.Gamma(self.alpha_z, self.beta_z).expand([self.top]).to_event(1))
+            mean = torch.matmul(z, w["top"])
+            z = pyro.sample("z_mid", dist.Gamma(self.alpha_z, self.beta_z / mean).to_event(1))
+            mean = torch.matmul(z, w["mid"])
+            z = pyro.sample("z_bottom", dist.Gamma(self.alpha_z, self.beta_z / mean).to_event(1))
+            mean = torch.matmul(z, w["bottom"])
+            pyro.sample("obs", dist.Poisson(mean).to_event(1), obs=x)
+
+    def guide(self, x):
+        n = x.size(0)
+        sp = torch.nn.functional.softplus
+        gen = torch.Generator().manual_seed(0)
+
+        def init(shape, mean):
+            return lambda: (mean + 0.1 * torch.randn(shape, generator=gen)).to(self.device, self.dtype)
+
+        def gamma_site(name, shape, event):
+            alpha = sp(pyro.param("alpha_%s" % name, init(shape, 0.5)))
+            mean = sp(pyro.param("mean_%s" % name, init(shape, 0.0)))
+            d = dist.Gamma(alpha, alpha / mean)
+            d = d.to_event(1) if event else d
+            site = name.replace("_q", "")
+            if self.inject is not None:
+                v = self.inject[site](alpha, alpha / mean)
+                if self.particles > 1:
+                    # batch dims: [particles, plate] (+ event dim for the z sites)
+                    v = v.expand((self.particles,) + tuple(v.shape))
+                with InjectValue({site: v}):
+                    pyro.sample(site, d)
+            else:
+                pyro.sample(site, d)
+
+        for name, width in (("w_q_top", self.top * self.mid), ("w_q_mid", self.mid * self.bottom),
+                            ("w_q_bottom", self.bottom * self.image_size)):
+            with pyro.plate(name.replace("_q", "") + "_plate", width):
+                gamma_site(name, (width,), False)
+        with pyro.plate("data", n):
+            gamma_site("z_q_top", (n, self.top), True)
+            gamma_site("z_q_mid", (n, self.mid), True)
+            gamma_site("z_q_bottom", (n, self.bottom), True)
+
+
+class InjectValue(poutine.Messenger):
+    def __init__(self, vals):
+        self.vals = vals
+
+    def _pyro_sample(self, msg):
+        if msg["name"] in self.vals and not msg["is_observed"]:
+            # only the value is fixed; the site still goes through plate broadcasting
+            msg["value"] = self.vals[msg["name"]]

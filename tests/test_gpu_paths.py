@@ -341,3 +341,10 @@ def test_nuts_leaf_vector_kernel_matches_torch_restatement():
                 assert torch.allclose(x.cpu(), y, atol=tol, rtol=tol), leaf
             act = active.bool().cpu()
             assert torch.equal(turn_k.cpu()[act], turn_t[act]), leaf
+
+
+def test_sparse_gamma_def_meanfield_matches_reference():
+    """BASELINE config 5 structure through the CUDA kernels (fused Gamma||Gamma KL, Poisson site,
+    fused AdagradRMSProp): the reference's 6-step loss trajectory and final parameters (fp64, 1e-9)."""
+    from test_host_logic_cpu import _def_meanfield
+    _def_meanfield(DEV)

@@ -309,3 +309,26 @@ def test_vectorised_adaptation_matches_reference_pieces():
     for s in torch.as_tensor(g["wf.samples"]):
         wf.update(s.expand(3, -1))
     assert torch.allclose(wf.get_covariance(True)[2], torch.as_tensor(g["wf.cov_reg"]), atol=1e-12)
+
+
+def _def_meanfield(device):
+    g = load_npz("def_meanfield.npz")
+    torch.set_default_dtype(torch.float64)
+    x = torch.as_tensor(g["x"]).to(device)
+    P, widths = int(g["P"]), tuple(int(w) for w in g["widths"])
+    inj = {s_: (lambda a, r, k=k: (a / r) * (0.6 + 0.1 * k)) for k, s_ in
+           enumerate(["w_top", "w_mid", "w_bottom", "z_top", "z_mid", "z_bottom"])}
+    m = models.SparseGammaDEF(x.shape[1], widths, device=device, dtype=torch.float64, inject=inj, particles=P)
+    svi = SVI(m.model, m.guide, AdagradRMSProp({"eta": 0.5, "t": 0.1}),
+              TraceMeanField_ELBO(num_particles=P, vectorize_particles=True, max_plate_nesting=1))
+    losses = [svi.step(x) for _ in range(6)]
+    assert np.allclose(losses, g["losses"], rtol=1e-9), (losses, g["losses"])
+    for k, v in pyro.get_param_store().named_parameters():
+        assert torch.allclose(v.detach().cpu(), torch.as_tensor(g["param." + k]), atol=1e-9, rtol=1e-9), k
+
+
+def test_sparse_gamma_def_meanfield_matches_reference(emu):
+    """BASELINE config 5 structure (three Gamma layers + Poisson likelihood, TraceMeanField_ELBO with
+    Gamma||Gamma KL terms, AdagradRMSProp): 6-step loss trajectory and final parameters of the
+    unmodified reference."""
+    _def_meanfield("cpu")
