@@ -35,10 +35,11 @@ constexpr int kMmaPitch = 36;                    // floats per staged row (32 + 
 constexpr int kMmaWarps = 8;                     // 4 row groups x 2 particle halves
 constexpr int kMmaParticles = 64;                // particles per CTA (blockIdx.y slabs)
 
+// fp32 -> tf32 with round-to-nearest (ties away), done with two integer ALU ops.  cvt.rna.tf32.f32
+// executes on the same 16-lane pipe as MUFU; at 3 conversions per (row, particle) it doubled the
+// load of the pipe that bounds this kernel (ncu: profiles/ncu_glm_mma_r1.txt).
 __device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
+  return (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
 }
 
 // D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col)

@@ -900,3 +900,6 @@ def _bernoulli_new(cls, probs=None, logits=None, validate_args=None):
 
 Bernoulli.__new__ = staticmethod(_bernoulli_new)
 __all__ += ["LinearPredictor", "linear_predictor"]
+
+from .hmm import GaussianHMM  # noqa: E402,F401
+__all__ += ["GaussianHMM"]

@@ -1,0 +1,133 @@
+"""GaussianHMM (BASELINE config 3).
+
+Interface mirrors pyro/distributions/hmm.py:434-582 (constructor arguments, shapes, ``log_prob``).
+The reference eliminates the time axis with a parallel scan of Gaussian tensordots
+(pyro/ops/gaussian.py:510-597): O(log T) depth but O(T (2H)^3) work and a materialised
+``[T, 2H, 2H]`` precision tensor (41.9 GB at H=512, T=10 000).  Here ``log_prob`` is the
+mathematically identical marginal likelihood computed by the innovation form of the Kalman
+filter: O(T H^3) work, O(H^2) live state, and every heavy operation is a dense ``H x H`` GEMM.
+
+Round-1 status: the GEMMs / small Choleskys run through cuBLAS / cuSOLVER (``torch.matmul``,
+``torch.linalg``) -- plain library contractions, fp32 (or TF32 tensor cores with ``tf32=True``) --
+and gradients come from autograd through the recursion.  There is no hand-written tcgen05 kernel
+for this row yet; parity with the reference is pinned by
+tests/golden/hmm.npz.
+"""
+import math
+
+import torch
+from torch.distributions import constraints
+
+from . import Distribution, Independent, MultivariateNormal, Normal
+
+
+def _loc_cov(d):
+    """(loc, covariance) of a MultivariateNormal or an Independent(Normal, 1)."""
+    if isinstance(d, MultivariateNormal):
+        L = d.scale_tril
+        return d.loc, L @ L.transpose(-1, -2)
+    if isinstance(d, Independent) and isinstance(d.base_dist, Normal) and d.reinterpreted_batch_ndims == 1:
+        base = d.base_dist
+        shape = base.batch_shape
+        loc = base.loc.expand(shape)
+        var = (base.scale ** 2).expand(shape)
+        return loc, torch.diag_embed(var)
+    if hasattr(d, "loc") and hasattr(d, "covariance_matrix"):  # a torch.distributions MVN
+        return d.loc, d.covariance_matrix
+    raise ValueError("expected a MultivariateNormal or Normal(...).to_event(1), got {}".format(type(d).__name__))
+
+
+class GaussianHMM(Distribution):
+    has_rsample = True
+    arg_constraints = {}
+    support = constraints.independent(constraints.real, 2)
+
+    def __init__(self, initial_dist, transition_matrix, transition_dist, observation_matrix,
+                 observation_dist, validate_args=None, duration=None, tf32=False):
+        hidden_dim, obs_dim = observation_matrix.shape[-2:]
+        self.hidden_dim, self.obs_dim = hidden_dim, obs_dim
+        self.duration = duration
+        self.tf32 = tf32
+        self._m0, self._P0 = _loc_cov(initial_dist)
+        self._F = transition_matrix
+        self._bw, self._Q = _loc_cov(transition_dist)
+        self._H = observation_matrix
+        self._bv, self._R = _loc_cov(observation_dist)
+        assert self._m0.shape[-1] == hidden_dim and self._F.shape[-2:] == (hidden_dim, hidden_dim)
+        assert self._bw.shape[-1] == hidden_dim and self._bv.shape[-1] == obs_dim
+        shape = torch.broadcast_shapes(self._m0.shape[:-1] + (1,), self._F.shape[:-2], self._bw.shape[:-1],
+                                       self._H.shape[:-2], self._bv.shape[:-1])
+        batch_shape, time_shape = shape[:-1], shape[-1:]
+        if duration is not None and time_shape[0] == 1:
+            time_shape = torch.Size((duration,))
+        super().__init__(batch_shape, time_shape + (obs_dim,))
+
+    def expand(self, batch_shape, _instance=None):
+        new = GaussianHMM.__new__(GaussianHMM)
+        new.__dict__.update(self.__dict__)
+        new._batch_shape = torch.Size(torch.broadcast_shapes(self.batch_shape, torch.Size(batch_shape)))
+        return new
+
+    # time-dependent parameters carry the time axis at dim -3 (matrices) / -2 (vectors)
+    @staticmethod
+    def _at(x, t, mat):
+        tdim = -3 if mat else -2
+        if x.dim() >= -tdim and x.shape[tdim] != 1:
+            return x.select(tdim, t)
+        if x.dim() >= -tdim:
+            return x.squeeze(tdim)
+        return x
+
+    def log_prob(self, value):
+        T = value.shape[-2]
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(self.tf32)
+        try:
+            return self._filter(value, T)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+
+    def _filter(self, value, T):
+        O = self.obs_dim
+        m = self._m0.unsqueeze(-2)            # [..., 1, H] row vector
+        P = self._P0
+        ll = 0.0
+        const = O * math.log(2 * math.pi)
+        for t in range(T):
+            F = self._at(self._F, t, True)
+            Hm = self._at(self._H, t, True)
+            bw = self._at(self._bw, t, False).unsqueeze(-2)
+            bv = self._at(self._bv, t, False).unsqueeze(-2)
+            Q = self._at(self._Q, t, True)
+            R = self._at(self._R, t, True)
+            # predict:  z_t = z_{t-1} F + w
+            m = m @ F + bw
+            P = F.transpose(-1, -2) @ P @ F + Q
+            # innovation:  x_t = z_t H + v
+            PH = P @ Hm                                     # [..., H, O]
+            S = Hm.transpose(-1, -2) @ PH + R               # [..., O, O]
+            v = value[..., t:t + 1, :] - (m @ Hm + bv)      # [..., 1, O]
+            Ls = torch.linalg.cholesky(S)
+            vs = torch.linalg.solve_triangular(Ls, v.transpose(-1, -2), upper=False)   # [..., O, 1]
+            ll = ll - 0.5 * ((vs * vs).sum((-1, -2)) + const) - Ls.diagonal(dim1=-2, dim2=-1).log().sum(-1)
+            # update
+            Kt = torch.cholesky_solve(PH.transpose(-1, -2), Ls)                        # S^-1 H^T P  [..., O, H]
+            m = m + v @ Kt
+            P = P - PH @ Kt
+            P = 0.5 * (P + P.transpose(-1, -2))
+        return ll
+
+    def rsample(self, sample_shape=torch.Size()):
+        T = self.event_shape[0] if self.duration is None else self.duration
+        shape = torch.Size(sample_shape) + self.batch_shape
+        L0 = torch.linalg.cholesky(self._P0)
+        z = self._m0 + (L0 @ torch.randn(shape + (self.hidden_dim, 1), dtype=L0.dtype, device=L0.device)).squeeze(-1)
+        xs = []
+        for t in range(T):
+            Lq = torch.linalg.cholesky(self._at(self._Q, t, True))
+            Lr = torch.linalg.cholesky(self._at(self._R, t, True))
+            w = (Lq @ torch.randn(shape + (self.hidden_dim, 1), dtype=L0.dtype, device=L0.device)).squeeze(-1)
+            z = (z.unsqueeze(-2) @ self._at(self._F, t, True)).squeeze(-2) + self._at(self._bw, t, False) + w
+            e = (Lr @ torch.randn(shape + (self.obs_dim, 1), dtype=L0.dtype, device=L0.device)).squeeze(-1)
+            xs.append((z.unsqueeze(-2) @ self._at(self._H, t, True)).squeeze(-2) + self._at(self._bv, t, False) + e)
+        return torch.stack(xs, dim=-2)

@@ -21,6 +21,7 @@ Files written
   optim.npz            ClippedAdam / AdagradRMSProp trajectories on given gradients
   def_meanfield.npz    config-5 structure (sparse gamma DEF, TraceMeanField_ELBO, AdagradRMSProp): 6 losses
                        and the final unconstrained parameters
+  hmm.npz              GaussianHMM.log_prob and parameter gradients (homogeneous, heterogeneous, wide)
   mcmc.npz             potentials + gradients, velocity_verlet trajectories, integrator KATs,
                        adaptation schedules, dual averaging / Welford sequences,
                        eight_schools NUTS posterior moments (4 chains, 200+200), stats (r_hat, ESS)
@@ -512,6 +513,43 @@ def mcmc_cases():
     print("mcmc ok; es long mu/tau mean:", out["es.long.mu.mean"], out["es.long.tau.mean"])
 
 
+def hmm_cases():
+    """GaussianHMM.log_prob + parameter gradients from the reference (parallel-scan formulation,
+    pyro/distributions/hmm.py:565-582) for time-homogeneous and time-heterogeneous models."""
+    g = torch.Generator().manual_seed(42)
+    torch.set_default_dtype(torch.float64)
+    out = {}
+
+    def rn(*s):
+        return torch.randn(*s, generator=g)
+
+    def spd(*lead, n):
+        A = rn(*lead, n, n)
+        return A @ A.transpose(-1, -2) / n + 0.5 * torch.eye(n)
+
+    for tag, H, O, T, B, hetero in (("homog", 3, 2, 7, (4,), False), ("hetero", 2, 3, 5, (), True),
+                                    ("wide", 6, 4, 19, (2,), False)):
+        tl = (T,) if hetero else ()
+        params = {"init_loc": rn(H), "init_cov": spd(n=H),
+                  "F": 0.5 * rn(*tl, H, H), "trans_loc": 0.1 * rn(*tl, H), "trans_cov": spd(*tl, n=H),
+                  "Hm": rn(*tl, H, O), "obs_loc": 0.1 * rn(*tl, O), "obs_scale": 0.5 + torch.rand(*tl, O, generator=g)}
+        value = rn(*B, T, O)
+        ps = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        d = dist.GaussianHMM(
+            dist.MultivariateNormal(ps["init_loc"], covariance_matrix=ps["init_cov"]), ps["F"],
+            dist.MultivariateNormal(ps["trans_loc"], covariance_matrix=ps["trans_cov"]), ps["Hm"],
+            dist.Normal(ps["obs_loc"], ps["obs_scale"]).to_event(1), duration=T)
+        lp = d.log_prob(value)
+        grads = torch.autograd.grad(lp.sum(), list(ps.values()))
+        out[tag + ".value"] = npy(value)
+        out[tag + ".lp"] = npy(lp)
+        for (k, v), gr in zip(params.items(), grads):
+            out["%s.%s" % (tag, k)] = npy(v)
+            out["%s.grad.%s" % (tag, k)] = npy(gr)
+    np.savez_compressed(os.path.join(HERE, "hmm.npz"), **out)
+    print("hmm ok", out["homog.lp"])
+
+
 def def_meanfield():
     """BASELINE config 5 structure at reduced size through the reference: sparse gamma DEF model of
     tests/models.py (the SAME source, with `pyro_b200` imports rewritten to `pyro`),
@@ -548,9 +586,9 @@ def def_meanfield():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["dist_fixtures", "dist_random", "kl", "optim", "svi_logistic",
-                             "elbo_grad", "mcmc", "def_meanfield"]
+                             "elbo_grad", "mcmc", "def_meanfield", "hmm"]
     fns = {"dist_fixtures": dist_fixtures, "dist_random": dist_random, "kl": kl_cases,
            "optim": optim_cases, "svi_logistic": svi_logistic, "elbo_grad": elbo_grad,
-           "mcmc": mcmc_cases, "def_meanfield": def_meanfield}
+           "mcmc": mcmc_cases, "def_meanfield": def_meanfield, "hmm": hmm_cases}
     for w in which:
         fns[w]()
