@@ -153,6 +153,54 @@ B2_HD float fast_log1p_unit(float e) {
 }
 B2_HD double fast_log1p_unit(double e) { return log1p(e); }
 
+// lgamma(x) and digamma(x) for fp32, x > 0, sharing one upward shift to x >= 8 and Stirling /
+// asymptotic series (absolute error ~1e-6 for lgamma, relative ~1e-6 for digamma; inside the fp32
+// tolerance).  libm's lgammaf alone is ~100 instructions and made the Gamma/Beta/Poisson kernels
+// issue-bound at 10-25% of HBM peak (profiles/micro_logprob_r1_before_fastgamma.txt).
+// Non-positive arguments (never produced by valid parameters) take the accurate route.
+template <bool WANT_PSI>
+B2_HD void lgamma_digamma_f32(float x, float& lg, float& psi) {
+  if (!(x > 0.f) || x > 1e30f) {
+    lg = lgammaf(x);
+    if (WANT_PSI) psi = digamma<float>(x);
+    return;
+  }
+  float prod = 1.f, acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool small = x < 8.f;
+    if (small) {
+      prod *= x;
+      if (WANT_PSI) acc -= fast_rcp(x);
+      x += 1.f;
+    }
+  }
+  const float lx = fast_log(x);
+  const float inv = fast_rcp(x);
+  const float inv2 = inv * inv;
+  // Stirling: (x - 1/2) ln x - x + ln sqrt(2 pi) + 1/(12x) - 1/(360 x^3) + 1/(1260 x^5)
+  lg = (x - 0.5f) * lx - x + 0.91893853320467274178f +
+       inv * (0.083333333333333333f - inv2 * (0.0027777777777777778f - inv2 * 0.00079365079365079365f)) -
+       fast_log(prod);
+  if (WANT_PSI) {
+    // psi(x) ~ ln x - 1/(2x) - 1/(12x^2) + 1/(120x^4) - 1/(252x^6)
+    psi = acc + lx - 0.5f * inv -
+          inv2 * (0.083333333333333333f - inv2 * (0.0083333333333333333f - inv2 * 0.0039682539682539683f));
+  }
+}
+template <typename T, bool WANT_PSI>
+B2_HD void lgamma_digamma(T x, T& lg, T& psi) {
+  if (sizeof(T) == 4) {
+    float l, p = 0.f;
+    lgamma_digamma_f32<WANT_PSI>((float)x, l, p);
+    lg = (T)l;
+    psi = (T)p;
+  } else {
+    lg = b2_lgamma(x);
+    if (WANT_PSI) psi = digamma(x);
+  }
+}
+
 // softplus(l) = log(1 + exp(l)) and sigmoid(l), sharing one exp.
 template <typename T>
 B2_HD void softplus_sigmoid(T l, T& sp, T& sg) {
@@ -296,11 +344,24 @@ template <typename T, bool GRAD>
 struct Eval<kGamma, T, GRAD> {
   static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
     const T a = p[0], b = p[1];
-    o.lp = xlogy(a, b) + xlogy(a - (T)1, x) - b * x - b2_lgamma(a);
-    if (GRAD) {
-      o.dx = (a - (T)1) / x - b;
-      o.dp[0] = b2_log(b) + b2_log(x) - digamma(a);
-      o.dp[1] = a / b - x;
+    T lga, psia;
+    lgamma_digamma<T, GRAD>(a, lga, psia);
+    if (sizeof(T) == 4) {
+      const T lb = fast_log(b), lx = fast_log(x);
+      // xlogy semantics: a zero coefficient contributes 0 even when the log is -inf
+      o.lp = ((a == (T)0) ? (T)0 : a * lb) + ((a == (T)1) ? (T)0 : (a - (T)1) * lx) - b * x - lga;
+      if (GRAD) {
+        o.dx = (a - (T)1) * fast_rcp(x) - b;
+        o.dp[0] = lb + lx - psia;
+        o.dp[1] = a * fast_rcp(b) - x;
+      }
+    } else {
+      o.lp = xlogy(a, b) + xlogy(a - (T)1, x) - b * x - lga;
+      if (GRAD) {
+        o.dx = (a - (T)1) / x - b;
+        o.dp[0] = b2_log(b) + b2_log(x) - psia;
+        o.dp[1] = a / b - x;
+      }
     }
   }
 };
@@ -312,13 +373,15 @@ struct Eval<kBeta, T, GRAD> {
   static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
     const T c1 = p[0], c0 = p[1];
     const T omx = (T)1 - x;
-    o.lp = (xlogy(c1 - (T)1, x) + xlogy(c0 - (T)1, omx)) + b2_lgamma(c1 + c0) -
-           (b2_lgamma(c1) + b2_lgamma(c0));
+    T lgs, psum, lg1, ps1, lg0, ps0;
+    lgamma_digamma<T, GRAD>(c1 + c0, lgs, psum);
+    lgamma_digamma<T, GRAD>(c1, lg1, ps1);
+    lgamma_digamma<T, GRAD>(c0, lg0, ps0);
+    o.lp = (xlogy(c1 - (T)1, x) + xlogy(c0 - (T)1, omx)) + lgs - (lg1 + lg0);
     if (GRAD) {
-      const T psum = digamma(c1 + c0);
       o.dx = (c1 - (T)1) / x - (c0 - (T)1) / omx;
-      o.dp[0] = b2_log(x) + psum - digamma(c1);
-      o.dp[1] = b2_log(omx) + psum - digamma(c0);
+      o.dp[0] = b2_log(x) + psum - ps1;
+      o.dp[1] = b2_log(omx) + psum - ps0;
     }
   }
 };
@@ -328,10 +391,21 @@ template <typename T, bool GRAD>
 struct Eval<kPoisson, T, GRAD> {
   static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
     const T rate = p[0];
-    o.lp = xlogy(x, rate) - rate - b2_lgamma(x + (T)1);
-    if (GRAD) {
-      o.dx = b2_log(rate) - digamma(x + (T)1);
-      o.dp[0] = x / rate - (T)1;
+    T lgx, psx;
+    lgamma_digamma<T, GRAD>(x + (T)1, lgx, psx);
+    if (sizeof(T) == 4) {
+      const T lr = fast_log(rate);
+      o.lp = ((x == (T)0) ? (T)0 : x * lr) - rate - lgx;
+      if (GRAD) {
+        o.dx = lr - psx;
+        o.dp[0] = x * fast_rcp(rate) - (T)1;
+      }
+    } else {
+      o.lp = xlogy(x, rate) - rate - lgx;
+      if (GRAD) {
+        o.dx = b2_log(rate) - psx;
+        o.dp[0] = x / rate - (T)1;
+      }
     }
   }
 };
@@ -342,14 +416,28 @@ template <typename T, bool GRAD>
 struct Eval<kCauchy, T, GRAD> {
   static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
     const T loc = p[0], scale = p[1];
-    const T u = (x - loc) / scale;
-    const T u2 = u * u;
-    o.lp = -Consts<T>::kLogPi - b2_log(scale) - b2_log1p(u2);
-    if (GRAD) {
-      const T w = (T)2 * u / (((T)1 + u2) * scale);  // d log1p(u^2) / d x
-      o.dx = -w;
-      o.dp[0] = w;
-      o.dp[1] = (-(T)1 + (T)2 * u2 / ((T)1 + u2)) / scale;
+    if (sizeof(T) == 4) {
+      const T inv_s = fast_rcp(scale);
+      const T u = (x - loc) * inv_s;
+      const T q = (T)1 + u * u;
+      o.lp = -Consts<T>::kLogPi - fast_log(scale) - fast_log(q);
+      if (GRAD) {
+        const T inv_q = fast_rcp(q);
+        const T w = (T)2 * u * inv_q * inv_s;
+        o.dx = -w;
+        o.dp[0] = w;
+        o.dp[1] = ((T)1 - (T)2 * inv_q) * inv_s;   // (-1 + 2u^2/(1+u^2)) / s
+      }
+    } else {
+      const T u = (x - loc) / scale;
+      const T u2 = u * u;
+      o.lp = -Consts<T>::kLogPi - b2_log(scale) - b2_log1p(u2);
+      if (GRAD) {
+        const T w = (T)2 * u / (((T)1 + u2) * scale);  // d log1p(u^2) / d x
+        o.dx = -w;
+        o.dp[0] = w;
+        o.dp[1] = (-(T)1 + (T)2 * u2 / ((T)1 + u2)) / scale;
+      }
     }
   }
 };
@@ -360,15 +448,28 @@ template <typename T, bool GRAD>
 struct Eval<kHalfCauchy, T, GRAD> {
   static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
     const T scale = p[0];
-    const T u = x / scale;
-    const T u2 = u * u;
-    T lp = (-Consts<T>::kLogPi - b2_log(scale) - b2_log1p(u2)) + Consts<T>::kLog2;
     const bool out = x < (T)0;
-    o.lp = out ? -b2_inf<T>() : lp;
-    if (GRAD) {
-      const T w = (T)2 * u / (((T)1 + u2) * scale);
-      o.dx = out ? (T)0 : -w;
-      o.dp[0] = out ? (T)0 : (-(T)1 + (T)2 * u2 / ((T)1 + u2)) / scale;
+    if (sizeof(T) == 4) {
+      const T inv_s = fast_rcp(scale);
+      const T u = x * inv_s;
+      const T q = (T)1 + u * u;
+      const T lp = (-Consts<T>::kLogPi - fast_log(scale) - fast_log(q)) + Consts<T>::kLog2;
+      o.lp = out ? -b2_inf<T>() : lp;
+      if (GRAD) {
+        const T inv_q = fast_rcp(q);
+        o.dx = out ? (T)0 : -(T)2 * u * inv_q * inv_s;
+        o.dp[0] = out ? (T)0 : ((T)1 - (T)2 * inv_q) * inv_s;
+      }
+    } else {
+      const T u = x / scale;
+      const T u2 = u * u;
+      const T lp = (-Consts<T>::kLogPi - b2_log(scale) - b2_log1p(u2)) + Consts<T>::kLog2;
+      o.lp = out ? -b2_inf<T>() : lp;
+      if (GRAD) {
+        const T w = (T)2 * u / (((T)1 + u2) * scale);
+        o.dx = out ? (T)0 : -w;
+        o.dp[0] = out ? (T)0 : (-(T)1 + (T)2 * u2 / ((T)1 + u2)) / scale;
+      }
     }
   }
 };

@@ -98,12 +98,16 @@ __global__ void __launch_bounds__(256) dirichlet_kernel(const EventArgs a) {
       const T c = cp[op0 + k], x = xp[ox + k];
       s_xlogy += xlogy(c - (T)1, x);
       s_conc += c;
-      s_lg += b2_lgamma(c);
+      T lgc, unused;
+      lgamma_digamma<T, false>(c, lgc, unused);
+      s_lg += lgc;
     }
     s_xlogy = group_sum(s_xlogy, G);
     s_conc = group_sum(s_conc, G);
     s_lg = group_sum(s_lg, G);
-    const T lp = s_xlogy + b2_lgamma(s_conc) - s_lg;
+    T lgsum, psum;
+    lgamma_digamma<T, GRAD>(s_conc, lgsum, psum);
+    const T lp = s_xlogy + lgsum - s_lg;
     const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
     const T slp = (m && live) ? lp * (T)a.scale : (T)0;
     if (lane == 0 && live) {
@@ -113,12 +117,14 @@ __global__ void __launch_bounds__(256) dirichlet_kernel(const EventArgs a) {
     if (GRAD && live) {
       T f = m ? (T)(a.weight * a.scale) : (T)0;
       if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[ou];
-      const T psum = digamma(s_conc);
       for (int k = lane; k < a.K; k += G) {
         const T c = cp[op0 + k], x = xp[ox + k];
         if (a.gx.ptr) reinterpret_cast<T*>(a.gx.ptr)[ogx + k] = m ? f * (c - (T)1) / x : (T)0;
-        if (a.gp0.ptr)
-          reinterpret_cast<T*>(a.gp0.ptr)[ogp0 + k] = m ? f * (b2_log(x) + psum - digamma(c)) : (T)0;
+        if (a.gp0.ptr) {
+          T lgc, psc;
+          lgamma_digamma<T, true>(c, lgc, psc);
+          reinterpret_cast<T*>(a.gp0.ptr)[ogp0 + k] = m ? f * (b2_log(x) + psum - psc) : (T)0;
+        }
       }
     }
   }
