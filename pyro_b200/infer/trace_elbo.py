@@ -34,6 +34,17 @@ def _compute_log_r(model_trace, guide_trace):
     return log_r
 
 
+_ONES = {}
+
+
+def _one_like(t):
+    key = (t.device, t.dtype)
+    one = _ONES.get(key)
+    if one is None:
+        one = _ONES[key] = torch.ones((), device=t.device, dtype=t.dtype)
+    return one
+
+
 def _all_reparam(guide_trace):
     for site in guide_trace.nodes.values():
         if site["type"] == "sample" and not getattr(site["fn"], "has_rsample", False):
@@ -143,8 +154,10 @@ class Trace_ELBO(ELBO):
                 elbo, terms = self._fused_particle(model_trace, guide_trace)
                 loss = loss + (-elbo / self.num_particles)
                 if trainable and terms:
-                    # every term's upstream gradient is exactly 1 (contract of the fused nodes)
-                    torch.autograd.backward(terms, retain_graph=self.retain_graph)
+                    # every term's upstream gradient is exactly 1 (contract of the fused nodes);
+                    # pass one cached ones-scalar instead of letting autograd fill a new one per term
+                    ones = [_one_like(t) for t in terms]
+                    torch.autograd.backward(terms, ones, retain_graph=self.retain_graph)
             else:
                 loss_particle, surrogate = self._differentiable_loss_particle(model_trace, guide_trace)
                 loss = loss + loss_particle / self.num_particles

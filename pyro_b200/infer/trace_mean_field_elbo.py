@@ -104,5 +104,6 @@ class TraceMeanField_ELBO(Trace_ELBO):
             trainable = any(site["type"] == "param" for trace in (model_trace, guide_trace)
                             for site in trace.nodes.values())
             if trainable and terms and not _no_backward:
-                torch.autograd.backward(terms, retain_graph=self.retain_graph)
+                from .trace_elbo import _one_like
+                torch.autograd.backward(terms, [_one_like(t) for t in terms], retain_graph=self.retain_graph)
         return loss
