@@ -23,8 +23,25 @@ __global__ void __launch_bounds__(256) kick_drift_kernel(T* __restrict__ z, T* _
     if (active && !active[c]) continue;
     const T e = eps[c];
     const T* mi = minv + c * minv_cs;
-    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D;
-         d += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // 4 independent elements per trip: all loads are issued before the first store
+    for (; d + 3 * stride < D; d += 4 * stride) {
+      T rv[4], gv[4], zv[4], mv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = c * D + d + u * stride;
+        rv[u] = r[i]; gv[u] = g[i]; zv[u] = z[i]; mv[u] = mi[d + u * stride];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = c * D + d + u * stride;
+        const T rn = rv[u] + (T)0.5 * e * (-gv[u]);
+        r[i] = rn;
+        z[i] = zv[u] + e * (mv[u] * rn);
+      }
+    }
+    for (; d < D; d += stride) {
       const int64_t i = c * D + d;
       const T rn = r[i] + (T)0.5 * e * (-g[i]);
       r[i] = rn;
@@ -48,13 +65,32 @@ __global__ void __launch_bounds__(256) kick_kernel(T* __restrict__ r, const T* _
     if (!(active && !active[c])) {
       const T e = eps[c];
       const T* mi = minv + c * minv_cs;
-      for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D;
-           d += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+      int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      double accf = 0.0;
+      for (; d + 3 * stride < D; d += 4 * stride) {
+        T t4 = (T)0;
+        T rv[4], gv[4], mv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t i = c * D + d + u * stride;
+          rv[u] = r[i]; gv[u] = g[i]; mv[u] = mi[d + u * stride];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const T rn = rv[u] + (T)0.5 * e * (-gv[u]);
+          r[c * D + d + u * stride] = rn;
+          t4 += mv[u] * rn * rn;
+        }
+        accf += (double)t4;
+      }
+      for (; d < D; d += stride) {
         const int64_t i = c * D + d;
         const T rn = r[i] + (T)0.5 * e * (-g[i]);
         r[i] = rn;
-        acc += (double)(mi[d] * rn * rn);
+        accf += (double)(mi[d] * rn * rn);
       }
+      acc = accf;
     }
     double red[1] = {acc};
     block_sum<1>(red, smem);
@@ -93,17 +129,42 @@ __global__ void __launch_bounds__(256) hier_normal_kernel(const T* __restrict__ 
       const T* zc = z + c * D;
       const T mu = zc[0];
       const T tau = b2_exp(zc[1]);
-      for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < J;
-           j += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+      int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      double a0 = 0, a1 = 0, a2 = 0;  // fp32 within a trip of 4, fp64 across trips
+      for (; j + 3 * stride < J; j += 4 * stride) {
+        T t0 = 0, t1 = 0, t2 = 0;
+        T ev[4], sv[4], yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ev[u] = zc[2 + j + u * stride];
+          sv[u] = __ldg(sigma + j + u * stride);
+          yv[u] = __ldg(y + j + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const T d = yv[u] - mu - tau * ev[u];
+          const T isg = fast_rcp(sv[u]);
+          const T res = d * isg * isg;
+          grad[c * D + 2 + j + u * stride] = ev[u] - tau * res;
+          t0 += (T)0.5 * ev[u] * ev[u] + (T)0.5 * d * res + fast_log(sv[u]);
+          t1 += res;
+          t2 += res * ev[u];
+        }
+        a0 += (double)t0; a1 += (double)t1; a2 += (double)t2;
+      }
+      for (; j < J; j += stride) {
         const T eta = zc[2 + j];
         const T sg = __ldg(sigma + j);
         const T d = __ldg(y + j) - mu - tau * eta;
-        const T res = d / (sg * sg);
+        const T isg = fast_rcp(sg);
+        const T res = d * isg * isg;
         grad[c * D + 2 + j] = eta - tau * res;
-        acc[0] += (double)((T)0.5 * eta * eta + (T)0.5 * d * res + b2_log(sg));
-        acc[1] += (double)res;
-        acc[2] += (double)(res * eta);
+        a0 += (double)((T)0.5 * eta * eta + (T)0.5 * d * res + fast_log(sg));
+        a1 += (double)res;
+        a2 += (double)(res * eta);
       }
+      acc[0] = a0; acc[1] = a1; acc[2] = a2;
     }
     block_sum<3>(acc, smem);
     if (threadIdx.x == 0) {
@@ -265,8 +326,9 @@ __global__ void nuts_small_kernel(Model model, int D, T* __restrict__ z, T* __re
 inline unsigned bx_for(int64_t D, int64_t C) {
   // CTAs along the data axis per chain: enough to fill the machine, few enough to keep the
   // second-stage reduction short
+  // each thread owns >= 4 elements per chain row; ~2 waves of resident CTAs over all chains
   int64_t bx = (D + 256 * 4 - 1) / (256 * 4);
-  const int64_t cap = ((int64_t)kNumSMs * 8 + C - 1) / (C > 0 ? C : 1);
+  const int64_t cap = ((int64_t)kNumSMs * 16 + C - 1) / (C > 0 ? C : 1);
   if (bx > cap) bx = cap;
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
