@@ -66,18 +66,45 @@ def _as_tensor(x, like=None):
     return torch.as_tensor(x, dtype=torch.get_default_dtype())
 
 
+_CONSTS = {}
+
+
+def _const(value, dtype, device):
+    """Cached 0-d constant: python-number parameters (``Normal(0., 1.)``) cost no fill kernel per
+    step and stay valid under CUDA-graph capture (a fresh H2D copy of a scalar would not)."""
+    key = (float(value), dtype, str(device))
+    t = _CONSTS.get(key)
+    if t is None:
+        t = _CONSTS[key] = torch.full((), float(value), dtype=dtype, device=device)
+    return t
+
+
+def constant(value, like):
+    """Cached 0-d tensor holding ``value`` on ``like``'s device/dtype (no kernel launch after the
+    first call; safe to use inside a CUDA-graph captured step)."""
+    return _const(value, like.dtype if like.is_floating_point() else torch.get_default_dtype(), like.device)
+
+
 def _broadcast_params(*xs):
-    """Tensor-ify python numbers next to the first tensor argument (dtype/device follow it)."""
+    """Tensor-ify python numbers next to the first tensor argument (dtype/device follow it; with no
+    tensor argument they follow torch's default dtype and default device)."""
     ref = None
     for x in xs:
         if isinstance(x, torch.Tensor):
             ref = x
             break
+    if ref is not None:
+        dtype, device = (ref.dtype if ref.is_floating_point() else torch.get_default_dtype()), ref.device
+    else:
+        dtype, device = torch.get_default_dtype(), torch.get_default_device()
     out = []
     for x in xs:
-        t = _as_tensor(x, ref)
-        if ref is not None and t.dtype != ref.dtype and t.is_floating_point():
-            t = t.to(ref.dtype)
+        if isinstance(x, Number):
+            t = _const(x, dtype, device)
+        else:
+            t = _as_tensor(x, ref)
+            if ref is not None and t.dtype != ref.dtype and t.is_floating_point():
+                t = t.to(ref.dtype)
         out.append(t)
     return out
 
@@ -253,7 +280,7 @@ class Normal(_Elementwise):
     def rsample(self, sample_shape=torch.Size()):
         shape = self.shape(sample_shape)
         eps = torch.randn(shape, dtype=self.loc.dtype, device=self.loc.device)
-        return self.loc + eps * self.scale
+        return torch.addcmul(self.loc, eps, self.scale)   # loc + eps*scale (normal.py:82-85), one launch
 
 
 class Cauchy(_Elementwise):
@@ -899,7 +926,7 @@ def _bernoulli_new(cls, probs=None, logits=None, validate_args=None):
 
 
 Bernoulli.__new__ = staticmethod(_bernoulli_new)
-__all__ += ["LinearPredictor", "linear_predictor"]
+__all__ += ["LinearPredictor", "linear_predictor", "constant"]
 
 from .hmm import GaussianHMM  # noqa: E402,F401
 __all__ += ["GaussianHMM"]

@@ -27,8 +27,9 @@ def logistic_model_fused(X, y):
     """Same model with the linear predictor handed over lazily, so the likelihood site is scored by
     the fused GLM kernel (X and y read once for value and gradient)."""
     D = X.shape[-1]
-    w = pyro.sample("w", dist.Normal(X.new_zeros(D), X.new_ones(D)).to_event(1))
-    b = pyro.sample("b", dist.Normal(X.new_zeros(()), X.new_full((), 10.0)))
+    zero = dist.constant(0.0, X)   # cached constants: no fill kernels inside the step
+    w = pyro.sample("w", dist.Normal(zero, 1.0).expand([D]).to_event(1))
+    b = pyro.sample("b", dist.Normal(zero, 10.0))
     with pyro.plate("data", X.shape[0]):
         pyro.sample("y", dist.Bernoulli(logits=dist.linear_predictor(X, w, b)), obs=y)
 
