@@ -291,6 +291,53 @@ def nuts_section(dev, quick=False):
     return out
 
 
+def nuts_multirank(dev, rank, world):
+    """Chain-sharded NUTS at N > 1 (rank r owns chains [r*C/W, (r+1)*C/W), no
+    collective during warm-up or sampling).  Times are CUDA-event times, max over ranks; leapfrog
+    counts are summed over ranks."""
+    import torch.distributed as dist
+    from pyro_b200.infer import MCMC, NUTS
+    from pyro_b200.infer.mcmc import HierNormalPotential
+    out = {}
+    y = torch.tensor([28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0], device=dev)
+    sigma = torch.tensor([15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0], device=dev)
+
+    def timed(label, make, note):
+        k, mc = make()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mc.run()
+        e1.record()
+        e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+        n = torch.tensor([float(k.leapfrog_count())], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        out[label] = {"leapfrogs": int(n), "seconds": round(float(t), 4),
+                      "leapfrog_per_sec": round(float(n) / float(t), 1), "scaling": note}
+
+    for total, note in ((1024, "strong: 1024 chains total, %d per rank" % (1024 // world)),
+                        (1024 * world, "weak: 1024 chains per rank")):
+        def make(total=total):
+            k = NUTS(potential_fn=HierNormalPotential(y, sigma, 10.0, 25.0))
+            return k, MCMC(k, num_samples=200, warmup_steps=200, num_chains=total, seed=0)
+        timed("eight_schools_%dchains" % total, make, note)
+    J, C = 1_000_000, 8
+    g = torch.Generator().manual_seed(0)
+    sig = (5 + 15 * torch.rand(J, generator=g)).to(dev)
+    yy = (5 + 3 * torch.randn(J, generator=g)).to(dev) + sig * torch.randn(J, generator=g).to(dev)
+
+    def make4():
+        k = NUTS(potential_fn=HierNormalPotential(yy, sig, 10.0, 25.0), native_small=False, max_tree_depth=6)
+        return k, MCMC(k, num_samples=4, warmup_steps=6, num_chains=C * world, seed=0)
+    timed("hier_normal_J1e6_%dchains" % (C * world), make4, "weak: %d chains per rank, 10 transitions, max_tree_depth 6" % C)
+    out["hier_normal_J1e6_%dchains" % (C * world)]["algorithmic_GBps"] = round(
+        out["hier_normal_J1e6_%dchains" % (C * world)]["leapfrog_per_sec"] * 16e6 / 1e9, 1)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -404,6 +451,12 @@ def main():
     e2e_val = e2e_n / (float(e2e_ms) * 1e-3)
     h2d = Xh.numel() * 4 + yh.numel() * 4
     clocks = sampler.stop() if rank == 0 else None
+    nuts_mr = None
+    if world > 1 and not a.no_nuts:
+        try:
+            nuts_mr = nuts_multirank(dev, rank, world)
+        except Exception as e:  # pragma: no cover
+            nuts_mr = {"error": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -453,6 +506,8 @@ def main():
                 out["nuts"] = nuts_section(dev)
             except Exception as e:  # pragma: no cover
                 out["nuts"] = {"error": repr(e)[:300]}
+    if nuts_mr is not None:
+        out["nuts"] = nuts_mr
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

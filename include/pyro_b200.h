@@ -69,13 +69,27 @@ extern "C" {
 #define B2_UNIFORM 11          /* (low, high)             torch/distributions/uniform.py          */
 #define B2_KL_NORMAL_NORMAL 12 /* value unused; (loc_p, scale_p, loc_q, scale_q) kl.py:468-471    */
 #define B2_KL_GAMMA_GAMMA 13   /* value unused; (conc_p, rate_p, conc_q, rate_q) kl.py:301-306    */
-#define B2_NUM_ELEMENTWISE_FAMILIES 14
+/* Reparameterised Normal draw fused with its own score (replaces
+ * rsample torch/distributions/normal.py:82-85 + the guide site's log_prob + its backward).
+ * Both are launched with scale = weight = 1.
+ *   B2_NORMAL_RSAMPLE:      value = eps ~ N(0,1), params (loc, scale);
+ *                           out_dvalue (full shape) receives z = loc + eps*scale,
+ *                           out_sum receives sum_coeff * SUM Normal(loc, scale).log_prob(z)
+ *   B2_NORMAL_RSAMPLE_BWD:  value = dL/dz, params (eps, scale, c);
+ *                           out_dparams[0] = dL/dloc   = SUM dL/dz
+ *                           out_dparams[1] = dL/dscale = SUM (dL/dz * eps - c/scale)
+ *                           (c = coefficient of SUM log q(z) in L; both reduced to the stored
+ *                           shapes of loc / scale)                                              */
+#define B2_NORMAL_RSAMPLE 14
+#define B2_NORMAL_RSAMPLE_BWD 15
+#define B2_NUM_ELEMENTWISE_FAMILIES 16
 /* Event families (event_dim >= 1), scored by b2_event_score. */
 #define B2_DIRICHLET 32   /* (concentration[...,K])           torch/distributions/dirichlet.py:90-97 */
 #define B2_CATEGORICAL 33 /* (logits[...,K]), int64 value      categorical.py:78,151-157             */
 #define B2_MVN_TRIL 34    /* (loc[...,n], scale_tril[...,n,n]) multivariate_normal.py:256-264        */
 
 #define B2_MAX_PARAMS 4
+#define B2_SITE_SMALL_N 8192 /* sites up to this many elements: single-CTA kernel, fused reductions */
 
 typedef struct {
   void* ptr;
@@ -87,6 +101,9 @@ typedef struct {
 
 /* flags for b2_site_score */
 #define B2_FLAG_ACCUMULATE_SUM 1 /* out_sum += coeff*sum instead of out_sum = coeff*sum */
+#define B2_FLAG_SITE_LARGE 4     /* b2_site_score: take the multi-CTA kernels even for a site of at
+                                    most B2_SITE_SMALL_N elements (tests cover both paths on the
+                                    reference's small fixtures) */
 #define B2_FLAG_GLM_FP32 2       /* b2_glm_bernoulli_logits: fp32 SIMT contractions instead of the
                                     TF32 tensor-core path */
 
@@ -110,8 +127,11 @@ typedef struct {
  *   grad of operand o at i:  weight * u_i * m_i * scale * d lp_i / d o
  * Gradient outputs (out_dvalue, out_dparams[k]; ptr may be NULL = not wanted) are written to a
  * tensor that is either full shape (no zero stride on a dim of size > 1) or a scalar (all strides
- * zero: the gradient is summed over every element).  Any other broadcast pattern returns
- * B2_ERR_UNSUPPORTED_REDUCTION without launching.
+ * zero: the gradient is summed over every element).  A mixed pattern (zero stride on some dims:
+ * the operand's stored shape, e.g. loc[D] scored against value[P, D]) is reduced in the same
+ * launch for sites of at most B2_SITE_SMALL_N elements -- those run as ONE CTA, one launch --
+ * and returns B2_ERR_UNSUPPORTED_REDUCTION without launching for larger ones (the caller then
+ * asks for a full-shape gradient and sums it with b2_reduce_to).
  *
  * workspace: b2_site_score_workspace() bytes, zero-initialised ONCE by the caller; the library
  * leaves it zeroed.  Must not be shared by kernels running concurrently on different streams.

@@ -19,11 +19,17 @@ B2_MAX_PARAMS = 4
 B2_F32, B2_F64, B2_I64, B2_U8 = 0, 1, 2, 3
 B2_FLAG_ACCUMULATE_SUM = 1
 B2_FLAG_GLM_FP32 = 2
+B2_FLAG_SITE_LARGE = 4
+FORCE_LARGE_SITE_KERNELS = False   # tests: score small fixtures with the multi-CTA kernels too
 B2_ERR_UNSUPPORTED_REDUCTION = -6
 
 # family ids (include/pyro_b200.h)
 NORMAL, BERNOULLI_LOGITS, GAMMA, BETA, POISSON, CAUCHY, HALFCAUCHY, EXPONENTIAL, LOGNORMAL, \
-    HALFNORMAL, BERNOULLI_PROBS, UNIFORM, KL_NORMAL_NORMAL, KL_GAMMA_GAMMA = range(14)
+    HALFNORMAL, BERNOULLI_PROBS, UNIFORM, KL_NORMAL_NORMAL, KL_GAMMA_GAMMA, NORMAL_RSAMPLE, \
+    NORMAL_RSAMPLE_BWD = range(16)
+FUSED_DRAW = True         # Normal.rsample draws and scores in one kernel (b2 family 14)
+EMULATE_RSAMPLE = False   # tests/cpu_emulation.py flips this to exercise the fused-draw host logic on CPU
+SITE_SMALL_N = 8192   # B2_SITE_SMALL_N: one-CTA kernel with fused stored-shape gradient reductions
 DIRICHLET, CATEGORICAL, MVN_TRIL = 32, 33, 34
 MODEL_HIER_NORMAL, MODEL_LOGISTIC = 0, 1
 NUTS_SMALL_MAX_D = 64

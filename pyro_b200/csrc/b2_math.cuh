@@ -231,7 +231,9 @@ enum : int {
   kUniform = 11,
   kKLNormalNormal = 12,
   kKLGammaGamma = 13,
-  kNumElementwise = 14
+  kNormalRsample = 14,     // reparameterised draw + its own log density (guide sites)
+  kNormalRsampleBwd = 15,  // chain rule of that draw back to (loc, scale)
+  kNumElementwise = 16
 };
 
 template <int FAM>
@@ -256,6 +258,8 @@ B2_TRAITS(kBernoulliProbs, 1, true)
 B2_TRAITS(kUniform, 2, true)
 B2_TRAITS(kKLNormalNormal, 4, false)
 B2_TRAITS(kKLGammaGamma, 4, false)
+B2_TRAITS(kNormalRsample, 2, true)
+B2_TRAITS(kNormalRsampleBwd, 3, true)
 #undef B2_TRAITS
 
 // eval<FAM, T, GRAD>(x, p, out): p[k] are the parameters in the order pyro_b200.h documents.
@@ -598,6 +602,45 @@ struct Eval<kKLGammaGamma, T, GRAD> {
       o.dp[1] = aq / bp - ap * bq / (bp * bp);
       o.dp[2] = b2_log(bp / bq) + digamma(aq) - psi;
       o.dp[3] = -aq / bq + ap / bp;
+    }
+  }
+};
+
+// Reparameterised Normal draw fused with its own score (guide sites).
+//   value = eps ~ N(0,1);  params = (loc, scale)
+//   z   = loc + eps*scale                 torch/distributions/normal.py:82-85   -> "dx" slot
+//   lp  = Normal(loc, scale).log_prob(z)  normal.py:87-102, evaluated on the ROUNDED z exactly as a
+//         separate log_prob(z) call would
+// The kernel is launched with scale = weight = 1 so the dx slot holds z itself.
+template <typename T, bool GRAD>
+struct Eval<kNormalRsample, T, GRAD> {
+  static B2_HD void run(T eps, const T* p, ElemOut<T>& o) {
+    const T z = p[0] + eps * p[1];
+    ElemOut<T> n;
+    Eval<kNormal, T, false>::run(z, p, n);
+    o.lp = n.lp;
+    if (GRAD) {
+      o.dx = z;
+      o.dp[0] = (T)0;
+      o.dp[1] = (T)0;
+    }
+  }
+};
+
+// Backward of the fused draw.  value = gz (gradient reaching z from its consumers, already
+// weighted); params = (eps, scale, c) with c the coefficient on d(sum log q)/d(.) -- the total
+// derivative of log q(z(loc, scale)) is 0 w.r.t. loc and -1/scale w.r.t. scale, so
+//   d/dloc   = gz                      -> dp[0] (reduced to loc's stored shape by the kernel)
+//   d/dscale = gz*eps - c/scale        -> dp[1]
+template <typename T, bool GRAD>
+struct Eval<kNormalRsampleBwd, T, GRAD> {
+  static B2_HD void run(T gz, const T* p, ElemOut<T>& o) {
+    o.lp = (T)0;
+    if (GRAD) {
+      o.dx = (T)0;
+      o.dp[0] = gz;
+      o.dp[1] = gz * p[0] - p[2] / p[1];
+      o.dp[2] = (T)0;
     }
   }
 };

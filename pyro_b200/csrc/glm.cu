@@ -140,8 +140,28 @@ __global__ void __launch_bounds__(256) glm_finish_kernel(const float* __restrict
                                                          int nblocks, int P, int D, double scale,
                                                          double weight, float* __restrict__ sum_p,
                                                          float* __restrict__ out_dW,
-                                                         float* __restrict__ out_db) {
+                                                         float* __restrict__ out_db,
+                                                         double sum_coeff, int flags,
+                                                         float* __restrict__ out_total) {
   const int total = P * (D + 2);
+  if (out_total && blockIdx.x == gridDim.x - 1) {
+    // the extra last CTA: total over particles AND CTAs straight from the partials (fixed order),
+    // with the ELBO coefficient -- saves a third launch
+    __shared__ double smem[32];
+    double acc = 0.0;
+    const int n = nblocks * P;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int bl = i / P, p = i - bl * P;
+      acc += (double)partials[(int64_t)bl * total + (int64_t)p * (D + 2) + D + 1];
+    }
+    double red[1] = {acc};
+    block_sum<1>(red, smem);
+    if (threadIdx.x == 0) {
+      const double v = sum_coeff * scale * red[0];
+      *out_total = (flags & B2_FLAG_ACCUMULATE_SUM) ? (float)((double)*out_total + v) : (float)v;
+    }
+    return;
+  }
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (e >= total) return;
@@ -156,20 +176,6 @@ __global__ void __launch_bounds__(256) glm_finish_kernel(const float* __restrict
     if (out_db) out_db[p] = (float)(weight * scale * s);
   } else {
     sum_p[p] = (float)(scale * s);
-  }
-}
-
-// third stage: total over particles (fixed order), with the ELBO coefficient
-__global__ void glm_total_kernel(const float* __restrict__ sum_p, int P, double sum_coeff,
-                                 int flags, float* __restrict__ out_total) {
-  __shared__ double smem[32];
-  double acc = 0.0;
-  for (int p = threadIdx.x; p < P; p += blockDim.x) acc += (double)sum_p[p];
-  double red[1] = {acc};
-  block_sum<1>(red, smem);
-  if (threadIdx.x == 0) {
-    const double v = sum_coeff * red[0];
-    *out_total = (flags & B2_FLAG_ACCUMULATE_SUM) ? (float)((double)*out_total + v) : (float)v;
   }
 }
 
@@ -222,13 +228,9 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   }
   float* sum_p = out_sum_p ? out_sum_p : partials + (size_t)gx * P * (D + 2);
   const int total = P * (D + 2);
-  glm_finish_kernel<<<(total + 7) / 8, 256, 0, s>>>(partials, gx, P, D, scale, weight, sum_p,
-                                                        out_dW, out_db);
-  int nl = 2;
-  if (out_total) {
-    glm_total_kernel<<<1, 64, 0, s>>>(sum_p, P, sum_coeff, flags, out_total);
-    ++nl;
-  }
+  glm_finish_kernel<<<(total + 7) / 8 + (out_total ? 1 : 0), 256, 0, s>>>(
+      partials, gx, P, D, scale, weight, sum_p, out_dW, out_db, sum_coeff, flags, out_total);
+  const int nl = 2;
   count_launch(nl);
   return check_launch();
 }

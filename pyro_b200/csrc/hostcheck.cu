@@ -37,6 +37,8 @@ int eval_t(int family, int grad, int64_t n, const T* x, const T* const* p, T* lp
       B2H_CASE(kUniform)
       B2H_CASE(kKLNormalNormal)
       B2H_CASE(kKLGammaGamma)
+      B2H_CASE(kNormalRsample)
+      B2H_CASE(kNormalRsampleBwd)
       default:
         return -3;
     }

@@ -12,6 +12,7 @@ namespace b2 {
 
 constexpr int kAdamHyperStride = 8;  // beta1, beta2, eps, weight_decay, clip_norm, lrd, [step_size], [unused]
 constexpr int kAgrHyperStride = 4;   // eta, delta, t, [lr]
+constexpr int64_t kAdamFusedAdvanceNumel = 4096;  // largest tensor for the one-launch (advance + update) path
 
 // pyro/optim/clipped_adam.py:62,80,91-93: lr *= lrd; step += 1;
 // step_size = lr * sqrt(1 - beta2^step) / (1 - beta1^step)      (all in double, like Python)
@@ -28,20 +29,42 @@ __global__ void adam_advance_kernel(int n, double* hyper, double* lrs, int32_t* 
   h[6] = lr * sqrt(bc2) / bc1;
 }
 
-template <typename T>
+// ADV: the launch has ONE CTA per tensor (small parameter sets, e.g. BASELINE config 2's four
+// tensors), so that CTA also advances its tensor's scalar state -- no separate advance launch.
+template <typename T, bool ADV>
 __global__ void __launch_bounds__(256) clipped_adam_kernel(void* const* __restrict__ ps,
                                                            void* const* __restrict__ gs,
                                                            void* const* __restrict__ ms,
                                                            void* const* __restrict__ vs,
                                                            const int64_t* __restrict__ numel,
-                                                           const double* __restrict__ hyper,
+                                                           double* __restrict__ hyper,
+                                                           double* __restrict__ lrs,
+                                                           int32_t* __restrict__ steps,
                                                            int zero_grad) {
   const int ti = blockIdx.y;
   const int64_t n = numel[ti];
-  const double* h = hyper + (size_t)ti * kAdamHyperStride;
+  double* h = hyper + (size_t)ti * kAdamHyperStride;
+  double step_size;
+  if (ADV) {
+    __shared__ double sh_step;
+    if (threadIdx.x == 0) {
+      const double lr = lrs[ti] * h[5];
+      const int32_t t = steps[ti] + 1;
+      const double bc1 = 1.0 - pow(h[0], (double)t);
+      const double bc2 = 1.0 - pow(h[1], (double)t);
+      sh_step = lr * sqrt(bc2) / bc1;
+      lrs[ti] = lr;
+      steps[ti] = t;
+      h[6] = sh_step;
+    }
+    __syncthreads();
+    step_size = sh_step;
+  } else {
+    step_size = h[6];
+  }
   const T b1 = (T)h[0], b2v = (T)h[1], eps = (T)h[2], wd = (T)h[3], clip = (T)h[4];
   const T omb1 = (T)(1.0 - h[0]), omb2 = (T)(1.0 - h[1]);
-  const T neg_step = (T)(-h[6]);
+  const T neg_step = (T)(-step_size);
   T* __restrict__ p = reinterpret_cast<T*>(ps[ti]);
   T* __restrict__ g = reinterpret_cast<T*>(gs[ti]);
   T* __restrict__ m = reinterpret_cast<T*>(ms[ti]);
@@ -125,12 +148,22 @@ extern "C" int b2_clipped_adam(int n, void* const* p, void* const* g, void* cons
   if (dtype != B2_F32 && dtype != B2_F64) return B2_ERR_BAD_DTYPE;
   if (n > 65535) return B2_ERR_TOO_LARGE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (max_numel <= kAdamFusedAdvanceNumel) {
+    // every tensor fits one CTA's grid-stride loop: one launch does advance + update
+    dim3 grid(1, (unsigned)n, 1);
+    if (dtype == B2_F32)
+      clipped_adam_kernel<float, true><<<grid, 256, 0, s>>>(p, g, m, v, numel, hyper, lrs, steps, zero_grad);
+    else
+      clipped_adam_kernel<double, true><<<grid, 256, 0, s>>>(p, g, m, v, numel, hyper, lrs, steps, zero_grad);
+    count_launch(1);
+    return check_launch();
+  }
   adam_advance_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, hyper, lrs, steps);
   dim3 grid(blocks_for(max_numel), (unsigned)n, 1);
   if (dtype == B2_F32)
-    clipped_adam_kernel<float><<<grid, 256, 0, s>>>(p, g, m, v, numel, hyper, zero_grad);
+    clipped_adam_kernel<float, false><<<grid, 256, 0, s>>>(p, g, m, v, numel, hyper, lrs, steps, zero_grad);
   else
-    clipped_adam_kernel<double><<<grid, 256, 0, s>>>(p, g, m, v, numel, hyper, zero_grad);
+    clipped_adam_kernel<double, false><<<grid, 256, 0, s>>>(p, g, m, v, numel, hyper, lrs, steps, zero_grad);
   count_launch(2);
   return check_launch();
 }

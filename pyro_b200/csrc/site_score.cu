@@ -15,27 +15,28 @@ struct OpView {
 
 inline bool is_float_dtype(int d) { return d == B2_F32 || d == B2_F64; }
 
-// classify an output's stride pattern on the common shape: 1 full, 2 scalar, -1 unsupported
+// classify an output's stride pattern on the common shape: 1 full, 2 scalar (summed over
+// everything), 3 summed over the dims where its stride is 0 (the operand's stored shape)
 int out_mode(const int64_t* shape, const int64_t* st, int ndim) {
   bool any_zero = false, any_nonzero = false;
   for (int d = 0; d < ndim; ++d) {
     if (shape[d] == 1) continue;
     if (st[d] == 0) any_zero = true; else any_nonzero = true;
   }
-  if (any_zero && any_nonzero) return -1;
+  if (any_zero && any_nonzero) return 3;
   return any_zero ? 2 : 1;
 }
 
 }  // namespace
 
-int dispatch_site(int family, int dtype, bool grad, const SiteArgs& a, bool vec, cudaStream_t s) {
+int dispatch_site(int family, int dtype, bool grad, const SiteArgs& a, int kind, cudaStream_t s) {
   if (family < 0 || family >= kNumElementwise) return B2_ERR_BAD_FAMILY;
-  if (family <= kPoisson) return dispatch_site_a(family, dtype, grad, a, vec, s);
-  if (family <= kHalfNormal) return dispatch_site_b(family, dtype, grad, a, vec, s);
-  return dispatch_site_c(family, dtype, grad, a, vec, s);
+  if (family <= kPoisson) return dispatch_site_a(family, dtype, grad, a, kind, s);
+  if (family <= kHalfNormal) return dispatch_site_b(family, dtype, grad, a, kind, s);
+  return dispatch_site_c(family, dtype, grad, a, kind, s);
 }
 
-static const int kFamilyNumParams[kNumElementwise] = {2, 1, 2, 2, 1, 2, 1, 1, 2, 1, 1, 2, 4, 4};
+static const int kFamilyNumParams[kNumElementwise] = {2, 1, 2, 2, 1, 2, 1, 1, 2, 1, 1, 2, 4, 4, 2, 3};
 
 }  // namespace b2
 
@@ -107,7 +108,9 @@ extern "C" int b2_site_score(int family, const b2_tensor* value, const b2_tensor
     modes[i] = 0;
     if (!outs[i]) continue;
     int m = out_mode(value->shape, outs[i]->stride, nd);
-    if (m < 0) return B2_ERR_UNSUPPORTED_REDUCTION;
+    // partial reductions are fused only by the one-CTA kernel; larger sites get a full-shape
+    // gradient from the caller and reduce it with b2_reduce_to
+    if (m == 3 && (n > kSmallN || (flags & B2_FLAG_SITE_LARGE))) return B2_ERR_UNSUPPORTED_REDUCTION;
     if (i == 0 && m != 1 && n > 1) return B2_ERR_BAD_SHAPE;  // log_prob output is always full
     modes[i] = m;
   }
@@ -130,7 +133,7 @@ extern "C" int b2_site_score(int family, const b2_tensor* value, const b2_tensor
     shp[cd] = value->shape[d];
     for (int i = 0; i < n_in; ++i) ist[i][cd] = ins[i]->ptr ? ins[i]->stride[d] : 0;
     for (int i = 0; i < n_out; ++i)
-      ost[i][cd] = (outs[i] && modes[i] == 1) ? outs[i]->stride[d] : 0;
+      ost[i][cd] = (outs[i] && (modes[i] == 1 || modes[i] == 3)) ? outs[i]->stride[d] : 0;
     ++cd;
   }
   // merge from the right
@@ -176,6 +179,12 @@ extern "C" int b2_site_score(int family, const b2_tensor* value, const b2_tensor
   fill_out(a.lp, 0);
   fill_out(a.gx, 1);
   for (int k = 0; k < n_params; ++k) fill_out(a.gp[k], 2 + k);
+
+  // ---- small sites: one CTA, one launch ----------------------------------------------------------
+  if (n > 0 && n <= kSmallN && !(flags & B2_FLAG_SITE_LARGE)) {
+    a.scratch = a.partials;  // a single CTA needs no cross-CTA partials; reuse them as the slabs
+    return dispatch_site(family, dtype, grad, a, kSiteSmall, reinterpret_cast<cudaStream_t>(stream));
+  }
 
   // ---- vector path eligibility -----------------------------------------------------------------
   const int V = (dtype == B2_F32) ? 4 : 2;
@@ -227,5 +236,6 @@ extern "C" int b2_site_score(int family, const b2_tensor* value, const b2_tensor
     while (lg < 8 && ((int64_t)1 << lg) < CV) ++lg;
     a.tx_log2 = lg;
   }
-  return dispatch_site(family, dtype, grad, a, vec, reinterpret_cast<cudaStream_t>(stream));
+  return dispatch_site(family, dtype, grad, a, vec ? kSiteVec : kSiteGen,
+                       reinterpret_cast<cudaStream_t>(stream));
 }

@@ -22,7 +22,8 @@ struct Opnd {
 struct OutOpnd {
   void* ptr;
   int64_t st[kMaxD];
-  int mode;  // 0 = not wanted, 1 = full shape, 2 = scalar (sum over everything)
+  int mode;  // 0 = not wanted, 1 = full shape, 2 = scalar (sum over everything),
+             // 3 = summed over the dims where st == 0 (small kernel only)
 };
 
 struct SiteArgs {
@@ -44,7 +45,15 @@ struct SiteArgs {
   // vector path
   int64_t R, C;
   int tx_log2;  // threads along the column-vector axis = 1 << tx_log2 (block is 256 threads)
+  // small path: scratch for mode-3 outputs, (2 + NP) slabs of n elements
+  void* scratch;
 };
+
+constexpr int kSiteGen = 0, kSiteVec = 1, kSiteSmall = 2;
+constexpr int64_t kSmallN = B2_SITE_SMALL_N;  // sites up to this many elements take the one-CTA kernel
+constexpr int kSmallThreads = 512;
+static_assert((1 + B2_MAX_PARAMS) * kSmallN * sizeof(double) <= sizeof(double) * kMaxRed * kMaxPartialBlocks,
+              "mode-3 slabs must fit in the partials region of the reduce workspace");
 
 template <typename T>
 __device__ __forceinline__ void finish_outputs(const SiteArgs& a, int k, double tot) {
@@ -337,10 +346,141 @@ __global__ void __launch_bounds__(256) site_gen_kernel(const SiteArgs a) {
                     [&](int k, double tot) { finish_outputs<T>(a, k, tot); });
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small kernel: sites of at most kSmallN elements (every latent site of the BASELINE SVI configs:
+// [P, D] weights, [P] biases) are launch-latency bound, so ONE CTA does everything in one launch --
+// the elementwise pass, the scalar sums, and the reduction of each parameter gradient to the
+// parameter's STORED shape (mode 3), which the large kernels leave to a follow-up b2_reduce_to.
+// Mode-3 gradients go through a scratch slab (common shape, row major); after a CTA barrier one
+// warp per stored element sums its broadcast positions in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void small_reduce_out(const SiteArgs& a, const OutOpnd& o, const T* slab) {
+  // dims with st != 0 index the output; dims with st == 0 are summed
+  int64_t cst[kMaxD];
+  int64_t m = 1;
+  {
+    int64_t c = 1;
+    for (int d = a.ndim - 1; d >= 0; --d) {
+      cst[d] = c;
+      c *= a.shape[d];
+      if (o.st[d] != 0) m *= a.shape[d];
+    }
+  }
+  const int64_t q = a.n / m;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  T* out = reinterpret_cast<T*>(o.ptr);
+  for (int64_t j = warp; j < m; j += nwarps) {
+    int64_t rem = j, base = 0, off = 0;
+    for (int d = a.ndim - 1; d >= 0; --d) {
+      if (o.st[d] == 0) continue;
+      const int64_t qq = rem / a.shape[d];
+      const int64_t idx = rem - qq * a.shape[d];
+      rem = qq;
+      base += idx * cst[d];
+      off += idx * o.st[d];
+    }
+    double s = 0.0;
+    for (int64_t t = lane; t < q; t += 32) {
+      int64_t r2 = t, flat = base;
+      for (int d = a.ndim - 1; d >= 0; --d) {
+        if (o.st[d] != 0) continue;
+        const int64_t qq = r2 / a.shape[d];
+        flat += (r2 - qq * a.shape[d]) * cst[d];
+        r2 = qq;
+      }
+      s += (double)slab[flat];
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[off] = (T)s;
+  }
+}
+
+template <int FAM, typename T, bool GRAD>
+__global__ void __launch_bounds__(kSmallThreads) site_small_kernel(const SiteArgs a) {
+  constexpr int NP = FamilyTraits<FAM>::kNumParams;
+  constexpr bool HASV = FamilyTraits<FAM>::kHasValue;
+  constexpr int NRED = GRAD ? 2 + NP : 1;
+  const T f0 = (T)(a.weight * a.scale);
+  const T scale = (T)a.scale;
+  T acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) acc[k] = (T)0;
+  T* slab = reinterpret_cast<T*>(a.scratch);
+
+  for (int64_t i = threadIdx.x; i < a.n; i += blockDim.x) {
+    int64_t rem = i;
+    int64_t ox = 0, om = 0, ou = 0, olp = 0, ogx = 0;
+    int64_t op[NP > 0 ? NP : 1], ogp[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) op[k] = ogp[k] = 0;
+    for (int d = a.ndim - 1; d >= 0; --d) {
+      const int64_t q = rem / a.shape[d];
+      const int64_t idx = rem - q * a.shape[d];
+      rem = q;
+      ox += idx * a.x.st[d];
+      om += idx * a.mask.st[d];
+      ou += idx * a.up.st[d];
+      olp += idx * a.lp.st[d];
+      ogx += idx * a.gx.st[d];
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        op[k] += idx * a.p[k].st[d];
+        ogp[k] += idx * a.gp[k].st[d];
+      }
+    }
+    T pl[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) pl[k] = reinterpret_cast<const T*>(a.p[k].ptr)[op[k]];
+    const T xv = (HASV && a.x.ptr) ? reinterpret_cast<const T*>(a.x.ptr)[ox] : (T)0;
+    const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
+    ElemOut<T> o;
+    Eval<FAM, T, GRAD>::run(xv, pl, o);
+    const T slp = m ? o.lp * scale : (T)0;
+    acc[0] += slp;
+    if (a.lp.mode == 1) reinterpret_cast<T*>(a.lp.ptr)[olp] = slp;
+    if (GRAD) {
+      T f = m ? f0 : (T)0;
+      if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[ou];
+      const T gxe = m ? f * o.dx : (T)0;
+      acc[1] += gxe;
+      if (a.gx.mode == 1) reinterpret_cast<T*>(a.gx.ptr)[ogx] = gxe;
+      else if (a.gx.mode == 3) slab[i] = gxe;
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        const T g = m ? f * o.dp[k] : (T)0;
+        acc[2 + k] += g;
+        if (a.gp[k].mode == 1) reinterpret_cast<T*>(a.gp[k].ptr)[ogp[k]] = g;
+        else if (a.gp[k].mode == 3) slab[(int64_t)(1 + k) * a.n + i] = g;
+      }
+    }
+  }
+  __shared__ double smem[NRED * 32];
+  double red[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) red[k] = (double)acc[k];
+  block_sum<NRED>(red, smem);  // ends with a CTA barrier: the slabs are complete and visible
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) finish_outputs<T>(a, k, red[k]);
+  }
+  if (GRAD) {
+    if (a.gx.mode == 3) small_reduce_out<T>(a, a.gx, slab);
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+      if (a.gp[k].mode == 3) small_reduce_out<T>(a, a.gp[k], slab + (int64_t)(1 + k) * a.n);
+  }
+}
+
 // host-side launcher for one (family, dtype, grad) combination
 template <int FAM, typename T, bool GRAD>
-int launch_site(const SiteArgs& a, bool vec, cudaStream_t stream) {
-  if (vec) {
+int launch_site(const SiteArgs& a, int kind, cudaStream_t stream) {
+  if (kind == kSiteSmall) {
+    int threads = (int)((a.n + 31) / 32) * 32;
+    if (threads > kSmallThreads) threads = kSmallThreads;
+    if (threads < 32) threads = 32;
+    site_small_kernel<FAM, T, GRAD><<<1, threads, 0, stream>>>(a);
+  } else if (kind == kSiteVec) {
     constexpr int V = VecOf<T>::N;
     constexpr int U = VecUnroll<T, GRAD>::U;
     const int64_t CV = a.C / V;
@@ -371,17 +511,17 @@ int launch_site(const SiteArgs& a, bool vec, cudaStream_t stream) {
 }
 
 // implemented in site_score_fam*.cu (split so the families compile in parallel)
-int dispatch_site_a(int family, int dtype, bool grad, const SiteArgs& a, bool vec, cudaStream_t s);
-int dispatch_site_b(int family, int dtype, bool grad, const SiteArgs& a, bool vec, cudaStream_t s);
-int dispatch_site_c(int family, int dtype, bool grad, const SiteArgs& a, bool vec, cudaStream_t s);
+int dispatch_site_a(int family, int dtype, bool grad, const SiteArgs& a, int kind, cudaStream_t s);
+int dispatch_site_b(int family, int dtype, bool grad, const SiteArgs& a, int kind, cudaStream_t s);
+int dispatch_site_c(int family, int dtype, bool grad, const SiteArgs& a, int kind, cudaStream_t s);
 
 #define B2_DISPATCH_CASE(FAM)                                                         \
   case FAM:                                                                           \
     if (dtype == B2_F32)                                                              \
-      return grad ? launch_site<FAM, float, true>(a, vec, s)                          \
-                  : launch_site<FAM, float, false>(a, vec, s);                        \
+      return grad ? launch_site<FAM, float, true>(a, kind, s)                          \
+                  : launch_site<FAM, float, false>(a, kind, s);                        \
     else                                                                              \
-      return grad ? launch_site<FAM, double, true>(a, vec, s)                         \
-                  : launch_site<FAM, double, false>(a, vec, s);
+      return grad ? launch_site<FAM, double, true>(a, kind, s)                         \
+                  : launch_site<FAM, double, false>(a, kind, s);
 
 }  // namespace b2

@@ -1,7 +1,7 @@
 // site_score_fam_a.cu -- instantiations: Normal, Bernoulli(logits), Gamma, Beta, Poisson
 #include "site_score.cuh"
 namespace b2 {
-int dispatch_site_a(int family, int dtype, bool grad, const SiteArgs& a, bool vec, cudaStream_t s) {
+int dispatch_site_a(int family, int dtype, bool grad, const SiteArgs& a, int kind, cudaStream_t s) {
   switch (family) {
     B2_DISPATCH_CASE(kNormal)
     B2_DISPATCH_CASE(kBernoulliLogits)

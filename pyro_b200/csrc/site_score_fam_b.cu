@@ -1,7 +1,7 @@
 // site_score_fam_b.cu -- instantiations: Cauchy, HalfCauchy, Exponential, LogNormal, HalfNormal
 #include "site_score.cuh"
 namespace b2 {
-int dispatch_site_b(int family, int dtype, bool grad, const SiteArgs& a, bool vec, cudaStream_t s) {
+int dispatch_site_b(int family, int dtype, bool grad, const SiteArgs& a, int kind, cudaStream_t s) {
   switch (family) {
     B2_DISPATCH_CASE(kCauchy)
     B2_DISPATCH_CASE(kHalfCauchy)

@@ -278,9 +278,74 @@ class Normal(_Elementwise):
         super().__init__(loc, scale)
 
     def rsample(self, sample_shape=torch.Size()):
+        """``loc + eps*scale`` (torch/distributions/normal.py:82-85).  On the GPU the draw and its
+        own log density come out of ONE kernel: the returned tensor carries
+        the 0-d ``sum log q(z)`` as ``z._b2_rsample`` so that an ELBO scoring this very site can
+        claim it instead of launching a scoring kernel, and the backward of the pair is one kernel
+        that hands (d/dloc, d/dscale) back in their stored shapes."""
         shape = self.shape(sample_shape)
         eps = torch.randn(shape, dtype=self.loc.dtype, device=self.loc.device)
-        return torch.addcmul(self.loc, eps, self.scale)   # loc + eps*scale (normal.py:82-85), one launch
+        return self.rsample_with_noise(eps)
+
+    def rsample_with_noise(self, eps):
+        """The draw for given standard-normal noise ``eps`` (shape = sample_shape + batch_shape)."""
+        if not N.FUSED_DRAW or (not eps.is_cuda and not N.EMULATE_RSAMPLE):
+            return torch.addcmul(self.loc, eps, self.scale)   # plain draw; scored later by b2_site_score
+        tag = _RsampleTag(self.loc, self.scale)
+        z, lq = _NormalRsampleFn.apply(tag, self.loc, self.scale, eps)
+        tag.lq = lq
+        z._b2_rsample = tag
+        return z
+
+
+class _RsampleTag:
+    """Travels on a fused draw: the parameters it was drawn with, its summed log density, and the
+    coefficient with which that sum entered the loss (set by whoever claims it)."""
+    __slots__ = ("loc", "scale", "lq", "coeff")
+
+    def __init__(self, loc, scale):
+        self.loc, self.scale, self.lq, self.coeff = loc, scale, None, 0.0
+
+
+class _NormalRsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tag, loc, scale, eps):
+        z, lq = _ops.normal_rsample_score(loc, scale, eps)
+        ctx.tag = tag
+        ctx.save_for_backward(eps, loc, scale)
+        ctx.set_materialize_grads(False)
+        return z, lq
+
+    @staticmethod
+    @_ops.once_differentiable
+    def backward(ctx, gz, glq):
+        eps, loc, scale = ctx.saved_tensors
+        if gz is None:
+            gz = _const(0.0, eps.dtype, eps.device)
+        # the sum log q output is only reachable through the tag; its consumer folds its
+        # coefficient into tag.coeff and sends a unit upstream gradient (Trace_ELBO's contract)
+        c = ctx.tag.coeff if glq is not None else 0.0
+        gloc, gscale = _ops.normal_rsample_backward(gz, eps, loc, scale, c,
+                                                    ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        return None, gloc, gscale, None
+
+
+def claim_rsample_score(fn, value, coeff):
+    """If ``value`` is a fused draw from (the Normal underneath) ``fn``, register ``coeff`` -- the
+    coefficient of ``sum log_prob(value)`` in the loss being differentiated -- and return the
+    precomputed 0-d sum; else None."""
+    tag = getattr(value, "_b2_rsample", None)
+    if tag is None:
+        return None
+    base = fn
+    while isinstance(base, Independent):
+        base = base.base_dist
+    if type(base) is not Normal or base.loc is not tag.loc or base.scale is not tag.scale:
+        return None
+    if torch.broadcast_shapes(value.shape, base.batch_shape) != value.shape:
+        return None
+    tag.coeff += float(coeff)
+    return tag.lq
 
 
 class Cauchy(_Elementwise):

@@ -33,7 +33,8 @@ def _pad_shape(t_shape, nd):
 
 def _grad_plan(t, shape):
     """How the gradient of operand ``t`` (stored shape) comes out of a kernel working on ``shape``:
-    ('full', out), ('scalar', out) or ('reduce', out, tmp)."""
+    ('full', out), ('scalar', out), ('inkernel', out) -- summed to the stored shape inside the
+    one-CTA kernel (small sites) -- or ('reduce', out, tmp)."""
     if t.numel() == 1 and len(shape) > 0 and _numel(shape) > 1:
         out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
         return ("scalar", out, None)
@@ -41,6 +42,8 @@ def _grad_plan(t, shape):
         out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
         return ("full", out, None)
     out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+    if _numel(shape) <= N.SITE_SMALL_N and not N.FORCE_LARGE_SITE_KERNELS:
+        return ("inkernel", out, None)
     tmp = torch.empty(shape, dtype=t.dtype, device=t.device)
     return ("reduce", out, tmp)
 
@@ -66,6 +69,8 @@ def _plan_desc(plan, shape):
         return d
     if kind == "full":
         return N.desc(out.reshape(_pad_shape(out.shape, nd)), shape)
+    if kind == "inkernel":
+        return N.desc(out.reshape(_pad_shape(out.shape, nd)).expand(shape), shape)
     return N.desc(tmp, shape)
 
 
@@ -96,8 +101,10 @@ def _finish_plans(plans):
 
 def site_score(family, value, params, shape, *, mask=None, scale=1.0, upstream=None, weight=1.0,
                sum_coeff=1.0, accumulate=False, want_logprob=False, out_sum=None,
-               need_dvalue=False, need_dparams=None, event_size=None):
-    """Launch the fused kernel for one site.  Returns (logprob | None, dvalue | None, [dparams])."""
+               need_dvalue=False, need_dparams=None, event_size=None, grad_like=None):
+    """Launch the fused kernel for one site.  Returns (logprob | None, dvalue | None, [dparams]).
+    ``grad_like[k]`` (elementwise families) overrides the tensor whose stored shape the k-th
+    parameter-slot gradient is reduced to."""
     ref = params[0]
     N.require_cuda(ref, "log_prob scoring")
     dev = ref.device
@@ -132,6 +139,8 @@ def site_score(family, value, params, shape, *, mask=None, scale=1.0, upstream=N
     lp = torch.empty(bshape, dtype=ref.dtype, device=dev) if want_logprob else None
     ws = N.workspace(dev)
     flags = N.B2_FLAG_ACCUMULATE_SUM if accumulate else 0
+    if N.FORCE_LARGE_SITE_KERNELS:
+        flags |= N.B2_FLAG_SITE_LARGE
     pdesc = (N.b2_tensor * np_)()
     gdesc = (N.b2_tensor * np_)()
     if elementwise:
@@ -146,7 +155,9 @@ def site_score(family, value, params, shape, *, mask=None, scale=1.0, upstream=N
         ud = N.desc(upstream, shape) if upstream is not None else None
         lpd = N.desc(lp, shape) if lp is not None else None
         vplan = _grad_plan(value, shape) if need_dvalue else None
-        pplans = [(_grad_plan(params[k], shape) if need_dparams[k] else None) for k in range(np_)]
+        like = [(grad_like[k] if grad_like is not None and grad_like[k] is not None else params[k])
+                for k in range(np_)]
+        pplans = [(_grad_plan(like[k], shape) if need_dparams[k] else None) for k in range(np_)]
         gvd = _plan_desc(vplan, shape) if vplan else None
         for k in range(np_):
             if pplans[k] is not None:
@@ -314,3 +325,47 @@ def fused_site_sum(family, value, params, batch_shape, *, mask=None, scale=1.0, 
     meta = (family, tuple(shape), event_size, mask, float(scale), float(weight), float(sum_coeff),
             None, False, vfloat, bool(assume_unit_upstream))
     return _FusedSiteSumFn.apply(meta, value, *params)
+
+
+# ---- fused reparameterised Normal draw ------------------------------------
+def normal_rsample_score(loc, scale, eps):
+    """(z, lq): z = loc + eps*scale on eps's shape and the 0-d sum of Normal(loc, scale).log_prob(z),
+    one launch (family NORMAL_RSAMPLE; replaces addcmul + the guide site's scoring kernel)."""
+    shape = tuple(eps.shape)
+    z = torch.empty(shape, dtype=eps.dtype, device=eps.device)
+    lq = torch.empty((), dtype=eps.dtype, device=eps.device)
+    if eps.numel() == 0:
+        return z, lq.zero_()
+    N.require_cuda(eps, "fused Normal rsample")
+    nd = len(shape)
+    pdesc = (N.b2_tensor * 2)()
+    pdesc[0] = N.desc(loc, shape)
+    pdesc[1] = N.desc(scale, shape)
+    gdesc = (N.b2_tensor * 2)()
+    for k in range(2):
+        gdesc[k].ptr = None
+        gdesc[k].ndim = nd
+    vd = N.desc(eps, shape)
+    zd = N.desc(z, shape)
+    ws = N.workspace(eps.device)
+    N.check(N.lib().b2_site_score(N.NORMAL_RSAMPLE, ctypes.byref(vd), pdesc, 2, None, 1.0, None, 1.0,
+                                  1.0, 0, None, lq.data_ptr(), ctypes.byref(zd), gdesc,
+                                  ws.data_ptr(), ws.numel(), N.stream_ptr(eps.device)),
+            "b2_site_score[normal_rsample]")
+    return z, lq
+
+
+def normal_rsample_backward(gz, eps, loc, scale, c, need_loc, need_scale):
+    """Gradients of L w.r.t. (loc, scale) given gz = dL/dz and c = coefficient of sum log q(z) in L,
+    reduced to the stored shapes, one launch for small sites (family NORMAL_RSAMPLE_BWD)."""
+    shape = tuple(eps.shape)
+    if eps.numel() == 0:
+        return (torch.zeros_like(loc) if need_loc else None,
+                torch.zeros_like(scale) if need_scale else None)
+    from . import _const
+    cten = _const(c, eps.dtype, eps.device)
+    params = [eps, scale, cten]
+    _, _, gp = site_score(N.NORMAL_RSAMPLE_BWD, gz, params, shape, need_dvalue=False,
+                          need_dparams=[need_loc, need_scale, False],
+                          grad_like=[loc, scale, None])
+    return gp[0], gp[1]

@@ -16,7 +16,7 @@ Rao-Blackwellised ``log_r`` of :20-29 and the score-function surrogate of :104-1
 import torch
 
 from ..distributions import is_identically_zero
-from ..poutine.trace_struct import _fused
+from ..poutine.trace_struct import ScaledTerm, _fused
 from ..util import torch_item, warn_if_nan
 from .elbo import ELBO, get_importance_trace
 from .util import MultiFrameTensor, get_plate_stacks
@@ -43,6 +43,17 @@ def _one_like(t):
     if one is None:
         one = _ONES[key] = torch.ones((), device=t.device, dtype=t.dtype)
     return one
+
+
+_COEFFS = {}
+
+
+def _coeff_vector(coeffs, like):
+    key = (coeffs, like.device, like.dtype)
+    v = _COEFFS.get(key)
+    if v is None:
+        v = _COEFFS[key] = torch.tensor(coeffs, dtype=like.dtype, device=like.device)
+    return v
 
 
 def _all_reparam(guide_trace):
@@ -107,25 +118,34 @@ class Trace_ELBO(ELBO):
 
     # ---- fused path ------------------------------------------------------------------------------
     def _fused_particle(self, model_trace, guide_trace):
-        """Returns (elbo as 0-d device tensor, [0-d terms whose backward with unit upstream yields
-        the surrogate-loss gradients])."""
+        """Returns (loss contribution ``-elbo/P`` as a 0-d device tensor, [0-d terms whose backward
+        with unit upstream yields the surrogate-loss gradients])."""
         from ..distributions import scale_and_mask
         P = self.num_particles
-        terms, elbo_terms = [], []
+        terms, parts, coeffs = [], [], []
 
         def add_site(site, coeff):
             # surrogate_loss = -(1/P) * sum_sites coeff * lp_sum ; elbo = sum coeff * lp_sum
             w = -coeff / P
-            t = _fused(site, weight=w, sum_coeff=coeff, unit=True)
+            t = _fused(site, weight=w, sum_coeff=coeff, unit=True, claim=True)
+            if isinstance(t, ScaledTerm):
+                # drawn and scored by one kernel at sampling time (fused Normal rsample)
+                parts.append(t.tensor.detach())
+                coeffs.append(t.coeff)
+                if t.tensor.requires_grad:
+                    terms.append(t.tensor)
+                return
             if t is not None:
-                elbo_terms.append(t.detach())
+                parts.append(t.detach())
+                coeffs.append(1.0)
                 if t.requires_grad:
                     terms.append(t)
                 return
             # no fused kernel for this site: materialised log_prob + autograd
             lp = site["fn"].log_prob(site["value"], *site["args"], **site["kwargs"])
             lp = scale_and_mask(lp, site["scale"], site["mask"]).sum()
-            elbo_terms.append(coeff * lp.detach())
+            parts.append(lp.detach())
+            coeffs.append(coeff)
             if lp.requires_grad:
                 terms.append(w * lp)
 
@@ -135,24 +155,23 @@ class Trace_ELBO(ELBO):
         for name, site in guide_trace.nodes.items():
             if site["type"] == "sample":
                 add_site(site, -1.0)
-        if len(elbo_terms) > 1:
-            elbo = torch.stack([e.reshape(()) for e in elbo_terms]).sum()
-        elif elbo_terms:
-            elbo = elbo_terms[0].reshape(())
-        else:
-            elbo = torch.zeros(())
-        return elbo, terms
+        if not parts:
+            return torch.zeros(()), terms
+        # loss = sum_i (-coeff_i / P) * part_i : one stack + one dot against a cached vector
+        ref = parts[0]
+        cvec = _coeff_vector(tuple(-c / P for c in coeffs), ref)
+        loss = torch.dot(torch.stack([e.reshape(()) for e in parts]), cvec)
+        return loss, terms
 
     def loss_and_grads_tensor(self, model, guide, *args, **kwargs):
         """Like ``loss_and_grads`` but returns the loss as a 0-d DEVICE tensor without
         synchronising (used by the graph-captured step)."""
-        loss = 0.0
+        loss = None
         for model_trace, guide_trace in self._get_traces(model, guide, args, kwargs):
             trainable = any(site["type"] == "param" for trace in (model_trace, guide_trace)
                             for site in trace.nodes.values())
             if _all_reparam(guide_trace):
-                elbo, terms = self._fused_particle(model_trace, guide_trace)
-                loss = loss + (-elbo / self.num_particles)
+                loss_particle, terms = self._fused_particle(model_trace, guide_trace)
                 if trainable and terms:
                     # every term's upstream gradient is exactly 1 (contract of the fused nodes);
                     # pass one cached ones-scalar instead of letting autograd fill a new one per term
@@ -160,10 +179,11 @@ class Trace_ELBO(ELBO):
                     torch.autograd.backward(terms, ones, retain_graph=self.retain_graph)
             else:
                 loss_particle, surrogate = self._differentiable_loss_particle(model_trace, guide_trace)
-                loss = loss + loss_particle / self.num_particles
+                loss_particle = loss_particle / self.num_particles
                 if trainable and getattr(surrogate, "requires_grad", False):
                     (surrogate / self.num_particles).backward(retain_graph=self.retain_graph)
-        return loss
+            loss = loss_particle if loss is None else loss + loss_particle
+        return loss if loss is not None else 0.0
 
     def loss_and_grads(self, model, guide, *args, **kwargs):
         loss = torch_item(self.loss_and_grads_tensor(model, guide, *args, **kwargs))

@@ -60,7 +60,12 @@ class ParamStoreDict:
     def __getitem__(self, name):
         unconstrained = self._params[name]
         constraint = self._constraints[name]
-        constrained = transform_to(constraint)(unconstrained)
+        if constraint is constraints.positive:
+            # transform_to(positive) = Affine(0, 1) o Exp: the affine part is the identity, skip its
+            # two launches (and two more in backward) per parameter per step
+            constrained = unconstrained.exp()
+        else:
+            constrained = transform_to(constraint)(unconstrained)
         constrained.unconstrained = weakref.ref(unconstrained)
         constrained._pyro_unconstrained_param = unconstrained
         return constrained

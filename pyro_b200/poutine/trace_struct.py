@@ -145,9 +145,19 @@ class Trace:
                 site["log_prob_sum"] = value.log_prob.sum()
 
 
-def _fused(site, weight, sum_coeff, unit=True):
+class ScaledTerm:
+    """A precomputed 0-d ``sum log_prob`` (fused draw) and the coefficient it enters the ELBO with."""
+    __slots__ = ("tensor", "coeff")
+
+    def __init__(self, tensor, coeff):
+        self.tensor, self.coeff = tensor, coeff
+
+
+def _fused(site, weight, sum_coeff, unit=True, claim=False):
     """Fused ``sum_coeff * sum(scale*mask*log_prob)`` of a site, or None if it has no fused path
-    (tensor-valued scale, python-bool mask False, exotic distribution)."""
+    (tensor-valued scale, python-bool mask False, exotic distribution).  With ``claim`` (and the
+    unit-upstream contract) a site whose value is a fused reparameterised draw from its own
+    distribution returns a :class:`ScaledTerm` around the sum computed at sampling time."""
     fn = site["fn"]
     scale = site["scale"]
     mask = site["mask"]
@@ -161,6 +171,11 @@ def _fused(site, weight, sum_coeff, unit=True):
         mask = None
     if site["args"] or site["kwargs"]:
         return None
+    if claim and unit and mask is None:
+        from ..distributions import claim_rsample_score
+        lq = claim_rsample_score(fn, site["value"], weight * scale)
+        if lq is not None:
+            return ScaledTerm(lq, sum_coeff * scale)
     f = getattr(fn, "_fused_sum", None)
     if f is None:
         return None

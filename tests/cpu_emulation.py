@@ -145,6 +145,20 @@ def _reduce_to(src, dst):
     view.copy_(src.sum_to_size(view.shape))
 
 
+def _normal_rsample_score(loc, scale, eps):
+    # families 14/15 of include/pyro_b200.h, restated with the oracle's Normal log density
+    z = loc + eps * scale
+    lq = odists.ELEMENTWISE[0][0](z, loc, scale).sum()
+    return z.detach(), lq.detach()
+
+
+def _normal_rsample_backward(gz, eps, loc, scale, c, need_loc, need_scale):
+    gz = gz.expand(eps.shape)
+    gloc = gz.sum_to_size(loc.shape) if need_loc else None
+    gscale = (gz * eps - c / scale).sum_to_size(scale.shape) if need_scale else None
+    return gloc, gscale
+
+
 @contextlib.contextmanager
 def enabled():
     """Patch the native seams with oracle-backed CPU stand-ins."""
@@ -169,9 +183,14 @@ def enabled():
     saved_leaf = nuts.NUTS._leaf_vector
     nuts.NUTS._leaf_vector = _leaf_vector
     ops.reduce_to = _reduce_to
+    saved_rs = (ops.normal_rsample_score, ops.normal_rsample_backward, N.EMULATE_RSAMPLE)
+    ops.normal_rsample_score = _normal_rsample_score
+    ops.normal_rsample_backward = _normal_rsample_backward
+    N.EMULATE_RSAMPLE = True
     try:
         yield
     finally:
+        ops.normal_rsample_score, ops.normal_rsample_backward, N.EMULATE_RSAMPLE = saved_rs
         pdist._BernoulliLinear._fused_sum = saved_glm
         nuts.NUTS._leaf_vector = saved_leaf
         (ops.site_score, N.require_cuda, optim.ClippedAdam._launch, optim.AdagradRMSProp._launch,

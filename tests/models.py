@@ -65,8 +65,9 @@ class InjectNoise(poutine.Messenger):
     tests/infer/test_gradient.py:77-91), so runs are comparable across devices and with the
     reference goldens."""
 
-    def __init__(self, eps):
+    def __init__(self, eps, fused_draw=False):
         self.eps = eps
+        self.fused_draw = fused_draw   # route the draw through Normal.rsample_with_noise (b2 family 14)
 
     def _pyro_sample(self, msg):
         if msg["name"] in self.eps and not msg["is_observed"]:
@@ -75,7 +76,11 @@ class InjectNoise(poutine.Messenger):
             while hasattr(base, "base_dist"):
                 base = base.base_dist
             e = self.eps[msg["name"]]
-            msg["value"] = base.loc + e.to(base.loc.dtype) * base.scale
+            if self.fused_draw:
+                shape = torch.broadcast_shapes(e.shape, base.batch_shape)
+                msg["value"] = base.rsample_with_noise(e.to(base.loc.dtype).expand(shape).contiguous())
+            else:
+                msg["value"] = base.loc + e.to(base.loc.dtype) * base.scale
             msg["done"] = True
 
 

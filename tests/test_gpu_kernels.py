@@ -40,6 +40,16 @@ MAKE = {
 }
 
 
+@pytest.fixture(params=["small", "large"])
+def site_kernels(request):
+    """The reference's fixtures are a few hundred elements: run them through the one-CTA kernel
+    (default for sites <= B2_SITE_SMALL_N) AND through the multi-CTA vector / generic kernels."""
+    from pyro_b200 import _native as N
+    N.FORCE_LARGE_SITE_KERNELS = request.param == "large"
+    yield request.param
+    N.FORCE_LARGE_SITE_KERNELS = False
+
+
 def _load(key, dtype):
     g = load_npz("dist_random.npz")
     v = torch.as_tensor(g[key + ".value"])
@@ -60,7 +70,7 @@ def _close(a, ref, tol):
 
 @pytest.mark.parametrize("key", sorted(MAKE))
 @pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-12, 1e-9), (torch.float32, 1e-5, 2e-4)])
-def test_log_prob_and_backward_match_reference(key, dtype, tol, gtol):
+def test_log_prob_and_backward_match_reference(site_kernels, key, dtype, tol, gtol):
     g, v, ps = _load(key, dtype)
     ps = [p.requires_grad_(True) for p in ps]
     has_dv = key + ".dvalue" in g
@@ -93,7 +103,7 @@ def test_log_prob_and_backward_match_reference(key, dtype, tol, gtol):
 @pytest.mark.parametrize("key", ["normal", "gamma", "bernoulli_logits", "normal_bcast", "normal_bcast2",
                                  "dirichlet_bcast", "categorical_bcast", "mvn_bcast", "beta", "poisson"])
 @pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-11, 1e-9), (torch.float32, 2e-5, 3e-4)])
-def test_fused_sum_path_scale_mask_weight(key, dtype, tol, gtol):
+def test_fused_sum_path_scale_mask_weight(site_kernels, key, dtype, tol, gtol):
     """ONE kernel: sum(scale*mask*lp) and the final weighted gradients, vs autograd on the oracle."""
     g, v, ps = _load(key, dtype)
     torch.manual_seed(0)
@@ -126,7 +136,7 @@ def test_fused_sum_path_scale_mask_weight(key, dtype, tol, gtol):
         _close(a, b, gtol)
 
 
-def test_kl_kernels():
+def test_kl_kernels(site_kernels):
     g = load_npz("kl.npz")
     for name, cls in (("normal", dist.Normal), ("gamma", dist.Gamma)):
         ps = [torch.as_tensor(g["%s.p%d" % (name, i)]).to(DEV).requires_grad_(True) for i in range(4)]
@@ -175,7 +185,7 @@ def test_large_sum_property_and_determinism():
     assert torch.allclose(lp[:3, :5000].cpu().double(), o, atol=1e-5)
 
 
-def test_empty_and_ragged_sites():
+def test_empty_and_ragged_sites(site_kernels):
     z = torch.zeros(0, 5, device=DEV)
     d = dist.Normal(torch.zeros(5, device=DEV), torch.ones(5, device=DEV))
     assert d.log_prob(z).shape == (0, 5)
@@ -196,7 +206,7 @@ def test_empty_and_ragged_sites():
     assert torch.allclose(lpt.cpu(), odists.normal(torch.zeros(19, 37, dtype=torch.float64), a.t().cpu(), torch.ones((), dtype=torch.float64)), atol=1e-12)
 
 
-def test_edge_values():
+def test_edge_values(site_kernels):
     """-inf outside the support, NaN propagation, masked NaNs do not leak."""
     hc = dist.HalfCauchy(torch.ones(3, device=DEV))
     lp = hc.log_prob(torch.tensor([-1.0, 0.0, 2.0], device=DEV))
@@ -210,3 +220,60 @@ def test_edge_values():
     p = dist.Poisson(torch.tensor([0.0, 2.0], device=DEV))
     lp = p.log_prob(torch.tensor([0.0, 3.0], device=DEV))
     assert abs(float(lp[0])) < 5e-6  # fp32 lgamma(1) via the shifted Stirling series: |err| ~ 1e-6
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-6)])
+@pytest.mark.parametrize("shape,pshape", [((64, 1, 32), (32,)), ((64, 1), ()), ((3, 5, 7), (5, 1)),
+                                          ((300, 1000), (1000,)), ((17,), (17,))])
+def test_fused_normal_draw_and_backward(shape, pshape, dtype, tol):
+    """b2 families 14 / 15 (draw + own score, and its backward) against torch autograd on the
+    same noise: z, sum log q, and d/d(loc, scale) of  L = sum(gz * z) + c * sum log q(z)  reduced
+    to the parameters' stored shapes (one-CTA kernel for the first three shapes, vector kernel +
+    b2_reduce_to for [300, 1000])."""
+    torch.manual_seed(0)
+    loc = torch.randn(pshape, device=DEV, dtype=dtype)
+    scale = (0.5 + torch.rand(pshape, device=DEV, dtype=dtype))
+    eps = torch.randn(shape, device=DEV, dtype=dtype)
+    gz = torch.randn(shape, device=DEV, dtype=dtype)
+    c = 0.37
+    z, lq = _ops.normal_rsample_score(loc, scale, eps)
+    lo, so = loc.double().cpu().requires_grad_(True), scale.double().cpu().requires_grad_(True)
+    zo = lo + eps.double().cpu() * so
+    lqo = odists.normal(zo, lo, so).sum()
+    _close(z, zo.detach(), tol)
+    assert abs(float(lq) - float(lqo)) <= 50 * tol * max(1.0, abs(float(lqo)))
+    gl, gs = _ops.normal_rsample_backward(gz, eps, loc, scale, c, True, True)
+    L = (gz.double().cpu() * zo).sum() + c * lqo
+    glo, gso = torch.autograd.grad(L, [lo, so])
+    assert gl.shape == loc.shape and gs.shape == scale.shape
+    n_red = eps.numel() / max(1, loc.numel())
+    _close(gl, glo, 20 * tol * max(1.0, n_red ** 0.5))
+    _close(gs, gso, 20 * tol * max(1.0, n_red ** 0.5))
+
+
+def test_fused_draw_step_equals_sitewise_step():
+    """Free-running guide (torch.randn noise, same seed): one Trace_ELBO loss_and_grads with the
+    fused draw claimed by the ELBO equals the same step with every site scored by b2_site_score."""
+    import models
+    import pyro_b200 as pyro
+    from pyro_b200 import _native as N
+    from pyro_b200.infer import Trace_ELBO
+    torch.manual_seed(1)
+    X = torch.randn(500, 6, device=DEV)
+    y = (torch.rand(500, device=DEV) < 0.4).float()
+    res = []
+    for fused in (True, False):
+        N.FUSED_DRAW = fused
+        try:
+            pyro.clear_param_store()
+            torch.manual_seed(7)
+            elbo = Trace_ELBO(num_particles=16, vectorize_particles=True, max_plate_nesting=1)
+            loss = elbo.loss_and_grads(models.logistic_model, models.logistic_guide, X, y)
+            store = pyro.get_param_store()
+            grads = {k: store._params[k].grad.clone() for k in ("w_loc", "w_scale", "b_loc", "b_scale")}
+            res.append((loss, grads))
+        finally:
+            N.FUSED_DRAW = True
+    assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[1][0])
+    for k in res[0][1]:
+        assert torch.allclose(res[0][1][k], res[1][1][k], rtol=2e-4, atol=2e-4 * float(res[1][1][k].abs().max())), k

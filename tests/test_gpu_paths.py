@@ -23,7 +23,7 @@ pytestmark = pytest.mark.gpu
 DEV = device()
 
 
-def _svi_trajectory(model, elbo_cls, dtype, tag, tol, steps=None):
+def _svi_trajectory(model, elbo_cls, dtype, tag, tol, steps=None, fused_draw=False):
     g = load_npz("svi_logistic.npz")
     torch.set_default_dtype(dtype)
     X, y = torch.as_tensor(g["X"]).to(DEV, dtype), torch.as_tensor(g["y"]).to(DEV, dtype)
@@ -32,7 +32,7 @@ def _svi_trajectory(model, elbo_cls, dtype, tag, tol, steps=None):
     box = {"i": 0}
 
     def guide(X, y):
-        with models.InjectNoise({"w": eps_w[box["i"]], "b": eps_b[box["i"]]}):
+        with models.InjectNoise({"w": eps_w[box["i"]], "b": eps_b[box["i"]]}, fused_draw=fused_draw):
             models.logistic_guide(X, y)
 
     svi = SVI(model, guide, ClippedAdam({"lr": 0.01}),
@@ -47,8 +47,11 @@ def _svi_trajectory(model, elbo_cls, dtype, tag, tol, steps=None):
 
 
 @pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-9), ("f32", torch.float32, 3e-4)])
-def test_svi_logistic_matches_reference_trajectory(tag, dtype, tol):
-    _svi_trajectory(models.logistic_model, Trace_ELBO, dtype, tag, tol)
+@pytest.mark.parametrize("fused_draw", [False, True])
+def test_svi_logistic_matches_reference_trajectory(tag, dtype, tol, fused_draw):
+    """fused_draw: the guide draws and their log densities come from the fused rsample kernel
+    (b2 family 14) and the ELBO claims them; otherwise every site is scored by b2_site_score."""
+    _svi_trajectory(models.logistic_model, Trace_ELBO, dtype, tag, tol, fused_draw=fused_draw)
 
 
 def test_svi_logistic_fused_glm_matches_reference_trajectory():
@@ -185,7 +188,10 @@ def test_elbo_grads_gamma_poisson_mask_subsample(cls, tag):
 
 
 @pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-12), ("f32", torch.float32, 2e-6)])
-def test_fused_optimisers_match_reference(tag, dtype, tol):
+@pytest.mark.parametrize("q_shape", [(5, 3), (70, 100)])
+def test_fused_optimisers_match_reference(tag, dtype, tol, q_shape):
+    """q_shape (5, 3): every tensor fits one CTA, ClippedAdam's advance + update is ONE launch;
+    (70, 100) exceeds that bound and takes the advance kernel + multi-CTA update kernel."""
     g = load_npz("optim.npz")
     for name, mk in (
         ("clipped_adam", lambda: ClippedAdam({"lr": 0.05, "betas": (0.9, 0.99), "clip_norm": 2.0, "lrd": 0.97, "weight_decay": 0.01})),
@@ -193,7 +199,7 @@ def test_fused_optimisers_match_reference(tag, dtype, tol):
         ("adagrad_rmsprop", lambda: AdagradRMSProp({"eta": 4.5, "t": 0.1})),
     ):
         p = torch.as_tensor(g["p0_" + tag]).to(DEV).clone().requires_grad_(True)
-        q = torch.zeros(5, 3, device=DEV, dtype=dtype).requires_grad_(True)  # a second tensor in the same launch
+        q = torch.zeros(q_shape, device=DEV, dtype=dtype).requires_grad_(True)  # a second tensor in the same launch
         pyro.get_param_store()._param_to_name[p] = "p"
         pyro.get_param_store()._param_to_name[q] = "q"
         opt = mk()

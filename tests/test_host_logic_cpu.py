@@ -73,9 +73,11 @@ def dist_ref_normal(x, m, s):
 
 @pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-9), ("f32", torch.float32, 3e-4)])
 @pytest.mark.parametrize("elbo_cls", [Trace_ELBO])
-def test_svi_logistic_matches_reference_trajectory(emu, tag, dtype, tol, elbo_cls):
+@pytest.mark.parametrize("fused_draw", [False, True])
+def test_svi_logistic_matches_reference_trajectory(emu, monkeypatch, tag, dtype, tol, elbo_cls, fused_draw):
     """The full host stack (particle plate, replay, fused-site ELBO assembly, per-parameter
-    ClippedAdam state) reproduces the reference's 5-step SVI trajectory."""
+    ClippedAdam state) reproduces the reference's 5-step SVI trajectory -- with the guide draws
+    scored site by site, and with draw + score claimed from the fused rsample node."""
     g = load_npz("svi_logistic.npz")
     torch.set_default_dtype(dtype)
     X, y = torch.as_tensor(g["X"]).to(dtype), torch.as_tensor(g["y"]).to(dtype)
@@ -84,14 +86,20 @@ def test_svi_logistic_matches_reference_trajectory(emu, tag, dtype, tol, elbo_cl
     box = {"i": 0}
 
     def guide(X, y):
-        with models.InjectNoise({"w": eps_w[box["i"]], "b": eps_b[box["i"]]}):
+        with models.InjectNoise({"w": eps_w[box["i"]], "b": eps_b[box["i"]]}, fused_draw=fused_draw):
             models.logistic_guide(X, y)
 
     svi = SVI(models.logistic_model, guide, ClippedAdam({"lr": 0.01}),
               elbo_cls(num_particles=P, vectorize_particles=True, max_plate_nesting=1))
+    claims = []
+    real_claim = dist.claim_rsample_score
+    monkeypatch.setattr(dist, "claim_rsample_score",
+                        lambda fn, value, coeff: claims.append(real_claim(fn, value, coeff)) or claims[-1])
     for i in range(eps_w.shape[0]):
         box["i"] = i
         loss = svi.step(X, y)
+        # both guide sites (and only those) hand over a precomputed sum log q when the draw is fused
+        assert sum(c is not None for c in claims) == (2 * (i + 1) if fused_draw else 0)
         assert abs(loss - g["losses_" + tag][i]) <= 10 * tol * abs(g["losses_" + tag][i]), i
         store = pyro.get_param_store()
         flat = torch.cat([store[k].detach().reshape(-1).double() for k in ("w_loc", "w_scale", "b_loc", "b_scale")])

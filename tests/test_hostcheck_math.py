@@ -47,6 +47,28 @@ def test_kl_functors():
             assert np.allclose(dp[k], g["%s.dp%d" % (name, k)], atol=1e-7, rtol=1e-7)
 
 
+def test_fused_normal_draw_functors():
+    """Families 14 / 15 (include/pyro_b200.h): the fused draw reproduces the reference's
+    rsample (normal.py:82-85) and log_prob (normal.py:87-102) on the golden Normal fixture's
+    parameters, and its backward is the chain rule of L = sum(gz*z) + c*sum log q(z)."""
+    g = load_npz("dist_random.npz")
+    loc, scale = g["normal.p0"], g["normal.p1"]
+    rng = np.random.default_rng(0)
+    eps, gz = rng.standard_normal(loc.shape), rng.standard_normal(loc.shape)
+    lp, z, _ = H.eval_family(14, eps, [loc, scale])
+    assert np.allclose(z, loc + eps * scale, rtol=1e-15, atol=0)
+    lo, so = torch.tensor(loc, requires_grad=True), torch.tensor(scale, requires_grad=True)
+    zt = lo + torch.tensor(eps) * so
+    lq = torch.distributions.Normal(lo, so).log_prob(zt)
+    assert np.allclose(lp, lq.detach().numpy(), rtol=1e-12, atol=1e-12)
+    c = np.full(loc.shape, 0.37)
+    _, _, dp = H.eval_family(15, gz, [eps, scale, c])
+    L = (torch.tensor(gz) * zt).sum() + 0.37 * lq.sum()
+    gl, gs = torch.autograd.grad(L, [lo, so])
+    assert np.allclose(dp[0], gl.numpy(), rtol=1e-12, atol=1e-12)
+    assert np.allclose(dp[1], gs.numpy(), rtol=1e-9, atol=1e-9)
+
+
 def test_digamma_special_values():
     L = H.lib()
     for x in [-2.5, -0.3, 1e-8, 0.5, 1.0, 5.9, 6.0, 100.0, 1e6]:
