@@ -170,6 +170,16 @@ int b2_reduce_to(const b2_tensor* src, b2_tensor* dst, void* workspace, size_t w
                  void* stream);
 
 /*
+ * b2_elbo_combine -- out = SUM_i coeffs[i] * (*terms[i]) over n <= 32 zero-dimensional DEVICE
+ * scalars of `dtype` (`terms` and `coeffs` are HOST arrays, passed to the kernel by value; added
+ * in index order).  Assembles the loss from the per-site sums in one launch; replaces the chain
+ * of python-level `elbo_particle = elbo_particle + site["log_prob_sum"]` additions, the
+ * `/ num_particles` and the negation of pyro/infer/trace_elbo.py:82-112,147-152.
+ */
+int b2_elbo_combine(const void* const* terms, const double* coeffs, int n, int dtype, void* out,
+                    void* stream);
+
+/*
  * b2_glm_bernoulli_logits -- fused Bayesian-logistic-regression likelihood term (BASELINE
  * config 2): for P particles, logits[p,n] = <X[n,:], W[p,:]> + b[p];
  *   sum_p[p]  = SUM_n ( y[n]*logits - softplus(logits) )               (Bernoulli log_prob)
@@ -183,6 +193,9 @@ int b2_reduce_to(const b2_tensor* src, b2_tensor* dst, void* workspace, size_t w
  * out_total (nullable): scalar, (=|+=) sum_coeff * scale * SUM_p sum_p[p].
  * For D == 32 the two contractions run on the tensor cores (TF32 operands, fp32 accumulate,
  * logits perturbed by ~1e-3 relative, unbiased); pass B2_FLAG_GLM_FP32 for the fp32 SIMT kernel.
+ * workspace: b2_glm_workspace() bytes, zero-initialised ONCE by the caller (its first 256 bytes
+ * hold a ticket counter that the library leaves zeroed).  Two launches: the streaming kernel
+ * and a finish kernel that sums the CTA partials in a fixed order (deterministic).
  */
 int b2_glm_bernoulli_logits(const float* X, const float* y, const float* W, const float* b,
                             int64_t N, int D, int P, double scale, double weight, double sum_coeff,

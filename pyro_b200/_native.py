@@ -61,6 +61,7 @@ SIGNATURES = {
     "b2_event_score": (_i32, [_i32, _tp, _tp, _i32, _i32, _tp, _f64, _tp, _f64, _f64, _i32, _tp,
                               _vp, _tp, _tp, _vp, _sz, _vp]),
     "b2_reduce_to": (_i32, [_tp, _tp, _vp, _sz, _vp]),
+    "b2_elbo_combine": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "b2_glm_bernoulli_logits": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32,
                                        _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b2_glm_workspace": (_sz, [_i64, _i32, _i32]),

@@ -501,3 +501,48 @@ extern "C" int b2_reduce_to(const b2_tensor* src, b2_tensor* dst, void* workspac
   }
   return check_launch();
 }
+
+// ---- b2_elbo_combine: loss = sum_i coeff[i] * term_i over 0-d device scalars ---------------------
+namespace b2 {
+constexpr int kMaxCombine = 32;
+struct CombineArgs {
+  const void* ptr[kMaxCombine];
+  double coeff[kMaxCombine];
+  int n;
+};
+template <typename T>
+__global__ void elbo_combine_kernel(const CombineArgs a, T* out) {
+  // one warp; lanes load the terms in parallel, thread 0 adds them in index order (deterministic)
+  __shared__ double v[kMaxCombine];
+  const int i = threadIdx.x;
+  if (i < a.n) v[i] = a.coeff[i] * (double)*reinterpret_cast<const T*>(a.ptr[i]);
+  __syncwarp();
+  if (i == 0) {
+    double s = 0.0;
+    for (int k = 0; k < a.n; ++k) s += v[k];
+    *out = (T)s;
+  }
+}
+}  // namespace b2
+
+extern "C" int b2_elbo_combine(const void* const* terms, const double* coeffs, int n, int dtype,
+                               void* out, void* stream) {
+  if (!terms || !coeffs || !out) return B2_ERR_NULL;
+  if (n < 0 || n > b2::kMaxCombine) return B2_ERR_TOO_LARGE;
+  if (dtype != B2_F32 && dtype != B2_F64) return B2_ERR_BAD_DTYPE;
+  b2::CombineArgs a;
+  a.n = n;
+  for (int i = 0; i < n; ++i) {
+    if (!terms[i]) return B2_ERR_NULL;
+    a.ptr[i] = terms[i];
+    a.coeff[i] = coeffs[i];
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == B2_F32)
+    b2::elbo_combine_kernel<float><<<1, 32, 0, s>>>(a, reinterpret_cast<float*>(out));
+  else
+    b2::elbo_combine_kernel<double><<<1, 32, 0, s>>>(a, reinterpret_cast<double*>(out));
+  b2::count_launch();
+  return b2::check_launch();
+}
+

@@ -142,40 +142,45 @@ __global__ void __launch_bounds__(256) glm_finish_kernel(const float* __restrict
                                                          float* __restrict__ out_dW,
                                                          float* __restrict__ out_db,
                                                          double sum_coeff, int flags,
-                                                         float* __restrict__ out_total) {
+                                                         float* __restrict__ out_total,
+                                                         unsigned int* __restrict__ ticket) {
   const int total = P * (D + 2);
-  if (out_total && blockIdx.x == gridDim.x - 1) {
-    // the extra last CTA: total over particles AND CTAs straight from the partials (fixed order),
-    // with the ELBO coefficient -- saves a third launch
-    __shared__ double smem[32];
-    double acc = 0.0;
-    const int n = nblocks * P;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int bl = i / P, p = i - bl * P;
-      acc += (double)partials[(int64_t)bl * total + (int64_t)p * (D + 2) + D + 1];
-    }
-    double red[1] = {acc};
-    block_sum<1>(red, smem);
-    if (threadIdx.x == 0) {
-      const double v = sum_coeff * scale * red[0];
-      *out_total = (flags & B2_FLAG_ACCUMULATE_SUM) ? (float)((double)*out_total + v) : (float)v;
-    }
-    return;
-  }
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (e >= total) return;
   double s = 0.0;
   for (int bl = lane; bl < nblocks; bl += 32) s += (double)partials[(int64_t)bl * total + e];
   s = warp_sum(s);
-  if (lane != 0) return;
   const int p = e / (D + 2), d = e - p * (D + 2);
   if (d < D) {
-    if (out_dW) out_dW[(int64_t)p * D + d] = (float)(weight * scale * s);
-  } else if (d == D) {
-    if (out_db) out_db[p] = (float)(weight * scale * s);
-  } else {
+    if (lane == 0 && out_dW) out_dW[(int64_t)p * D + d] = (float)(weight * scale * s);
+    return;
+  }
+  if (d == D) {
+    if (lane == 0 && out_db) out_db[p] = (float)(weight * scale * s);
+    return;
+  }
+  // per-particle sum; the LAST of the P warps to get here also totals them (fixed order), with
+  // the ELBO coefficient -- a ticket instead of a third launch
+  unsigned int t = 0;
+  if (lane == 0) {
     sum_p[p] = (float)(scale * s);
+    if (out_total) {
+      __threadfence();
+      t = atomicAdd(ticket, 1u);
+    }
+  }
+  if (!out_total) return;
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t != (unsigned)(P - 1)) return;
+  __threadfence();
+  double acc = 0.0;
+  for (int q = lane; q < P; q += 32) acc += (double)__ldcg(sum_p + q);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const double v = sum_coeff * acc;
+    *out_total = (flags & B2_FLAG_ACCUMULATE_SUM) ? (float)((double)*out_total + v) : (float)v;
+    *ticket = 0u;
   }
 }
 
@@ -197,8 +202,8 @@ inline int glm_grid_x(int64_t N) {
 using namespace b2;
 
 extern "C" size_t b2_glm_workspace(int64_t N, int D, int P) {
-  // CTA partials + one [P] row for the per-particle sums
-  return ((size_t)glm_grid_x(N) * (size_t)P * (size_t)(D + 2) + (size_t)P) * sizeof(float);
+  // [ticket, 256 B] + CTA partials + one [P] row for the per-particle sums
+  return 256 + ((size_t)glm_grid_x(N) * (size_t)P * (size_t)(D + 2) + (size_t)P) * sizeof(float);
 }
 
 extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const float* W,
@@ -215,7 +220,8 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   const bool use_mma = (D == 32) && !(flags & B2_FLAG_GLM_FP32);
   const int gx = use_mma ? glm_mma_grid_x(N) : glm_grid_x(N);
   dim3 grid((unsigned)gx, (unsigned)((P + kGlmParticles - 1) / kGlmParticles), 1);
-  float* partials = reinterpret_cast<float*>(workspace);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
+  float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   if (use_mma) {
     launch_glm_mma(X, y, W, b, N, P, partials, gx, s);
   } else
@@ -228,8 +234,8 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   }
   float* sum_p = out_sum_p ? out_sum_p : partials + (size_t)gx * P * (D + 2);
   const int total = P * (D + 2);
-  glm_finish_kernel<<<(total + 7) / 8 + (out_total ? 1 : 0), 256, 0, s>>>(
-      partials, gx, P, D, scale, weight, sum_p, out_dW, out_db, sum_coeff, flags, out_total);
+  glm_finish_kernel<<<(total + 7) / 8, 256, 0, s>>>(
+      partials, gx, P, D, scale, weight, sum_p, out_dW, out_db, sum_coeff, flags, out_total, ticket);
   const int nl = 2;
   count_launch(nl);
   return check_launch();

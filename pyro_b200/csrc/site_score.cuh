@@ -356,37 +356,41 @@ __global__ void __launch_bounds__(256) site_gen_kernel(const SiteArgs a) {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void small_reduce_out(const SiteArgs& a, const OutOpnd& o, const T* slab) {
-  // dims with st != 0 index the output; dims with st == 0 are summed
-  int64_t cst[kMaxD];
-  int64_t m = 1;
+  // dims with st != 0 index the output; dims with st == 0 are summed.  n <= kSmallN, so every
+  // index fits 32 bits (64-bit integer division is a ~100-instruction dependent chain on the GPU).
+  unsigned cst[kMaxD], shp[kMaxD];
+  unsigned m = 1;
   {
-    int64_t c = 1;
+    unsigned c = 1;
     for (int d = a.ndim - 1; d >= 0; --d) {
+      shp[d] = (unsigned)a.shape[d];
       cst[d] = c;
-      c *= a.shape[d];
-      if (o.st[d] != 0) m *= a.shape[d];
+      c *= shp[d];
+      if (o.st[d] != 0) m *= shp[d];
     }
   }
-  const int64_t q = a.n / m;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const unsigned n = (unsigned)a.n;
+  const unsigned q = n / m;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   T* out = reinterpret_cast<T*>(o.ptr);
-  for (int64_t j = warp; j < m; j += nwarps) {
-    int64_t rem = j, base = 0, off = 0;
+  for (unsigned j = warp; j < m; j += nwarps) {
+    unsigned rem = j, base = 0;
+    int64_t off = 0;
     for (int d = a.ndim - 1; d >= 0; --d) {
       if (o.st[d] == 0) continue;
-      const int64_t qq = rem / a.shape[d];
-      const int64_t idx = rem - qq * a.shape[d];
+      const unsigned qq = rem / shp[d];
+      const unsigned idx = rem - qq * shp[d];
       rem = qq;
       base += idx * cst[d];
-      off += idx * o.st[d];
+      off += (int64_t)idx * o.st[d];
     }
     double s = 0.0;
-    for (int64_t t = lane; t < q; t += 32) {
-      int64_t r2 = t, flat = base;
+    for (unsigned t = lane; t < q; t += 32) {
+      unsigned r2 = t, flat = base;
       for (int d = a.ndim - 1; d >= 0; --d) {
         if (o.st[d] != 0) continue;
-        const int64_t qq = r2 / a.shape[d];
-        flat += (r2 - qq * a.shape[d]) * cst[d];
+        const unsigned qq = r2 / shp[d];
+        flat += (r2 - qq * shp[d]) * cst[d];
         r2 = qq;
       }
       s += (double)slab[flat];
@@ -407,16 +411,18 @@ __global__ void __launch_bounds__(kSmallThreads) site_small_kernel(const SiteArg
 #pragma unroll
   for (int k = 0; k < NRED; ++k) acc[k] = (T)0;
   T* slab = reinterpret_cast<T*>(a.scratch);
+  const unsigned n = (unsigned)a.n;
 
-  for (int64_t i = threadIdx.x; i < a.n; i += blockDim.x) {
-    int64_t rem = i;
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    unsigned rem = i;
     int64_t ox = 0, om = 0, ou = 0, olp = 0, ogx = 0;
     int64_t op[NP > 0 ? NP : 1], ogp[NP > 0 ? NP : 1];
 #pragma unroll
     for (int k = 0; k < NP; ++k) op[k] = ogp[k] = 0;
     for (int d = a.ndim - 1; d >= 0; --d) {
-      const int64_t q = rem / a.shape[d];
-      const int64_t idx = rem - q * a.shape[d];
+      const unsigned sd = (unsigned)a.shape[d];
+      const unsigned q = rem / sd;
+      const int64_t idx = (int64_t)(rem - q * sd);
       rem = q;
       ox += idx * a.x.st[d];
       om += idx * a.mask.st[d];
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(kSmallThreads) site_small_kernel(const SiteArg
         const T g = m ? f * o.dp[k] : (T)0;
         acc[2 + k] += g;
         if (a.gp[k].mode == 1) reinterpret_cast<T*>(a.gp[k].ptr)[ogp[k]] = g;
-        else if (a.gp[k].mode == 3) slab[(int64_t)(1 + k) * a.n + i] = g;
+        else if (a.gp[k].mode == 3) slab[(size_t)(1 + k) * n + i] = g;
       }
     }
   }
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(kSmallThreads) site_small_kernel(const SiteArg
     if (a.gx.mode == 3) small_reduce_out<T>(a, a.gx, slab);
 #pragma unroll
     for (int k = 0; k < NP; ++k)
-      if (a.gp[k].mode == 3) small_reduce_out<T>(a, a.gp[k], slab + (int64_t)(1 + k) * a.n);
+      if (a.gp[k].mode == 3) small_reduce_out<T>(a, a.gp[k], slab + (size_t)(1 + k) * n);
   }
 }
 

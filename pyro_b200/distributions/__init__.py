@@ -291,27 +291,37 @@ class Normal(_Elementwise):
         """The draw for given standard-normal noise ``eps`` (shape = sample_shape + batch_shape)."""
         if not N.FUSED_DRAW or (not eps.is_cuda and not N.EMULATE_RSAMPLE):
             return torch.addcmul(self.loc, eps, self.scale)   # plain draw; scored later by b2_site_score
-        tag = _RsampleTag(self.loc, self.scale)
-        z, lq = _NormalRsampleFn.apply(tag, self.loc, self.scale, eps)
-        tag.lq = lq
-        z._b2_rsample = tag
+        coeff = _Coeff()
+        z, lq = _NormalRsampleFn.apply(coeff, self.loc, self.scale, eps)
+        z._b2_rsample = _RsampleTag(self.loc, self.scale, lq, coeff)
         return z
+
+
+class _Coeff:
+    """Coefficient with which a fused draw's ``sum log q`` entered the loss (set by whoever claims
+    it).  Kept apart from the tag: the autograd node holds THIS object only -- holding the tag (which
+    holds the node's own output) would be a reference cycle through the C++ graph that Python's GC
+    cannot break, keeping every step's graph alive."""
+    __slots__ = ("value", "__weakref__")
+
+    def __init__(self):
+        self.value = 0.0
 
 
 class _RsampleTag:
     """Travels on a fused draw: the parameters it was drawn with, its summed log density, and the
-    coefficient with which that sum entered the loss (set by whoever claims it)."""
+    coefficient holder shared with the draw's autograd node."""
     __slots__ = ("loc", "scale", "lq", "coeff")
 
-    def __init__(self, loc, scale):
-        self.loc, self.scale, self.lq, self.coeff = loc, scale, None, 0.0
+    def __init__(self, loc, scale, lq, coeff):
+        self.loc, self.scale, self.lq, self.coeff = loc, scale, lq, coeff
 
 
 class _NormalRsampleFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tag, loc, scale, eps):
+    def forward(ctx, coeff, loc, scale, eps):
         z, lq = _ops.normal_rsample_score(loc, scale, eps)
-        ctx.tag = tag
+        ctx.coeff = coeff
         ctx.save_for_backward(eps, loc, scale)
         ctx.set_materialize_grads(False)
         return z, lq
@@ -324,7 +334,7 @@ class _NormalRsampleFn(torch.autograd.Function):
             gz = _const(0.0, eps.dtype, eps.device)
         # the sum log q output is only reachable through the tag; its consumer folds its
         # coefficient into tag.coeff and sends a unit upstream gradient (Trace_ELBO's contract)
-        c = ctx.tag.coeff if glq is not None else 0.0
+        c = ctx.coeff.value if glq is not None else 0.0
         gloc, gscale = _ops.normal_rsample_backward(gz, eps, loc, scale, c,
                                                     ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return None, gloc, gscale, None
@@ -344,7 +354,7 @@ def claim_rsample_score(fn, value, coeff):
         return None
     if torch.broadcast_shapes(value.shape, base.batch_shape) != value.shape:
         return None
-    tag.coeff += float(coeff)
+    tag.coeff.value += float(coeff)
     return tag.lq
 
 

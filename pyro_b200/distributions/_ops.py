@@ -369,3 +369,19 @@ def normal_rsample_backward(gz, eps, loc, scale, c, need_loc, need_scale):
                           need_dparams=[need_loc, need_scale, False],
                           grad_like=[loc, scale, None])
     return gp[0], gp[1]
+
+
+def elbo_combine(terms, coeffs):
+    """0-d ``sum_i coeffs[i] * terms[i]`` of 0-d device tensors in ONE launch (b2_elbo_combine)."""
+    ref = terms[0]
+    N.require_cuda(ref, "ELBO assembly")
+    n = len(terms)
+    if n > 32:
+        return torch.dot(torch.stack([t.reshape(()) for t in terms]),
+                         torch.tensor(coeffs, dtype=ref.dtype, device=ref.device))
+    out = torch.empty((), dtype=ref.dtype, device=ref.device)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in terms])
+    cs = (ctypes.c_double * n)(*[float(c) for c in coeffs])
+    N.check(N.lib().b2_elbo_combine(ptrs, cs, n, N._DTYPES[ref.dtype], out.data_ptr(),
+                                    N.stream_ptr(ref.device)), "b2_elbo_combine")
+    return out

@@ -45,17 +45,6 @@ def _one_like(t):
     return one
 
 
-_COEFFS = {}
-
-
-def _coeff_vector(coeffs, like):
-    key = (coeffs, like.device, like.dtype)
-    v = _COEFFS.get(key)
-    if v is None:
-        v = _COEFFS[key] = torch.tensor(coeffs, dtype=like.dtype, device=like.device)
-    return v
-
-
 def _all_reparam(guide_trace):
     for site in guide_trace.nodes.values():
         if site["type"] == "sample" and not getattr(site["fn"], "has_rsample", False):
@@ -157,10 +146,10 @@ class Trace_ELBO(ELBO):
                 add_site(site, -1.0)
         if not parts:
             return torch.zeros(()), terms
-        # loss = sum_i (-coeff_i / P) * part_i : one stack + one dot against a cached vector
-        ref = parts[0]
-        cvec = _coeff_vector(tuple(-c / P for c in coeffs), ref)
-        loss = torch.dot(torch.stack([e.reshape(()) for e in parts]), cvec)
+        # loss = sum_i (-coeff_i / P) * part_i, assembled on the device in one launch
+        from ..distributions import _ops
+        parts = [e.to(parts[0].dtype) if e.dtype != parts[0].dtype else e for e in parts]
+        loss = _ops.elbo_combine(parts, [-c / P for c in coeffs])
         return loss, terms
 
     def loss_and_grads_tensor(self, model, guide, *args, **kwargs):

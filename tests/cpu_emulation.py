@@ -159,6 +159,10 @@ def _normal_rsample_backward(gz, eps, loc, scale, c, need_loc, need_scale):
     return gloc, gscale
 
 
+def _elbo_combine(terms, coeffs):
+    return sum(c * t.reshape(()) for c, t in zip(coeffs, terms))
+
+
 @contextlib.contextmanager
 def enabled():
     """Patch the native seams with oracle-backed CPU stand-ins."""
@@ -184,6 +188,8 @@ def enabled():
     nuts.NUTS._leaf_vector = _leaf_vector
     ops.reduce_to = _reduce_to
     saved_rs = (ops.normal_rsample_score, ops.normal_rsample_backward, N.EMULATE_RSAMPLE)
+    saved_comb = ops.elbo_combine
+    ops.elbo_combine = _elbo_combine
     ops.normal_rsample_score = _normal_rsample_score
     ops.normal_rsample_backward = _normal_rsample_backward
     N.EMULATE_RSAMPLE = True
@@ -191,6 +197,7 @@ def enabled():
         yield
     finally:
         ops.normal_rsample_score, ops.normal_rsample_backward, N.EMULATE_RSAMPLE = saved_rs
+        ops.elbo_combine = saved_comb
         pdist._BernoulliLinear._fused_sum = saved_glm
         nuts.NUTS._leaf_vector = saved_leaf
         (ops.site_score, N.require_cuda, optim.ClippedAdam._launch, optim.AdagradRMSProp._launch,

@@ -277,3 +277,15 @@ def test_fused_draw_step_equals_sitewise_step():
     assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[1][0])
     for k in res[0][1]:
         assert torch.allclose(res[0][1][k], res[1][1][k], rtol=2e-4, atol=2e-4 * float(res[1][1][k].abs().max())), k
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_elbo_combine(dtype):
+    """b2_elbo_combine: weighted sum of 0-d device scalars in index order, one launch."""
+    torch.manual_seed(0)
+    terms = [torch.randn((), device=DEV, dtype=dtype) * 10 ** k for k in range(7)]
+    coeffs = [1.0, -1.0, 0.5, -1.0 / 64, 2.0, 0.0, -3.0]
+    out = _ops.elbo_combine(terms, coeffs)
+    ref = sum(c * float(t.double()) for c, t in zip(coeffs, terms))
+    assert out.shape == () and out.dtype == dtype
+    assert abs(float(out) - ref) <= (1e-6 if dtype == torch.float32 else 1e-14) * abs(ref)

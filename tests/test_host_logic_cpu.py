@@ -340,3 +340,21 @@ def test_sparse_gamma_def_meanfield_matches_reference(emu):
     Gamma||Gamma KL terms, AdagradRMSProp): 6-step loss trajectory and final parameters of the
     unmodified reference."""
     _def_meanfield("cpu")
+
+
+def test_fused_draw_graph_is_released(emu):
+    """The fused draw's autograd node must die with the draw (a tag <-> node reference cycle would
+    run through the C++ graph, which Python's GC cannot break: every step's graph, and the
+    AccumulateGrad nodes of the parameters with it, would stay alive -- which also breaks CUDA-graph
+    capture on a side stream)."""
+    import gc
+    import weakref
+    loc = torch.zeros(3, requires_grad=True)
+    scale = torch.ones(3, requires_grad=True)
+    z = dist.Normal(loc, scale).rsample((5,))
+    tag = z._b2_rsample
+    assert tag.lq.requires_grad and tag.lq.shape == ()
+    alive = weakref.ref(tag.coeff)
+    del z, tag
+    gc.collect()
+    assert alive() is None
