@@ -158,20 +158,25 @@ B2_HD double fast_log1p_unit(double e) { return log1p(e); }
 // tolerance).  libm's lgammaf alone is ~100 instructions and made the Gamma/Beta/Poisson kernels
 // issue-bound at 10-25% of HBM peak (profiles/micro_logprob_r1_before_fastgamma.txt).
 // Non-positive arguments (never produced by valid parameters) take the accurate route.
-template <bool WANT_PSI>
-B2_HD void lgamma_digamma_f32(float x, float& lg, float& psi) {
+template <bool WANT_PSI, bool WANT_TRI>
+B2_HD void lgamma_polygamma_f32(float x, float& lg, float& psi, float& tri) {
   if (!(x > 0.f) || x > 1e30f) {
     lg = lgammaf(x);
     if (WANT_PSI) psi = digamma<float>(x);
+    if (WANT_TRI) tri = x - x == 0.f ? 1.f / (x * x) : x;  // invalid concentration: inf / NaN
     return;
   }
-  float prod = 1.f, acc = 0.f;
+  float prod = 1.f, acc = 0.f, acc2 = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const bool small = x < 8.f;
     if (small) {
       prod *= x;
-      if (WANT_PSI) acc -= fast_rcp(x);
+      if (WANT_PSI || WANT_TRI) {
+        const float r = fast_rcp(x);
+        if (WANT_PSI) acc -= r;
+        if (WANT_TRI) acc2 += r * r;
+      }
       x += 1.f;
     }
   }
@@ -187,6 +192,16 @@ B2_HD void lgamma_digamma_f32(float x, float& lg, float& psi) {
     psi = acc + lx - 0.5f * inv -
           inv2 * (0.083333333333333333f - inv2 * (0.0083333333333333333f - inv2 * 0.0039682539682539683f));
   }
+  if (WANT_TRI) {
+    // psi'(x) ~ 1/x + 1/(2x^2) + 1/(6x^3) - 1/(30x^5) + 1/(42x^7)
+    tri = acc2 + inv + 0.5f * inv2 +
+          inv * inv2 * (0.16666666666666667f - inv2 * (0.033333333333333333f - inv2 * 0.023809523809523810f));
+  }
+}
+template <bool WANT_PSI>
+B2_HD void lgamma_digamma_f32(float x, float& lg, float& psi) {
+  float tri;
+  lgamma_polygamma_f32<WANT_PSI, false>(x, lg, psi, tri);
 }
 template <typename T, bool WANT_PSI>
 B2_HD void lgamma_digamma(T x, T& lg, T& psi) {
@@ -390,27 +405,54 @@ struct Eval<kBeta, T, GRAD> {
   }
 };
 
+// Value-only terms.  Some densities carry a term that depends on the value alone (Poisson's
+// lgamma(x + 1)); when the value is shared by many rows of parameters -- observations scored
+// against [particles, ...] rates -- the vector kernel evaluates it once per column and reuses it
+// for every row.  ValueAux<FAM, T, GRAD>::kHas marks such families; make(x) computes the term,
+// Eval::run_aux consumes it.
+template <int FAM, typename T, bool GRAD>
+struct ValueAux {
+  static constexpr bool kHas = false;
+  struct type {};
+  static B2_HD type make(T) { return type{}; }
+};
+
 // Poisson(rate): torch/distributions/poisson.py:75-79   xlogy(x, rate) - rate - lgamma(x + 1)
 template <typename T, bool GRAD>
-struct Eval<kPoisson, T, GRAD> {
-  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
-    const T rate = p[0];
+struct ValueAux<kPoisson, T, GRAD> {
+  static constexpr bool kHas = true;
+  struct type {
     T lgx, psx;
-    lgamma_digamma<T, GRAD>(x + (T)1, lgx, psx);
+  };
+  static B2_HD type make(T x) {
+    type a;
+    lgamma_digamma<T, GRAD>(x + (T)1, a.lgx, a.psx);
+    return a;
+  }
+};
+
+template <typename T, bool GRAD>
+struct Eval<kPoisson, T, GRAD> {
+  using Aux = typename ValueAux<kPoisson, T, GRAD>::type;
+  static B2_HD void run_aux(T x, const Aux& ax, const T* p, ElemOut<T>& o) {
+    const T rate = p[0];
     if (sizeof(T) == 4) {
       const T lr = fast_log(rate);
-      o.lp = ((x == (T)0) ? (T)0 : x * lr) - rate - lgx;
+      o.lp = ((x == (T)0) ? (T)0 : x * lr) - rate - ax.lgx;
       if (GRAD) {
-        o.dx = lr - psx;
+        o.dx = lr - ax.psx;
         o.dp[0] = x * fast_rcp(rate) - (T)1;
       }
     } else {
-      o.lp = xlogy(x, rate) - rate - lgx;
+      o.lp = xlogy(x, rate) - rate - ax.lgx;
       if (GRAD) {
-        o.dx = b2_log(rate) - psx;
+        o.dx = b2_log(rate) - ax.psx;
         o.dp[0] = x / rate - (T)1;
       }
     }
+  }
+  static B2_HD void run(T x, const T* p, ElemOut<T>& o) {
+    run_aux(x, ValueAux<kPoisson, T, GRAD>::make(x), p, o);
   }
 };
 
@@ -590,6 +632,24 @@ template <typename T, bool GRAD>
 struct Eval<kKLGammaGamma, T, GRAD> {
   static B2_HD void run(T, const T* p, ElemOut<T>& o) {
     const T ap = p[0], bp = p[1], aq = p[2], bq = p[3];
+    if (sizeof(T) == 4) {
+      // fp32: shared shift-and-Stirling evaluation of lgamma / digamma / trigamma, SFU log and
+      // reciprocal (the libdevice routes made this kernel issue-bound, like Gamma / Beta)
+      float lga, psia, tria = 0.f, lgq, psiq = 0.f, unused;
+      lgamma_polygamma_f32<true, GRAD>((float)ap, lga, psia, tria);
+      lgamma_polygamma_f32<GRAD, false>((float)aq, lgq, psiq, unused);
+      const T lratio = fast_log(bp) - fast_log(bq);
+      const T inv_bp = fast_rcp(bp);
+      o.lp = aq * lratio + ((T)lgq - (T)lga) + (ap - aq) * (T)psia + (bq - bp) * (ap * inv_bp);
+      if (GRAD) {
+        o.dx = (T)0;
+        o.dp[0] = (ap - aq) * (T)tria + (bq - bp) * inv_bp;
+        o.dp[1] = (aq - ap * bq * inv_bp) * inv_bp;
+        o.dp[2] = lratio + (T)psiq - (T)psia;
+        o.dp[3] = ap * inv_bp - aq * fast_rcp(bq);
+      }
+      return;
+    }
     const T t1 = aq * b2_log(bp / bq);
     const T t2 = b2_lgamma(aq) - b2_lgamma(ap);
     const T psi = digamma(ap);

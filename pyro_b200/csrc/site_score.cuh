@@ -103,13 +103,22 @@ struct VecBody {
   bool u_vec, m_vec;
   // operand registers (invariant ones persist across rows)
   Pack<T> xv[NVEC], pv[NVEC][NP];
+  // value-only term of a row-invariant value (b2_math.cuh ValueAux): once per column, not per row
+  using VA = ValueAux<FAM, T, GRAD>;
+  typename VA::type xa[VA::kHas ? NVEC : 1][VA::kHas ? V : 1];
 
   __device__ __forceinline__ void load_invariant(const T* xbase, const T* const (&pbase)[NP],
                                                  int64_t cv, int64_t cstep) {
 #pragma unroll
     for (int u = 0; u < NVEC; ++u) {
       const int64_t c = (cv + u * cstep) * V;
-      if (HASV && x_vec && x_inv) xv[u] = ld_keep(xbase + c);
+      if (HASV && x_vec && x_inv) {
+        xv[u] = ld_keep(xbase + c);
+        if (VA::kHas) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) xa[VA::kHas ? u : 0][VA::kHas ? j : 0] = VA::make(xv[u].v[j]);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < NP; ++k)
         if (p_vec[k] && p_inv[k]) pv[u][k] = ld_keep(pbase[k] + c);
@@ -147,7 +156,12 @@ struct VecBody {
         for (int k = 0; k < NP; ++k) pl[k] = p_vec[k] ? pv[u][k].v[j] : ps[k];
         const T xe = HASV ? (x_vec ? xv[u].v[j] : xs) : (T)0;
         ElemOut<T> o;
-        Eval<FAM, T, GRAD>::run(xe, pl, o);
+        if constexpr (VA::kHas) {
+          if (x_vec && x_inv) Eval<FAM, T, GRAD>::run_aux(xe, xa[u][j], pl, o);
+          else Eval<FAM, T, GRAD>::run(xe, pl, o);
+        } else {
+          Eval<FAM, T, GRAD>::run(xe, pl, o);
+        }
         T slp = o.lp * scale;
         T f = f0;
         if (MASKUP) {

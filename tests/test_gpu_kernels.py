@@ -136,15 +136,16 @@ def test_fused_sum_path_scale_mask_weight(site_kernels, key, dtype, tol, gtol):
         _close(a, b, gtol)
 
 
-def test_kl_kernels(site_kernels):
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-12, 1e-7), (torch.float32, 2e-5, 3e-4)])
+def test_kl_kernels(site_kernels, dtype, tol, gtol):
     g = load_npz("kl.npz")
     for name, cls in (("normal", dist.Normal), ("gamma", dist.Gamma)):
-        ps = [torch.as_tensor(g["%s.p%d" % (name, i)]).to(DEV).requires_grad_(True) for i in range(4)]
+        ps = [torch.as_tensor(g["%s.p%d" % (name, i)]).to(DEV, dtype).requires_grad_(True) for i in range(4)]
         kl = dist.kl_divergence(cls(ps[0], ps[1]), cls(ps[2], ps[3]))
-        _close(kl, g[name + ".kl"], 1e-12)
+        _close(kl, g[name + ".kl"], tol)
         grads = torch.autograd.grad(kl.sum(), ps)
         for k in range(4):
-            _close(grads[k], g["%s.dp%d" % (name, k)], 1e-7)
+            _close(grads[k], g["%s.dp%d" % (name, k)], gtol)
 
 
 @pytest.mark.parametrize("shape,dst_shape", [((7, 5, 3), (5, 3)), ((7, 5, 3), (7, 1, 3)), ((6, 4), (1, 4)),

@@ -47,6 +47,20 @@ def test_kl_functors():
             assert np.allclose(dp[k], g["%s.dp%d" % (name, k)], atol=1e-7, rtol=1e-7)
 
 
+def test_kl_functors_fp32():
+    """fp32 KL kernels (fast lgamma / digamma / trigamma, SFU log and reciprocal on the device):
+    value within 2e-5 * max(1, |kl|) of the fp64 reference, gradients within 3e-4."""
+    g = load_npz("kl.npz")
+    for name, fam in (("normal", 12), ("gamma", 13)):
+        ps = [g["%s.p%d" % (name, i)] for i in range(4)]
+        lp, _, dp = H.eval_family(fam, None, ps, np.float32)
+        ref = g[name + ".kl"]
+        assert np.all(np.abs(lp - ref) <= 2e-5 * np.maximum(1, np.abs(ref)))
+        for k in range(4):
+            r = g["%s.dp%d" % (name, k)]
+            assert np.all(np.abs(dp[k] - r) <= 3e-4 * np.maximum(1, np.abs(r))), (name, k)
+
+
 def test_fused_normal_draw_functors():
     """Families 14 / 15 (include/pyro_b200.h): the fused draw reproduces the reference's
     rsample (normal.py:82-85) and log_prob (normal.py:87-102) on the golden Normal fixture's
