@@ -51,7 +51,7 @@ struct SiteArgs {
 
 constexpr int kSiteGen = 0, kSiteVec = 1, kSiteSmall = 2;
 constexpr int64_t kSmallN = B2_SITE_SMALL_N;  // sites up to this many elements take the one-CTA kernel
-constexpr int kSmallThreads = 512;
+constexpr int kSmallThreads = 1024;
 static_assert((1 + B2_MAX_PARAMS) * kSmallN * sizeof(double) <= sizeof(double) * kMaxRed * kMaxPartialBlocks,
               "mode-3 slabs must fit in the partials region of the reduce workspace");
 
