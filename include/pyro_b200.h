@@ -322,6 +322,48 @@ int b2_nuts_leaf_vector(const void* z, const void* r, const void* g, const void*
                         int idx_max, int nblk, void* dots, int64_t C, int64_t D, int dtype,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * b2_nuts_leaf_hier -- lockstep iterative NUTS, one new leaf for every still-active chain, for the
+ * B2_MODEL_HIER_NORMAL model class (BASELINE configs 1 / 4) at any J: TWO launches replace the
+ * five launches + ~20 [C]-sized tensor ops of the generic leaf (b2_leapfrog_half_kick_drift,
+ * b2_potential_grad, b2_leapfrog_half_kick, b2_nuts_leaf_vector and the scalar glue):
+ *   pass 1, over [C, D]: the whole velocity-Verlet step (pyro/ops/integrator.py:45-65) with the
+ *     local gradients recomputed from the global coordinates instead of stored; whitened momentum,
+ *     running subtree sum, checkpoint store (store_slot >= 0, even leaf) or the 2*nblk U-turn dot
+ *     products (odd leaf; checkpoint slots idx_max, idx_max-1, ...); proposal copy zs <- z for
+ *     chains whose PREVIOUS leaf was drawn (take[c], written by the previous call);
+ *   pass 2, one warp per chain: potential energy and global gradients at the new point, second
+ *     half kick of the global coordinates, then the scalar tree logic of pyro/infer/mcmc/nuts.py:
+ *     197-248 for one leaf: energy (NaN -> inf), divergence (delta > max_delta_energy), accept-prob
+ *     sum, progressive multinomial draw (Philox stream (seed, chain), counter rng_counter[c]),
+ *     U-turn flags -> done[c].
+ * State is advanced IN PLACE.  After the last leaf of a subtree the caller copies z -> zs for
+ * chains with take[c] still set.  Chains with done[c] != 0 are untouched.
+ */
+typedef struct {
+  void *z, *r;        /* [C, D] position / momentum of the growing end, D = J + 2 */
+  const void* minv;   /* diagonal inverse mass, chain stride minv_chain_stride (0 = shared) */
+  int64_t minv_chain_stride;
+  void *rsub;         /* [C, D] whitened momentum sum of the subtree under construction */
+  void *zs;           /* [C, D] proposal of the subtree */
+  void *rck, *sck;    /* [slots, C, D] checkpoints: first-leaf momentum / running sum */
+  const void* eps;    /* [C] signed step size */
+  void *gsc, *gsc_s;  /* [C, 2] dU/d(mu, log tau) at z / at the proposal */
+  void *U, *Us;       /* [C] potential at z / at the proposal */
+  const void* energy0; /* [C] initial energy of the transition */
+  void *logw_sub, *sum_accept, *num_prop; /* [C] */
+  uint8_t *done, *diverged, *take;        /* [C] */
+  int32_t* num_leapfrogs;                 /* [C] nullable: += 1 per active chain */
+  uint64_t* rng_counter;                  /* [C] */
+  uint64_t seed;
+  double max_delta_energy;
+  int64_t C;
+} b2_nuts_lockstep;
+
+int b2_nuts_leaf_hier(const b2_model* model, const b2_nuts_lockstep* st, int leaf, int store_slot,
+                      int idx_max, int nblk, void* workspace, size_t workspace_bytes, void* stream);
+size_t b2_nuts_leaf_hier_workspace(int64_t C, int64_t J);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 const char* b2_last_error(int code);
 int b2_version(void);

@@ -605,6 +605,288 @@ __global__ void nuts_dots_finish_kernel(const double* __restrict__ partials, int
   dots[i] = (T)s;
 }
 
+
+// ---- lockstep NUTS, hierarchical-Normal model class: ONE pass per leaf ------------------------------
+// The generic lockstep leaf costs five launches that move ~65 B per chain-element (kick_drift,
+// potential, kick, leaf_vector + finish) plus ~20 [C]-sized torch ops.  For the model class of
+// BASELINE configs 1/4 the latent vector is [mu, log tau | eta_1..J] and, given the two global
+// coordinates, dU/d eta_j is local:  g_j = eta_j - tau * (y_j - mu - tau*eta_j) / sigma_j^2.
+// So one kernel can take the whole velocity-Verlet step (pyro/ops/integrator.py:45-65) for the
+// local coordinates WITHOUT a stored gradient vector -- the old gradient is recomputed from the old
+// (mu, tau), the new one from the drifted (mu', tau') that every thread derives from six scalars --
+// and, in the same pass, everything the tree needs from the new leaf (nuts.py:197-248,285-342
+// restated iteratively, see nuts_core.cuh): whitened momentum, running sum, checkpoint store or
+// the U-turn dot products, and the proposal copy of the PREVIOUS leaf (its value is read here
+// anyway).  Traffic: read eta, r, minv, rsub (+ y, sigma from L2), write eta, r, rsub, plus the
+// checkpoint row(s): ~40 B per chain-element.  A warp-per-chain finish kernel then assembles U,
+// the two global gradients, finishes the global coordinates' kick, and runs the per-chain scalar
+// logic of the tree (energy, divergence, multinomial draw with Philox, U-turn flags).
+struct LeafHierArgs {
+  void *z, *r, *rsub, *zs, *rck, *sck;  // [C, D] / [slots, C, D]
+  const void *minv, *y, *sigma;         // [C, D] (chain stride minv_cs), [J], [J]
+  const void* eps;                      // [C] signed step
+  void *gsc, *gsc_s;                    // [C, 2] global-coordinate gradients at z / at the proposal
+  void *U, *Us, *logw_sub, *sum_accept, *num_prop;  // [C]
+  const void* energy0;                  // [C]
+  uint8_t *done, *diverged, *take;      // [C]
+  int32_t* nleaf;                       // [C] leapfrogs taken (nullable)
+  uint64_t* rng_counter;                // [C]
+  double* partials;
+  int64_t C, J, minv_cs, ck_stride;
+  uint64_t seed;
+  double s_mu, s_tau, max_delta;
+  int leaf, store_slot, idx_max, nblk, nb;
+};
+
+constexpr int kLeafHierBase = 4;  // a0 (U part), a1 (sum res), a2 (sum res*eta), ke
+
+// NBMAX: compile-time bound on the U-turn blocks checked at this leaf (0 = even leaf; 2 covers 75%
+// of the odd leaves; kNutsMaxBlocks the rest) -- keeps the dot accumulators in registers without
+// paying 24 of them on every leaf.
+template <typename T, int NBMAX>
+__global__ void __launch_bounds__(256) nuts_leaf_hier_kernel(const LeafHierArgs a) {
+  __shared__ double smem[(kLeafHierBase + 2 * kNutsMaxBlocks) * 8];
+  const int64_t J = a.J, D = J + 2;
+  const int NV = kLeafHierBase + 2 * a.nblk;
+  const T* __restrict__ y = reinterpret_cast<const T*>(a.y);
+  const T* __restrict__ sigma = reinterpret_cast<const T*>(a.sigma);
+  for (int64_t c = blockIdx.y; c < a.C; c += gridDim.y) {
+    if (a.done[c]) continue;  // uniform over the CTA
+    T* __restrict__ zc = reinterpret_cast<T*>(a.z) + c * D;
+    T* __restrict__ rc = reinterpret_cast<T*>(a.r) + c * D;
+    T* __restrict__ rs = reinterpret_cast<T*>(a.rsub) + c * D;
+    T* __restrict__ zsc = reinterpret_cast<T*>(a.zs) + c * D;
+    const T* __restrict__ mi = reinterpret_cast<const T*>(a.minv) + c * a.minv_cs;
+    const T* gsc = reinterpret_cast<const T*>(a.gsc) + c * 2;
+    const bool tk = a.take[c] != 0;  // the previous leaf was drawn as the proposal
+    const T e = reinterpret_cast<const T*>(a.eps)[c];
+    const T he = (T)0.5 * e;
+    // global coordinates: every thread repeats the (cheap) scalar update; the finish kernel stores it
+    const T mu = zc[0], lt = zc[1];
+    const T mu2 = mu + e * mi[0] * (rc[0] - he * gsc[0]);
+    const T lt2 = lt + e * mi[1] * (rc[1] - he * gsc[1]);
+    const T tau = b2_exp(lt), tau2 = b2_exp(lt2);
+    // the four energy/gradient sums in fp64; the U-turn dot products in T per thread (each thread
+    // owns ~100 elements of a chain) and fp64 from the warp reduction on -- all in registers
+    double acc[kLeafHierBase];
+    T dacc[NBMAX > 0 ? 2 * NBMAX : 1];
+#pragma unroll
+    for (int k = 0; k < kLeafHierBase; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < (NBMAX > 0 ? 2 * NBMAX : 1); ++k) dacc[k] = (T)0;
+    T* ck_r = reinterpret_cast<T*>(a.rck);
+    T* ck_s = reinterpret_cast<T*>(a.sck);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int UN = 2;
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto elem = [&](int64_t jj, T eta, T rj, T mv, T rsv, T yv, T sv) {
+      const T isg = fast_rcp(sv);
+      const T isg2 = isg * isg;
+      const T g0 = eta - tau * ((yv - mu - tau * eta) * isg2);     // dU/d eta_j at z
+      const T rh = rj - he * g0;                                    // half kick
+      const T eta2 = eta + e * mv * rh;                             // drift
+      const T d2 = yv - mu2 - tau2 * eta2;
+      const T res2 = d2 * isg2;
+      const T r2 = rh - he * (eta2 - tau2 * res2);                  // half kick with the new gradient
+      if (tk) zsc[2 + jj] = eta;
+      zc[2 + jj] = eta2;
+      rc[2 + jj] = r2;
+      const T ru = r2 * b2_sqrt(mv);
+      const T rsn = rsv + ru;
+      rs[2 + jj] = rsn;
+      T t[kLeafHierBase];
+      t[0] = (T)0.5 * eta2 * eta2 + (T)0.5 * d2 * res2 + fast_log(sv);
+      t[1] = res2;
+      t[2] = res2 * eta2;
+      t[3] = mv * r2 * r2;
+#pragma unroll
+      for (int k = 0; k < kLeafHierBase; ++k) acc[k] += (double)t[k];
+      const int64_t i = c * D + 2 + jj;
+      if (NBMAX == 0) {
+        ck_r[(int64_t)a.store_slot * a.ck_stride + i] = ru;
+        ck_s[(int64_t)a.store_slot * a.ck_stride + i] = rsn;
+      } else {
+#pragma unroll
+        for (int b = 0; b < NBMAX; ++b) {
+          if (b < a.nblk) {
+            const int64_t o = (int64_t)(a.idx_max - b) * a.ck_stride + i;
+            const T rk = ck_r[o];
+            const T rho = (rsn - ck_s[o] + rk) - (T)0.5 * (rk + ru);
+            dacc[2 * b] += rk * rho;
+            dacc[2 * b + 1] += ru * rho;
+          }
+        }
+      }
+    };
+    for (; j + (UN - 1) * stride < J; j += UN * stride) {
+      T ev[UN], rv[UN], mv[UN], sv[UN], yv[UN], gv[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int64_t jj = j + u * stride;
+        ev[u] = zc[2 + jj];
+        rv[u] = rc[2 + jj];
+        mv[u] = mi[2 + jj];
+        sv[u] = rs[2 + jj];
+        yv[u] = __ldg(y + jj);
+        gv[u] = __ldg(sigma + jj);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) elem(j + u * stride, ev[u], rv[u], mv[u], sv[u], yv[u], gv[u]);
+    }
+    for (; j < J; j += stride)
+      elem(j, zc[2 + j], rc[2 + j], mi[2 + j], rs[2 + j], __ldg(y + j), __ldg(sigma + j));
+    // CTA reduction of the NV sums (fixed order), one partial row per (chain, CTA)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kLeafHierBase; ++k) {
+      const double w = warp_sum(acc[k]);
+      if (lane == 0) smem[k * 8 + warp] = w;
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * NBMAX; ++k) {
+      if (k < 2 * a.nblk) {
+        const double w = warp_sum((double)dacc[k]);
+        if (lane == 0) smem[(kLeafHierBase + k) * 8 + warp] = w;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int k = 0; k < NV; ++k) {
+        double w = (lane < 8) ? smem[k * 8 + lane] : 0.0;
+        w = warp_sum(w);
+        if (lane == 0) a.partials[((size_t)c * gridDim.x + blockIdx.x) * NV + k] = w;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+B2_HD double logaddexp_d(double x, double y) {
+  const double m = x > y ? x : y;
+  if (m == -INFINITY) return -INFINITY;
+  return m + log(exp(x - m) + exp(y - m));
+}
+
+// one warp per chain: sum the CTA partials, finish the global coordinates, run the scalar tree logic
+template <typename T>
+__global__ void __launch_bounds__(128) nuts_leaf_hier_finish_kernel(const LeafHierArgs a) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= a.C) return;
+  if (a.done[c]) return;
+  const int NV = kLeafHierBase + 2 * a.nblk;
+  double v[kLeafHierBase + 2 * kNutsMaxBlocks];
+  for (int k = 0; k < NV; ++k) {
+    double s = 0.0;
+    for (int b = lane; b < a.nb; b += 32) s += a.partials[((size_t)c * a.nb + b) * NV + k];
+    v[k] = warp_sum(s);
+  }
+  if (lane != 0) return;
+  const int64_t J = a.J, D = J + 2;
+  T* zc = reinterpret_cast<T*>(a.z) + c * D;
+  T* rc = reinterpret_cast<T*>(a.r) + c * D;
+  T* rs = reinterpret_cast<T*>(a.rsub) + c * D;
+  T* zsc = reinterpret_cast<T*>(a.zs) + c * D;
+  const T* mi = reinterpret_cast<const T*>(a.minv) + c * a.minv_cs;
+  T* gsc = reinterpret_cast<T*>(a.gsc) + c * 2;
+  const bool tk = a.take[c] != 0;
+  const T e = reinterpret_cast<const T*>(a.eps)[c];
+  const T he = (T)0.5 * e;
+  // global coordinates (same arithmetic, in T, as the vector kernel used)
+  const T mu = zc[0], lt = zc[1];
+  const T rh0 = rc[0] - he * gsc[0], rh1 = rc[1] - he * gsc[1];
+  const T mu2 = mu + e * mi[0] * rh0;
+  const T lt2 = lt + e * mi[1] * rh1;
+  // potential and global gradients at the new point (as hier_normal_finish_kernel)
+  const double mud = (double)mu2, t = (double)lt2;
+  const double tau = exp(t);
+  const double u = tau / a.s_tau, u2 = u * u;
+  const double c0 = 0.91893853320467274178;  // log sqrt(2 pi)
+  double Uv = 0.5 * mud * mud / (a.s_mu * a.s_mu) + log(a.s_mu) + c0;
+  Uv += 1.14472988584940017414 + log(a.s_tau) - 0.69314718055994530942 + log1p(u2) - t;
+  Uv += v[0] + 2.0 * c0 * (double)J;
+  const T g0 = (T)(mud / (a.s_mu * a.s_mu) - v[1]);
+  const T g1 = (T)(2.0 * u2 / (1.0 + u2) - 1.0 - tau * v[2]);
+  const T r0 = rh0 - he * g0, r1 = rh1 - he * g1;
+  if (tk) {
+    zsc[0] = mu;
+    zsc[1] = lt;
+  }
+  zc[0] = mu2; zc[1] = lt2;
+  rc[0] = r0; rc[1] = r1;
+  gsc[0] = g0; gsc[1] = g1;
+  const double ke = 0.5 * (v[3] + (double)(mi[0] * r0 * r0) + (double)(mi[1] * r1 * r1));
+  // tree vectors of the two global coordinates
+  bool turn = false;
+  {
+    const T ru[2] = {r0 * b2_sqrt(mi[0]), r1 * b2_sqrt(mi[1])};
+    T rsn[2];
+    for (int d = 0; d < 2; ++d) {
+      rsn[d] = rs[d] + ru[d];
+      rs[d] = rsn[d];
+    }
+    T* ck_r = reinterpret_cast<T*>(a.rck);
+    T* ck_s = reinterpret_cast<T*>(a.sck);
+    if (a.store_slot >= 0) {
+      for (int d = 0; d < 2; ++d) {
+        ck_r[(int64_t)a.store_slot * a.ck_stride + c * D + d] = ru[d];
+        ck_s[(int64_t)a.store_slot * a.ck_stride + c * D + d] = rsn[d];
+      }
+    } else {
+      for (int b = 0; b < a.nblk; ++b) {
+        double d0 = v[kLeafHierBase + 2 * b], d1 = v[kLeafHierBase + 2 * b + 1];
+        for (int d = 0; d < 2; ++d) {
+          const int64_t o = (int64_t)(a.idx_max - b) * a.ck_stride + c * D + d;
+          const T rk = ck_r[o];
+          const T rho = (rsn[d] - ck_s[o] + rk) - (T)0.5 * (rk + ru[d]);
+          d0 += (double)(rk * rho);
+          d1 += (double)(ru[d] * rho);
+        }
+        // the comparison happens in T, like the torch glue of the generic path ((T)dots <= 0)
+        turn = turn || ((T)d0 <= (T)0) || ((T)d1 <= (T)0);
+      }
+    }
+  }
+  // ---- scalar tree logic (nuts.py:197-248 for one new leaf) ----------------------------------------
+  T* Uarr = reinterpret_cast<T*>(a.U);
+  const T Unew = (T)Uv;
+  Uarr[c] = Unew;
+  T energy = Unew + (T)ke;
+  if (energy != energy) energy = b2_inf<T>();
+  const T delta = energy - reinterpret_cast<const T*>(a.energy0)[c];
+  const bool div_now = delta > (T)a.max_delta;
+  T accp = b2_exp(-delta);
+  accp = accp > (T)1 ? (T)1 : accp;
+  reinterpret_cast<T*>(a.sum_accept)[c] += accp;
+  reinterpret_cast<T*>(a.num_prop)[c] += (T)1;
+  if (a.nleaf) a.nleaf[c] += 1;
+  const T w_leaf = -delta;
+  T* lws = reinterpret_cast<T*>(a.logw_sub);
+  bool take;
+  T nw;
+  if (a.leaf == 0) {
+    nw = w_leaf;
+    take = true;
+  } else {
+    nw = (T)logaddexp_d((double)lws[c], (double)w_leaf);
+    Philox rng;
+    rng.init(a.seed, (uint64_t)c, a.rng_counter[c]);
+    const T un = rng.uniform<T>();
+    a.rng_counter[c] = rng.counter() + 1;
+    take = un < b2_exp(w_leaf - nw);
+  }
+  lws[c] = nw;
+  if (take) {
+    reinterpret_cast<T*>(a.Us)[c] = Unew;
+    T* gs = reinterpret_cast<T*>(a.gsc_s) + c * 2;
+    gs[0] = g0;
+    gs[1] = g1;
+  }
+  a.take[c] = take ? 1 : 0;
+  if (div_now) a.diverged[c] = 1;
+  if (div_now || (turn && !div_now)) a.done[c] = 1;
+}
+
 }  // namespace b2
 extern "C" int b2_nuts_leaf_vector(const void* z, const void* r, const void* g, const void* minv,
                                    int64_t minv_chain_stride, const uint8_t* active,
@@ -647,3 +929,57 @@ extern "C" int b2_nuts_leaf_vector(const void* z, const void* r, const void* g, 
   count_launch(nblk > 0 ? 2 : 1);
   return check_launch();
 }
+
+extern "C" size_t b2_nuts_leaf_hier_workspace(int64_t C, int64_t J) {
+  return (size_t)C * b2::bx_for(J, C) * (b2::kLeafHierBase + 2 * b2::kNutsMaxBlocks) * sizeof(double);
+}
+
+extern "C" int b2_nuts_leaf_hier(const b2_model* model, const b2_nuts_lockstep* st, int leaf,
+                                 int store_slot, int idx_max, int nblk, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  using namespace b2;
+  if (!model || !st) return B2_ERR_NULL;
+  if (model->model != B2_MODEL_HIER_NORMAL) return B2_ERR_BAD_FAMILY;
+  if (model->dtype != B2_F32 && model->dtype != B2_F64) return B2_ERR_BAD_DTYPE;
+  if (!st->z || !st->r || !st->rsub || !st->zs || !st->rck || !st->sck || !st->minv || !st->eps ||
+      !st->gsc || !st->gsc_s || !st->U || !st->Us || !st->energy0 || !st->logw_sub ||
+      !st->sum_accept || !st->num_prop || !st->done || !st->diverged || !st->take || !st->rng_counter)
+    return B2_ERR_NULL;
+  const int64_t C = st->C, J = model->J;
+  if (C <= 0 || J <= 0) return B2_OK;
+  if (C > 65535) return B2_ERR_TOO_LARGE;
+  if (nblk < 0 || nblk > kNutsMaxBlocks) return B2_ERR_BAD_SHAPE;
+  if (!workspace || workspace_bytes < b2_nuts_leaf_hier_workspace(C, J)) return B2_ERR_WORKSPACE;
+  LeafHierArgs a;
+  a.z = st->z; a.r = st->r; a.rsub = st->rsub; a.zs = st->zs; a.rck = st->rck; a.sck = st->sck;
+  a.minv = st->minv; a.y = model->data0; a.sigma = model->data1; a.eps = st->eps;
+  a.gsc = st->gsc; a.gsc_s = st->gsc_s; a.U = st->U; a.Us = st->Us; a.energy0 = st->energy0;
+  a.logw_sub = st->logw_sub; a.sum_accept = st->sum_accept; a.num_prop = st->num_prop;
+  a.done = st->done; a.diverged = st->diverged; a.take = st->take; a.nleaf = st->num_leapfrogs;
+  a.rng_counter = st->rng_counter;
+  a.partials = reinterpret_cast<double*>(workspace);
+  a.C = C; a.J = J; a.minv_cs = st->minv_chain_stride; a.ck_stride = C * (J + 2);
+  a.seed = st->seed; a.s_mu = model->hyper[0]; a.s_tau = model->hyper[1];
+  a.max_delta = st->max_delta_energy;
+  a.leaf = leaf; a.store_slot = store_slot; a.idx_max = idx_max; a.nblk = nblk;
+  const unsigned bx = bx_for(J, C);
+  a.nb = (int)bx;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(bx, (unsigned)C, 1);
+  const unsigned fin_blocks = (unsigned)((C * 32 + 127) / 128);
+  if ((store_slot >= 0) != (nblk == 0)) return B2_ERR_BAD_SHAPE;  // even leaf <=> no blocks end here
+  if (model->dtype == B2_F32) {
+    if (nblk == 0) nuts_leaf_hier_kernel<float, 0><<<grid, 256, 0, s>>>(a);
+    else if (nblk <= 2) nuts_leaf_hier_kernel<float, 2><<<grid, 256, 0, s>>>(a);
+    else nuts_leaf_hier_kernel<float, kNutsMaxBlocks><<<grid, 256, 0, s>>>(a);
+    nuts_leaf_hier_finish_kernel<float><<<fin_blocks, 128, 0, s>>>(a);
+  } else {
+    if (nblk == 0) nuts_leaf_hier_kernel<double, 0><<<grid, 256, 0, s>>>(a);
+    else if (nblk <= 2) nuts_leaf_hier_kernel<double, 2><<<grid, 256, 0, s>>>(a);
+    else nuts_leaf_hier_kernel<double, kNutsMaxBlocks><<<grid, 256, 0, s>>>(a);
+    nuts_leaf_hier_finish_kernel<double><<<fin_blocks, 128, 0, s>>>(a);
+  }
+  count_launch(2);
+  return check_launch();
+}
+

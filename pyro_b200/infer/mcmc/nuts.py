@@ -26,7 +26,7 @@ import torch
 
 from ... import _native as N
 from .adaptation import WarmupAdapter
-from .potential import NativePotential, TracePotential
+from .potential import HierNormalPotential, NativePotential, TracePotential
 
 _MAX_SLICED_ENERGY = 1000.0
 
@@ -259,7 +259,7 @@ class NUTS(HMC):
                  adapt_mass_matrix=True, full_mass=False, use_multinomial_sampling=True,
                  transforms=None, max_plate_nesting=None, jit_compile=False, jit_options=None,
                  ignore_jit_warnings=False, target_accept_prob=0.8, max_tree_depth=10,
-                 init_strategy=None, native_small=True):
+                 init_strategy=None, native_small=True, fused_leaf=True):
         super().__init__(model, potential_fn, step_size, adapt_step_size=adapt_step_size,
                          adapt_mass_matrix=adapt_mass_matrix, full_mass=full_mass,
                          transforms=transforms, max_plate_nesting=max_plate_nesting,
@@ -269,13 +269,17 @@ class NUTS(HMC):
                                       "(multinomial) is")
         self._max_tree_depth = max_tree_depth
         self._native_small = native_small
+        self._fused_leaf = fused_leaf    # model-class leaf kernel (b2_nuts_leaf_hier) when available
         self._rng_counter = None
 
     def setup(self, warmup_steps, num_chains, *args, **kwargs):
         super().setup(warmup_steps, num_chains, *args, **kwargs)
         self._use_native = (self._native_small and isinstance(self.potential, NativePotential)
                             and self.D <= N.NUTS_SMALL_MAX_D)
-        if self._use_native:
+        self._use_fused_hier = (not self._use_native and self._fused_leaf
+                                and isinstance(self.potential, HierNormalPotential))
+        self._gsc = None
+        if self._use_native or self._use_fused_hier:
             self._rng_counter = torch.zeros(num_chains, dtype=torch.int64, device=self._z.device)
 
     # ---- native whole-transition path ---------------------------------------------------------------
@@ -311,7 +315,126 @@ class NUTS(HMC):
             self._leap_dev = steps.sum() if self._leap_dev is None else self._leap_dev + steps.sum()
             self._post_transition(acc[0], torch.ones_like(div[0], dtype=torch.bool), div[0] > 0)
             return self._z
+        if self._use_fused_hier:
+            return self._sample_lockstep_hier()
         return self._sample_lockstep()
+
+    # ---- lockstep tree on the fused leaf kernel (hierarchical-Normal model class, any J) -----------------
+    def _leaf_hier(self, st, leaf):
+        """One new leaf for every active chain: b2_nuts_leaf_hier (two launches, no tensor ops)."""
+        idx_max = _popcount(leaf >> 1)
+        even = leaf % 2 == 0
+        nblk = 0 if even else _trailing_ones(leaf)
+        lib = N.lib()
+        dev = self._z.device
+        ws = N.workspace(dev, int(lib.b2_nuts_leaf_hier_workspace(self.C, self.D - 2)), tag="mcmc")
+        N.check(lib.b2_nuts_leaf_hier(ctypes.byref(self.potential._model), ctypes.byref(st["c"]), leaf,
+                                      idx_max if even else -1, idx_max, nblk, ws.data_ptr(), ws.numel(),
+                                      N.stream_ptr(dev)), "b2_nuts_leaf_hier")
+
+    def _lockstep_struct(self, t):
+        c = N.b2_nuts_lockstep()
+        for k in ("z", "r", "minv", "rsub", "zs", "rck", "sck", "eps", "gsc", "gsc_s", "U", "Us", "energy0",
+                  "logw_sub", "sum_accept", "num_prop", "done", "diverged", "take", "num_leapfrogs",
+                  "rng_counter"):
+            setattr(c, k, t[k].data_ptr())
+        c.minv_chain_stride = t["minv"].stride(0)
+        c.seed = self._seed
+        c.max_delta_energy = _MAX_SLICED_ENERGY
+        c.C = self.C
+        return c
+
+    def _sample_lockstep_hier(self):
+        """Same transition as ``_sample_lockstep`` (nuts.py:367-522 restated iteratively, all active
+        chains sharing (depth, leaf)), but every leaf is ONE call of the fused kernel pair: the
+        leapfrog with recomputed local gradients, the tree vectors, and the per-chain scalar logic
+        all stay on the device; the host loop only counts leaves.  Per tree end only the two
+        global-coordinate gradients are kept (``gsc``), not a gradient vector."""
+        C, D = self.C, self.D
+        dev, dtype = self._z.device, self._z.dtype
+        eps_abs = self._adapter.step_size
+        minv = self._adapter.inverse_mass.contiguous()
+        s = minv.sqrt()
+        z0, U0 = self._z, self._U
+        gsc0 = self._gsc if self._gsc is not None else self._g[:, :2].contiguous()
+        ru = self._randn(C, D)
+        r = ru / s
+        energy0 = U0 + 0.5 * (ru * ru).sum(-1)
+        zl, rl, gl, rul = z0, r, gsc0, ru          # never written in place: torch.where makes the work copies
+        zr, rr, gr, rur = z0, r, gsc0, ru
+        zp, gp, Up = z0, gsc0, U0
+        rsum = ru.clone()
+        maxd = self._max_tree_depth
+        u8 = dict(dtype=torch.uint8, device=dev)
+        t = {
+            "minv": minv, "energy0": energy0.contiguous(),
+            "rck": torch.empty(maxd + 1, C, D, dtype=dtype, device=dev),
+            "sck": torch.empty(maxd + 1, C, D, dtype=dtype, device=dev),
+            "sum_accept": torch.zeros(C, dtype=dtype, device=dev),
+            "num_prop": torch.zeros(C, dtype=dtype, device=dev),
+            "done": torch.zeros(C, **u8), "diverged": torch.zeros(C, **u8), "take": torch.zeros(C, **u8),
+            "num_leapfrogs": torch.zeros(C, dtype=torch.int32, device=dev),
+            "rng_counter": self._rng_counter,
+            "gsc_s": torch.empty(C, 2, dtype=dtype, device=dev),
+            "U": torch.empty(C, dtype=dtype, device=dev), "Us": torch.empty(C, dtype=dtype, device=dev),
+            "zs": torch.empty(C, D, dtype=dtype, device=dev),
+        }
+        logw_tree = torch.zeros(C, dtype=dtype, device=dev)
+        accepted = torch.zeros(C, dtype=torch.bool, device=dev)
+        depth_reached = torch.zeros(C, dtype=torch.int32, device=dev)
+        done = t["done"]
+        for depth in range(maxd):
+            if depth > 0 and bool(done.all()):
+                break
+            go_right = self._rand(C) < 0.5
+            grm = go_right[:, None]
+            t["z"] = torch.where(grm, zr, zl).contiguous()
+            t["r"] = torch.where(grm, rr, rl).contiguous()
+            t["gsc"] = torch.where(grm, gr, gl).contiguous()
+            t["eps"] = torch.where(go_right, eps_abs, -eps_abs).contiguous()
+            t["rsub"] = torch.zeros(C, D, dtype=dtype, device=dev)
+            t["logw_sub"] = torch.full((C,), float("-inf"), dtype=dtype, device=dev)
+            t["take"].zero_()
+            st = {"c": self._lockstep_struct(t), "t": t}
+            nleaves = 1 << depth
+            for leaf in range(nleaves):
+                self._leaf_hier(st, leaf)
+                if (leaf & 15) == 15 and leaf + 1 < nleaves and bool(done.all()):
+                    break
+            z, rcur, g = t["z"], t["r"], t["gsc"]
+            # the last drawn leaf of each chain has not been copied yet (the copy rides on the NEXT leaf)
+            zs = torch.where(t["take"].bool()[:, None], z, t["zs"])
+            # ---- merge the finished subtree (chains cut short are already `done`) ---------------
+            active = ~done.bool()
+            am = active[:, None]
+            right = am & grm
+            left = am & ~grm
+            ru_c = rcur * s
+            zr = torch.where(right, z, zr); rr = torch.where(right, rcur, rr)
+            gr = torch.where(right, g, gr); rur = torch.where(right, ru_c, rur)
+            zl = torch.where(left, z, zl); rl = torch.where(left, rcur, rl)
+            gl = torch.where(left, g, gl); rul = torch.where(left, ru_c, rul)
+            depth_reached = depth_reached + active.to(torch.int32)
+            logw_sub = t["logw_sub"]
+            acc_tree = active & (self._rand(C) < torch.exp(logw_sub - logw_tree))
+            accepted = accepted | acc_tree
+            at = acc_tree[:, None]
+            zp = torch.where(at, zs, zp)
+            gp = torch.where(at, t["gsc_s"], gp)
+            Up = torch.where(acc_tree, t["Us"], Up)
+            rsum = rsum + torch.where(am, t["rsub"], torch.zeros_like(rsum))
+            rho = rsum - 0.5 * (rul + rur)
+            turning_top = ((rul * rho).sum(-1) <= 0) | ((rur * rho).sum(-1) <= 0)
+            logw_tree = torch.where(active & ~turning_top, _logaddexp(logw_tree, logw_sub), logw_tree)
+            done |= (active & turning_top).to(torch.uint8)
+        self._z, self._gsc, self._U = zp, gp, Up
+        self._g = None
+        nl = t["num_leapfrogs"].sum()
+        self._leap_dev = nl if self._leap_dev is None else self._leap_dev + nl
+        accept_prob = t["sum_accept"] / t["num_prop"].clamp(min=1)
+        self._last_depth = depth_reached
+        self._post_transition(accept_prob, accepted, t["diverged"].bool())
+        return self._z
 
     def _leaf_vector(self, z, rcur, g, minv, active8, take8, rsub, zs, gs, rck, sck, leaf):
         """Everything a new leaf needs over the [C, D] state in one fused pass

@@ -105,6 +105,70 @@ def _leaf_vector(self, z, rcur, g, minv, active8, take8, rsub, zs, gs, rck, sck,
     return turn
 
 
+def _leaf_hier(self, st, leaf):
+    """torch stand-in for b2_nuts_leaf_hier (include/pyro_b200.h): one new leaf for every active
+    chain, state advanced in place, scalar tree logic included; the uniform for the multinomial draw
+    comes from the kernel's torch generator instead of Philox."""
+    t = st["t"]
+    done = t["done"].bool()
+    act = ~done
+    am = act[:, None]
+    z, r, minv, eps = t["z"], t["r"], t["minv"], t["eps"]
+    tk = (t["take"].bool() & act)[:, None]
+    t["zs"].copy_(torch.where(tk, z, t["zs"]))
+    _, g_old = self.potential.value_and_grad(z)
+    e = eps[:, None]
+    rh = r - 0.5 * e * g_old
+    z2 = z + e * (minv * rh)
+    U2, g2 = self.potential.value_and_grad(z2)
+    r2 = rh - 0.5 * e * g2
+    ke = 0.5 * (minv * r2 * r2).sum(-1)
+    z.copy_(torch.where(am, z2, z))
+    r.copy_(torch.where(am, r2, r))
+    t["gsc"].copy_(torch.where(am, g2[:, :2], t["gsc"]))
+    t["U"].copy_(torch.where(act, U2, t["U"]))
+    ru = r2 * minv.sqrt()
+    rsub = t["rsub"]
+    rsub.add_(torch.where(am, ru, torch.zeros_like(ru)))
+    idx_max = bin(leaf >> 1).count("1")
+    turn = torch.zeros(z.shape[0], dtype=torch.bool)
+    rck, sck = t["rck"], t["sck"]
+    if leaf % 2 == 0:
+        rck[idx_max] = torch.where(am, ru, rck[idx_max])
+        sck[idx_max] = torch.where(am, rsub, sck[idx_max])
+    else:
+        q, nblk = leaf, 0
+        while q & 1:
+            nblk += 1
+            q >>= 1
+        for k in range(idx_max, idx_max - nblk, -1):
+            rho = (rsub - sck[k] + rck[k]) - 0.5 * (rck[k] + ru)
+            turn = turn | ((rck[k] * rho).sum(-1) <= 0) | ((ru * rho).sum(-1) <= 0)
+    energy = U2 + ke
+    energy = torch.where(torch.isnan(energy), torch.full_like(energy, float("inf")), energy)
+    delta = energy - t["energy0"]
+    div_now = act & (delta > 1000.0)
+    accp = (-delta).exp().clamp(max=1.0)
+    t["sum_accept"].add_(torch.where(act, accp, torch.zeros_like(accp)))
+    t["num_prop"].add_(act.to(accp.dtype))
+    t["num_leapfrogs"].add_(act.to(torch.int32))
+    w_leaf = -delta
+    lws = t["logw_sub"]
+    if leaf == 0:
+        nw, take = w_leaf, act.clone()
+    else:
+        m = torch.maximum(lws, w_leaf)
+        ms = torch.where(torch.isinf(m) & (m < 0), torch.zeros_like(m), m)
+        nw = ms + torch.log(torch.exp(lws - ms) + torch.exp(w_leaf - ms))
+        take = act & (torch.rand(z.shape[0], generator=self._gen, dtype=z.dtype) < torch.exp(w_leaf - nw))
+    lws.copy_(torch.where(act, nw, lws))
+    t["Us"].copy_(torch.where(take, U2, t["Us"]))
+    t["gsc_s"].copy_(torch.where(take[:, None], g2[:, :2], t["gsc_s"]))
+    t["take"].copy_(torch.where(act, take, t["take"].bool()).to(torch.uint8))
+    t["diverged"].copy_((t["diverged"].bool() | div_now).to(torch.uint8))
+    t["done"].copy_((done | div_now | (act & turn & ~div_now)).to(torch.uint8))
+
+
 def _native_value_and_grad(self, z, active=None, out_grad=None):
     from pyro_b200 import _native as N
     if self.model_id == N.MODEL_HIER_NORMAL:
@@ -186,6 +250,8 @@ def enabled():
     nuts.HMC._leapfrog = _leapfrog
     saved_leaf = nuts.NUTS._leaf_vector
     nuts.NUTS._leaf_vector = _leaf_vector
+    saved_leaf_hier = nuts.NUTS._leaf_hier
+    nuts.NUTS._leaf_hier = _leaf_hier
     ops.reduce_to = _reduce_to
     saved_rs = (ops.normal_rsample_score, ops.normal_rsample_backward, N.EMULATE_RSAMPLE)
     saved_comb = ops.elbo_combine
@@ -200,5 +266,6 @@ def enabled():
         ops.elbo_combine = saved_comb
         pdist._BernoulliLinear._fused_sum = saved_glm
         nuts.NUTS._leaf_vector = saved_leaf
+        nuts.NUTS._leaf_hier = saved_leaf_hier
         (ops.site_score, N.require_cuda, optim.ClippedAdam._launch, optim.AdagradRMSProp._launch,
          pot.NativePotential.value_and_grad, nuts.HMC._leapfrog, ops.reduce_to) = saved

@@ -292,6 +292,89 @@ def test_native_nuts_eight_schools_posterior():
     assert kernel.leapfrog_count() > 16 * 1300
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-4)])
+def test_fused_leaf_kernel_equals_generic_leaf(dtype, tol):
+    """b2_nuts_leaf_hier (leapfrog with recomputed local gradients + tree vectors + scalar logic in
+    two launches) against the generic leaf built from b2_leapfrog_half_kick_drift, b2_potential_grad,
+    b2_leapfrog_half_kick and b2_nuts_leaf_vector, over leaves 0..7 of one subtree from the same
+    start: positions, momenta, potential, global gradients, momentum sums, checkpoints, subtree
+    weights and U-turn decisions."""
+    torch.manual_seed(0)
+    C, J = 5, 3000
+    D = J + 2
+    sig = (5 + 15 * torch.rand(J)).to(DEV, dtype)
+    yy = (5 + 3 * torch.randn(J)).to(DEV, dtype) + sig * torch.randn(J).to(DEV, dtype)
+    pot = HierNormalPotential(yy, sig, 10.0, 25.0)
+    k = NUTS(potential_fn=pot, native_small=False, max_tree_depth=4)
+    k.setup(10, C, seed=0)
+    assert k._use_fused_hier
+    z0 = (0.3 * torch.randn(C, D)).to(DEV, dtype)
+    U0, g0 = pot.value_and_grad(z0.clone())
+    minv = (0.5 + torch.rand(C, D)).to(DEV, dtype)
+    r0 = torch.randn(C, D).to(DEV, dtype)
+    eps = (torch.tensor([1e-3, -1e-3, 2e-3, -5e-4, 1e-3])).to(DEV, dtype)
+    energy0 = U0 + 0.5 * (minv * r0 * r0).sum(-1)
+    u8 = dict(dtype=torch.uint8, device=DEV)
+    t = {"minv": minv, "energy0": energy0, "z": z0.clone(), "r": r0.clone(), "gsc": g0[:, :2].contiguous().clone(),
+         "eps": eps, "rsub": torch.zeros(C, D, device=DEV, dtype=dtype),
+         "rck": torch.zeros(5, C, D, device=DEV, dtype=dtype), "sck": torch.zeros(5, C, D, device=DEV, dtype=dtype),
+         "sum_accept": torch.zeros(C, device=DEV, dtype=dtype), "num_prop": torch.zeros(C, device=DEV, dtype=dtype),
+         "done": torch.zeros(C, **u8), "diverged": torch.zeros(C, **u8), "take": torch.zeros(C, **u8),
+         "num_leapfrogs": torch.zeros(C, dtype=torch.int32, device=DEV), "rng_counter": k._rng_counter,
+         "gsc_s": torch.zeros(C, 2, device=DEV, dtype=dtype), "U": torch.zeros(C, device=DEV, dtype=dtype),
+         "Us": torch.zeros(C, device=DEV, dtype=dtype), "zs": torch.zeros(C, D, device=DEV, dtype=dtype),
+         "logw_sub": torch.full((C,), float("-inf"), device=DEV, dtype=dtype)}
+    st = {"c": k._lockstep_struct(t), "t": t}
+    # generic twin
+    z, r, g = z0.clone(), r0.clone(), g0.clone()
+    rsub = torch.zeros(C, D, device=DEV, dtype=dtype)
+    rck, sck = torch.zeros(5, C, D, device=DEV, dtype=dtype), torch.zeros(5, C, D, device=DEV, dtype=dtype)
+    zs, gs = z.clone(), g.clone()
+    act8 = torch.ones(C, **u8)
+    logw = torch.full((C,), float("-inf"), device=DEV, dtype=dtype)
+    for leaf in range(8):
+        k._leaf_hier(st, leaf)
+        z, r, g, U, ke = k._leapfrog(z, r, g, eps, minv, act8)
+        take8 = torch.zeros(C, **u8)
+        turn = k._leaf_vector(z, r, g, minv, act8, take8, rsub, zs, gs, rck, sck, leaf)
+        sc = lambda a: a.abs().max().clamp(min=1.0)  # noqa: E731
+        assert float((t["z"] - z).abs().max()) <= tol * float(sc(z)), leaf
+        assert float((t["r"] - r).abs().max()) <= tol * float(sc(r)) * 10, leaf
+        assert torch.allclose(t["U"], U, rtol=tol, atol=tol * float(sc(U))), leaf
+        assert torch.allclose(t["gsc"], g[:, :2], rtol=50 * tol, atol=50 * tol * float(sc(g[:, :2]))), leaf
+        assert float((t["rsub"] - rsub).abs().max()) <= 20 * tol * float(sc(rsub)), leaf
+        if leaf % 2 == 0:
+            i = bin(leaf >> 1).count("1")
+            assert float((t["rck"][i] - rck[i]).abs().max()) <= 20 * tol * float(sc(rck[i])), leaf
+            assert float((t["sck"][i] - sck[i]).abs().max()) <= 20 * tol * float(sc(sck[i])), leaf
+        w_leaf = -((U + ke) - energy0)
+        logw = w_leaf if leaf == 0 else torch.logaddexp(logw, w_leaf)
+        assert torch.allclose(t["logw_sub"], logw, rtol=0, atol=200 * tol * float(sc(energy0))), leaf
+        # 8 tiny steps from a random momentum: no U-turn, no divergence, in either implementation
+        assert not bool(turn.any()) and not bool(t["done"].any()) and not bool(t["diverged"].any()), leaf
+    assert int(t["num_leapfrogs"].sum()) == 8 * C
+    assert torch.allclose(t["num_prop"], torch.full_like(t["num_prop"], 8.0))
+
+
+def test_fused_leaf_nuts_eight_schools_posterior():
+    """BASELINE config 1's model through the lockstep driver on the fused leaf kernel (the path
+    config 4 takes at J = 1e6), fp32, 16 chains: posterior moments vs the reference's long run."""
+    torch.set_default_dtype(torch.float32)
+    g = load_npz("mcmc.npz")
+    y, sigma = torch.as_tensor(g["es.y"]).to(DEV, torch.float32), torch.as_tensor(g["es.sigma"]).to(DEV, torch.float32)
+    kernel = NUTS(potential_fn=HierNormalPotential(y, sigma, 10.0, 25.0), native_small=False)
+    n_s, n_w, C = (500, 200, 16) if not EMULATE else (60, 60, 4)
+    mc = MCMC(kernel, num_samples=n_s, warmup_steps=n_w, num_chains=C, seed=0)
+    mc.run()
+    assert kernel._use_fused_hier
+    s = mc.get_samples()
+    tol = 1.0 if not EMULATE else 3.0
+    assert abs(float(s["mu"].mean()) - float(g["es.long.mu.mean"][0])) < 0.6 * tol
+    assert abs(float(s["tau"].mean()) - float(g["es.long.tau.mean"][0])) < 0.8 * tol
+    assert float((s["eta"].mean(0).cpu() - torch.as_tensor(g["es.long.eta.mean"])).abs().max()) < 0.15 * tol
+    assert kernel.leapfrog_count() > C * (n_s + n_w)
+
+
 def test_lockstep_nuts_logistic_posterior():
     torch.set_default_dtype(torch.float64)
     g = load_npz("mcmc.npz")

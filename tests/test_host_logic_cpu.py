@@ -269,6 +269,26 @@ def test_lockstep_nuts_recovers_posterior_logistic(emu):
     assert kernel.leapfrog_count() > 0
 
 
+def test_fused_leaf_lockstep_driver_eight_schools(emu):
+    """Host logic of the fused-leaf lockstep driver (``NUTS._sample_lockstep_hier``: per-depth
+    merges, proposal flush, global-gradient bookkeeping) with the leaf kernel emulated: posterior of
+    eight_schools against the reference's long run (goldens es.long.*)."""
+    from pyro_b200.infer import MCMC, NUTS
+    from pyro_b200.infer.mcmc import HierNormalPotential
+    torch.set_default_dtype(torch.float64)
+    g = load_npz("mcmc.npz")
+    y, sigma = torch.as_tensor(g["es.y"]), torch.as_tensor(g["es.sigma"])
+    kernel = NUTS(potential_fn=HierNormalPotential(y, sigma, 10.0, 25.0), native_small=False)
+    mc = MCMC(kernel, num_samples=150, warmup_steps=100, num_chains=6, seed=3)
+    mc.run()
+    assert kernel._use_fused_hier
+    s = mc.get_samples()
+    assert abs(float(s["mu"].mean()) - float(g["es.long.mu.mean"][0])) < 1.0
+    assert abs(float(s["tau"].mean()) - float(g["es.long.tau.mean"][0])) < 1.5
+    assert float((s["eta"].mean(0) - torch.as_tensor(g["es.long.eta.mean"])).abs().max()) < 0.25
+    assert kernel.leapfrog_count() > 6 * 250
+
+
 def test_trace_potential_matches_reference(emu):
     """Generic model potential (model run under a chain plate, fused site scoring) == reference
     potential + gradient at the golden points."""
