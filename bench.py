@@ -298,7 +298,8 @@ def nuts_section(dev, quick=False):
         "leapfrogs": n, "seconds": round(e0.elapsed_time(e1) * 1e-3, 3),
         "leapfrog_per_sec": round(n / (e0.elapsed_time(e1) * 1e-3), 1),
         "algorithmic_GBps": round(n * 16e6 / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1),
-        "path": "lockstep iterative tree (torch glue) + b2_potential_grad + b2_leapfrog_* kernels; "
+        "path": "lockstep iterative tree, every leaf = b2_nuts_leaf_hier (fused leapfrog with recomputed local "
+                "gradients + tree vectors + scalar logic, 2 launches); per-depth merges in torch; "
                 "10 transitions, max_tree_depth 6 (bounded sample of config 4)"}
     # CPU baseline: oracle restatement of the reference sampler, config 1, one chain
     torch.set_num_threads(1)

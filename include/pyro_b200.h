@@ -341,15 +341,20 @@ int b2_nuts_leaf_vector(const void* z, const void* r, const void* g, const void*
  * chains with take[c] still set.  Chains with done[c] != 0 are untouched.
  */
 typedef struct {
-  void *z, *r;        /* [C, D] position / momentum of the growing end, D = J + 2 */
+  void *zL, *rL, *zR, *rR; /* [C, D] position / momentum at the two ends of the trajectory, D = J + 2;
+                              the end picked by dir[c] is advanced IN PLACE (a doubling always extends
+                              the trajectory; a chain cut short is `done` and its ends are dead) */
+  const uint8_t* dir; /* [C] 1 = the right end grows (with eps[c] > 0), 0 = the left end */
+  void *gscL, *gscR;  /* [C, 2] dU/d(mu, log tau) at the two ends */
   const void* minv;   /* diagonal inverse mass, chain stride minv_chain_stride (0 = shared) */
   int64_t minv_chain_stride;
-  void *rsub;         /* [C, D] whitened momentum sum of the subtree under construction */
+  void *rsub;         /* [C, D] whitened momentum sum of the subtree under construction (leaf 0
+                         overwrites it: no zero-fill needed between subtrees) */
   void *zs;           /* [C, D] proposal of the subtree */
   void *rck, *sck;    /* [slots, C, D] checkpoints: first-leaf momentum / running sum */
   const void* eps;    /* [C] signed step size */
-  void *gsc, *gsc_s;  /* [C, 2] dU/d(mu, log tau) at z / at the proposal */
-  void *U, *Us;       /* [C] potential at z / at the proposal */
+  void *gsc_s;        /* [C, 2] dU/d(mu, log tau) at the proposal */
+  void *U, *Us;       /* [C] potential at the growing end / at the proposal */
   const void* energy0; /* [C] initial energy of the transition */
   void *logw_sub, *sum_accept, *num_prop; /* [C] */
   uint8_t *done, *diverged, *take;        /* [C] */
@@ -363,6 +368,23 @@ typedef struct {
 int b2_nuts_leaf_hier(const b2_model* model, const b2_nuts_lockstep* st, int leaf, int store_slot,
                       int idx_max, int nblk, void* workspace, size_t workspace_bytes, void* stream);
 size_t b2_nuts_leaf_hier_workspace(int64_t C, int64_t J);
+
+/*
+ * b2_nuts_tree_merge -- root of the doubling loop (pyro/infer/mcmc/nuts.py:285-342, 404-440) after
+ * a subtree is finished, for every chain with done[c] == 0:  rsum += rsub;  rho = rsum -
+ * (ruL + ruR)/2 with ru = r * sqrt(minv) at the two trajectory ends;  dots[c] = (<ruL, rho>,
+ * <ruR, rho>) -- the generalised U-turn test of the whole tree.  One pass over [C, D].
+ * workspace: C * 64 * 2 doubles (the b2_mcmc_workspace() size suffices).
+ */
+int b2_nuts_tree_merge(const void* rL, const void* rR, const void* minv, int64_t minv_chain_stride,
+                       void* rsum, const void* rsub, const uint8_t* done, void* dots, int64_t C,
+                       int64_t D, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* b2_rows_copy_masked -- dst[c, :] = src[c, :] for chains with mask[c] != 0 ([C, D] row-major):
+ * the proposal hand-over `torch.where(accepted, new, old)` of nuts.py:303-320 moving only the
+ * accepted rows. */
+int b2_rows_copy_masked(void* dst, const void* src, const uint8_t* mask, int64_t C, int64_t D,
+                        int dtype, void* stream);
 
 /* ---- misc -------------------------------------------------------------------------------- */
 const char* b2_last_error(int code);

@@ -48,10 +48,12 @@ class b2_model(ctypes.Structure):
 
 class b2_nuts_lockstep(ctypes.Structure):
     """Mirror of ``b2_nuts_lockstep`` (include/pyro_b200.h): device pointers of the lockstep tree state."""
-    _fields_ = [("z", ctypes.c_void_p), ("r", ctypes.c_void_p), ("minv", ctypes.c_void_p),
+    _fields_ = [("zL", ctypes.c_void_p), ("rL", ctypes.c_void_p), ("zR", ctypes.c_void_p),
+                ("rR", ctypes.c_void_p), ("dir", ctypes.c_void_p), ("gscL", ctypes.c_void_p),
+                ("gscR", ctypes.c_void_p), ("minv", ctypes.c_void_p),
                 ("minv_chain_stride", ctypes.c_int64), ("rsub", ctypes.c_void_p), ("zs", ctypes.c_void_p),
                 ("rck", ctypes.c_void_p), ("sck", ctypes.c_void_p), ("eps", ctypes.c_void_p),
-                ("gsc", ctypes.c_void_p), ("gsc_s", ctypes.c_void_p), ("U", ctypes.c_void_p),
+                ("gsc_s", ctypes.c_void_p), ("U", ctypes.c_void_p),
                 ("Us", ctypes.c_void_p), ("energy0", ctypes.c_void_p), ("logw_sub", ctypes.c_void_p),
                 ("sum_accept", ctypes.c_void_p), ("num_prop", ctypes.c_void_p), ("done", ctypes.c_void_p),
                 ("diverged", ctypes.c_void_p), ("take", ctypes.c_void_p), ("num_leapfrogs", ctypes.c_void_p),
@@ -92,6 +94,8 @@ SIGNATURES = {
                                    _i32, _vp, _i64, _i64, _i32, _vp, _sz, _vp]),
     "b2_nuts_leaf_hier": (_i32, [_mp, ctypes.POINTER(b2_nuts_lockstep), _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "b2_nuts_leaf_hier_workspace": (_sz, [_i64, _i64]),
+    "b2_rows_copy_masked": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "b2_nuts_tree_merge": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _sz, _vp]),
     "b2_last_error": (ctypes.c_char_p, [_i32]),
     "b2_version": (_i32, []),
     "b2_launch_count": (_i64, []),

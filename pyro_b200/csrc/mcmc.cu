@@ -622,10 +622,13 @@ __global__ void nuts_dots_finish_kernel(const double* __restrict__ partials, int
 // the two global gradients, finishes the global coordinates' kick, and runs the per-chain scalar
 // logic of the tree (energy, divergence, multinomial draw with Philox, U-turn flags).
 struct LeafHierArgs {
-  void *z, *r, *rsub, *zs, *rck, *sck;  // [C, D] / [slots, C, D]
+  void *zL, *rL, *zR, *rR;              // [C, D] the two ends of the trajectory; dir[c] picks the one that grows
+  const uint8_t* dir;                   // [C] 1 = the right end grows
+  void *gscL, *gscR;                    // [C, 2] global-coordinate gradients at the two ends
+  void *rsub, *zs, *rck, *sck;          // [C, D] / [slots, C, D]
   const void *minv, *y, *sigma;         // [C, D] (chain stride minv_cs), [J], [J]
   const void* eps;                      // [C] signed step
-  void *gsc, *gsc_s;                    // [C, 2] global-coordinate gradients at z / at the proposal
+  void* gsc_s;                          // [C, 2] global-coordinate gradients at the proposal
   void *U, *Us, *logw_sub, *sum_accept, *num_prop;  // [C]
   const void* energy0;                  // [C]
   uint8_t *done, *diverged, *take;      // [C]
@@ -652,13 +655,15 @@ __global__ void __launch_bounds__(256) nuts_leaf_hier_kernel(const LeafHierArgs 
   const T* __restrict__ sigma = reinterpret_cast<const T*>(a.sigma);
   for (int64_t c = blockIdx.y; c < a.C; c += gridDim.y) {
     if (a.done[c]) continue;  // uniform over the CTA
-    T* __restrict__ zc = reinterpret_cast<T*>(a.z) + c * D;
-    T* __restrict__ rc = reinterpret_cast<T*>(a.r) + c * D;
+    const bool right = a.dir[c] != 0;
+    T* __restrict__ zc = reinterpret_cast<T*>(right ? a.zR : a.zL) + c * D;
+    T* __restrict__ rc = reinterpret_cast<T*>(right ? a.rR : a.rL) + c * D;
     T* __restrict__ rs = reinterpret_cast<T*>(a.rsub) + c * D;
     T* __restrict__ zsc = reinterpret_cast<T*>(a.zs) + c * D;
     const T* __restrict__ mi = reinterpret_cast<const T*>(a.minv) + c * a.minv_cs;
-    const T* gsc = reinterpret_cast<const T*>(a.gsc) + c * 2;
+    const T* gsc = reinterpret_cast<const T*>(right ? a.gscR : a.gscL) + c * 2;
     const bool tk = a.take[c] != 0;  // the previous leaf was drawn as the proposal
+    const bool first = a.leaf == 0;  // the subtree's momentum sum starts at zero: nothing to read
     const T e = reinterpret_cast<const T*>(a.eps)[c];
     const T he = (T)0.5 * e;
     // global coordinates: every thread repeats the (cheap) scalar update; the finish kernel stores it
@@ -726,7 +731,7 @@ __global__ void __launch_bounds__(256) nuts_leaf_hier_kernel(const LeafHierArgs 
         ev[u] = zc[2 + jj];
         rv[u] = rc[2 + jj];
         mv[u] = mi[2 + jj];
-        sv[u] = rs[2 + jj];
+        sv[u] = first ? (T)0 : rs[2 + jj];
         yv[u] = __ldg(y + jj);
         gv[u] = __ldg(sigma + jj);
       }
@@ -734,7 +739,7 @@ __global__ void __launch_bounds__(256) nuts_leaf_hier_kernel(const LeafHierArgs 
       for (int u = 0; u < UN; ++u) elem(j + u * stride, ev[u], rv[u], mv[u], sv[u], yv[u], gv[u]);
     }
     for (; j < J; j += stride)
-      elem(j, zc[2 + j], rc[2 + j], mi[2 + j], rs[2 + j], __ldg(y + j), __ldg(sigma + j));
+      elem(j, zc[2 + j], rc[2 + j], mi[2 + j], first ? (T)0 : rs[2 + j], __ldg(y + j), __ldg(sigma + j));
     // CTA reduction of the NV sums (fixed order), one partial row per (chain, CTA)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -783,12 +788,13 @@ __global__ void __launch_bounds__(128) nuts_leaf_hier_finish_kernel(const LeafHi
   }
   if (lane != 0) return;
   const int64_t J = a.J, D = J + 2;
-  T* zc = reinterpret_cast<T*>(a.z) + c * D;
-  T* rc = reinterpret_cast<T*>(a.r) + c * D;
+  const bool right = a.dir[c] != 0;
+  T* zc = reinterpret_cast<T*>(right ? a.zR : a.zL) + c * D;
+  T* rc = reinterpret_cast<T*>(right ? a.rR : a.rL) + c * D;
   T* rs = reinterpret_cast<T*>(a.rsub) + c * D;
   T* zsc = reinterpret_cast<T*>(a.zs) + c * D;
   const T* mi = reinterpret_cast<const T*>(a.minv) + c * a.minv_cs;
-  T* gsc = reinterpret_cast<T*>(a.gsc) + c * 2;
+  T* gsc = reinterpret_cast<T*>(right ? a.gscR : a.gscL) + c * 2;
   const bool tk = a.take[c] != 0;
   const T e = reinterpret_cast<const T*>(a.eps)[c];
   const T he = (T)0.5 * e;
@@ -822,7 +828,7 @@ __global__ void __launch_bounds__(128) nuts_leaf_hier_finish_kernel(const LeafHi
     const T ru[2] = {r0 * b2_sqrt(mi[0]), r1 * b2_sqrt(mi[1])};
     T rsn[2];
     for (int d = 0; d < 2; ++d) {
-      rsn[d] = rs[d] + ru[d];
+      rsn[d] = (a.leaf == 0 ? (T)0 : rs[d]) + ru[d];
       rs[d] = rsn[d];
     }
     T* ck_r = reinterpret_cast<T*>(a.rck);
@@ -887,6 +893,58 @@ __global__ void __launch_bounds__(128) nuts_leaf_hier_finish_kernel(const LeafHi
   if (div_now || (turn && !div_now)) a.done[c] = 1;
 }
 
+
+// ---- top-level merge of a finished subtree (nuts.py:285-342 at the root of the doubling loop) --------
+// For every chain still active:  rsum += rsub ;  rho = rsum - (ruL + ruR)/2 ;  the two U-turn dot
+// products <ruL, rho>, <ruR, rho> of the whole tree, ru = r * sqrt(minv) at the two ends.  One pass over
+// [C, D] (28 B per chain-element) instead of ~8 elementwise/reduction launches.
+template <typename T>
+__global__ void __launch_bounds__(256) nuts_tree_merge_kernel(
+    const T* __restrict__ rL, const T* __restrict__ rR, const T* __restrict__ minv, int64_t minv_cs,
+    T* __restrict__ rsum, const T* __restrict__ rsub, const uint8_t* __restrict__ done,
+    double* __restrict__ partials, int64_t C, int64_t D) {
+  __shared__ double smem[2 * 32];
+  for (int64_t c = blockIdx.y; c < C; c += gridDim.y) {
+    double acc[2] = {0.0, 0.0};
+    if (!done[c]) {
+      const T* mi = minv + c * minv_cs;
+      T a0 = 0, a1 = 0;
+      for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D;
+           d += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = c * D + d;
+        const T sq = b2_sqrt(mi[d]);
+        const T ul = rL[i] * sq, ur = rR[i] * sq;
+        const T rs = rsum[i] + rsub[i];
+        rsum[i] = rs;
+        const T rho = rs - (T)0.5 * (ul + ur);
+        a0 += ul * rho;
+        a1 += ur * rho;
+      }
+      acc[0] = (double)a0;
+      acc[1] = (double)a1;
+    }
+    block_sum<2>(acc, smem);
+    if (threadIdx.x == 0) {
+      partials[(c * gridDim.x + blockIdx.x) * 2] = acc[0];
+      partials[(c * gridDim.x + blockIdx.x) * 2 + 1] = acc[1];
+    }
+  }
+}
+
+
+// dst[c, :] = src[c, :] for the chains with mask[c] != 0 (proposal hand-over at the root of the tree:
+// only the accepted rows move, 8 B per moved element, instead of a full-size torch.where)
+template <typename T>
+__global__ void __launch_bounds__(256) rows_copy_masked_kernel(T* __restrict__ dst, const T* __restrict__ src,
+                                                               const uint8_t* __restrict__ mask, int64_t C,
+                                                               int64_t D) {
+  for (int64_t c = blockIdx.y; c < C; c += gridDim.y) {
+    if (!mask[c]) continue;
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D; d += (int64_t)gridDim.x * blockDim.x)
+      dst[c * D + d] = src[c * D + d];
+  }
+}
+
 }  // namespace b2
 extern "C" int b2_nuts_leaf_vector(const void* z, const void* r, const void* g, const void* minv,
                                    int64_t minv_chain_stride, const uint8_t* active,
@@ -941,8 +999,9 @@ extern "C" int b2_nuts_leaf_hier(const b2_model* model, const b2_nuts_lockstep* 
   if (!model || !st) return B2_ERR_NULL;
   if (model->model != B2_MODEL_HIER_NORMAL) return B2_ERR_BAD_FAMILY;
   if (model->dtype != B2_F32 && model->dtype != B2_F64) return B2_ERR_BAD_DTYPE;
-  if (!st->z || !st->r || !st->rsub || !st->zs || !st->rck || !st->sck || !st->minv || !st->eps ||
-      !st->gsc || !st->gsc_s || !st->U || !st->Us || !st->energy0 || !st->logw_sub ||
+  if (!st->zL || !st->rL || !st->zR || !st->rR || !st->dir || !st->gscL || !st->gscR || !st->rsub ||
+      !st->zs || !st->rck || !st->sck || !st->minv || !st->eps ||
+      !st->gsc_s || !st->U || !st->Us || !st->energy0 || !st->logw_sub ||
       !st->sum_accept || !st->num_prop || !st->done || !st->diverged || !st->take || !st->rng_counter)
     return B2_ERR_NULL;
   const int64_t C = st->C, J = model->J;
@@ -951,9 +1010,11 @@ extern "C" int b2_nuts_leaf_hier(const b2_model* model, const b2_nuts_lockstep* 
   if (nblk < 0 || nblk > kNutsMaxBlocks) return B2_ERR_BAD_SHAPE;
   if (!workspace || workspace_bytes < b2_nuts_leaf_hier_workspace(C, J)) return B2_ERR_WORKSPACE;
   LeafHierArgs a;
-  a.z = st->z; a.r = st->r; a.rsub = st->rsub; a.zs = st->zs; a.rck = st->rck; a.sck = st->sck;
+  a.zL = st->zL; a.rL = st->rL; a.zR = st->zR; a.rR = st->rR; a.dir = st->dir;
+  a.gscL = st->gscL; a.gscR = st->gscR;
+  a.rsub = st->rsub; a.zs = st->zs; a.rck = st->rck; a.sck = st->sck;
   a.minv = st->minv; a.y = model->data0; a.sigma = model->data1; a.eps = st->eps;
-  a.gsc = st->gsc; a.gsc_s = st->gsc_s; a.U = st->U; a.Us = st->Us; a.energy0 = st->energy0;
+  a.gsc_s = st->gsc_s; a.U = st->U; a.Us = st->Us; a.energy0 = st->energy0;
   a.logw_sub = st->logw_sub; a.sum_accept = st->sum_accept; a.num_prop = st->num_prop;
   a.done = st->done; a.diverged = st->diverged; a.take = st->take; a.nleaf = st->num_leapfrogs;
   a.rng_counter = st->rng_counter;
@@ -971,15 +1032,67 @@ extern "C" int b2_nuts_leaf_hier(const b2_model* model, const b2_nuts_lockstep* 
   if (model->dtype == B2_F32) {
     if (nblk == 0) nuts_leaf_hier_kernel<float, 0><<<grid, 256, 0, s>>>(a);
     else if (nblk <= 2) nuts_leaf_hier_kernel<float, 2><<<grid, 256, 0, s>>>(a);
+    else if (nblk <= 4) nuts_leaf_hier_kernel<float, 4><<<grid, 256, 0, s>>>(a);
     else nuts_leaf_hier_kernel<float, kNutsMaxBlocks><<<grid, 256, 0, s>>>(a);
     nuts_leaf_hier_finish_kernel<float><<<fin_blocks, 128, 0, s>>>(a);
   } else {
     if (nblk == 0) nuts_leaf_hier_kernel<double, 0><<<grid, 256, 0, s>>>(a);
     else if (nblk <= 2) nuts_leaf_hier_kernel<double, 2><<<grid, 256, 0, s>>>(a);
+    else if (nblk <= 4) nuts_leaf_hier_kernel<double, 4><<<grid, 256, 0, s>>>(a);
     else nuts_leaf_hier_kernel<double, kNutsMaxBlocks><<<grid, 256, 0, s>>>(a);
     nuts_leaf_hier_finish_kernel<double><<<fin_blocks, 128, 0, s>>>(a);
   }
   count_launch(2);
+  return check_launch();
+}
+
+extern "C" int b2_nuts_tree_merge(const void* rL, const void* rR, const void* minv,
+                                  int64_t minv_chain_stride, void* rsum, const void* rsub,
+                                  const uint8_t* done, void* dots, int64_t C, int64_t D, int dtype,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace b2;
+  if (!rL || !rR || !minv || !rsum || !rsub || !done || !dots) return B2_ERR_NULL;
+  if (C <= 0 || D <= 0) return B2_OK;
+  if (C > 65535) return B2_ERR_TOO_LARGE;
+  const unsigned bx = bx_for(D, C);
+  if (!workspace || workspace_bytes < (size_t)C * bx * 2 * sizeof(double)) return B2_ERR_WORKSPACE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  double* partials = reinterpret_cast<double*>(workspace);
+  dim3 grid(bx, (unsigned)C, 1);
+  if (dtype == B2_F32) {
+    nuts_tree_merge_kernel<float><<<grid, 256, 0, s>>>((const float*)rL, (const float*)rR, (const float*)minv,
+                                                        minv_chain_stride, (float*)rsum, (const float*)rsub,
+                                                        done, partials, C, D);
+    nuts_dots_finish_kernel<float><<<(unsigned)((C * 2 + 127) / 128), 128, 0, s>>>(partials, (int)bx, 2,
+                                                                                     (float*)dots, C);
+  } else if (dtype == B2_F64) {
+    nuts_tree_merge_kernel<double><<<grid, 256, 0, s>>>((const double*)rL, (const double*)rR,
+                                                         (const double*)minv, minv_chain_stride,
+                                                         (double*)rsum, (const double*)rsub, done, partials, C, D);
+    nuts_dots_finish_kernel<double><<<(unsigned)((C * 2 + 127) / 128), 128, 0, s>>>(partials, (int)bx, 2,
+                                                                                      (double*)dots, C);
+  } else {
+    return B2_ERR_BAD_DTYPE;
+  }
+  count_launch(2);
+  return check_launch();
+}
+
+extern "C" int b2_rows_copy_masked(void* dst, const void* src, const uint8_t* mask, int64_t C, int64_t D,
+                                   int dtype, void* stream) {
+  using namespace b2;
+  if (!dst || !src || !mask) return B2_ERR_NULL;
+  if (C <= 0 || D <= 0) return B2_OK;
+  if (C > 65535) return B2_ERR_TOO_LARGE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(bx_for(D, C), (unsigned)C, 1);
+  if (dtype == B2_F32)
+    rows_copy_masked_kernel<float><<<grid, 256, 0, s>>>((float*)dst, (const float*)src, mask, C, D);
+  else if (dtype == B2_F64)
+    rows_copy_masked_kernel<double><<<grid, 256, 0, s>>>((double*)dst, (const double*)src, mask, C, D);
+  else
+    return B2_ERR_BAD_DTYPE;
+  count_launch();
   return check_launch();
 }
 

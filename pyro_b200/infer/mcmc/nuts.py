@@ -334,9 +334,9 @@ class NUTS(HMC):
 
     def _lockstep_struct(self, t):
         c = N.b2_nuts_lockstep()
-        for k in ("z", "r", "minv", "rsub", "zs", "rck", "sck", "eps", "gsc", "gsc_s", "U", "Us", "energy0",
-                  "logw_sub", "sum_accept", "num_prop", "done", "diverged", "take", "num_leapfrogs",
-                  "rng_counter"):
+        for k in ("zL", "rL", "zR", "rR", "dir", "gscL", "gscR", "minv", "rsub", "zs", "rck", "sck", "eps",
+                  "gsc_s", "U", "Us", "energy0", "logw_sub", "sum_accept", "num_prop", "done", "diverged",
+                  "take", "num_leapfrogs", "rng_counter"):
             setattr(c, k, t[k].data_ptr())
         c.minv_chain_stride = t["minv"].stride(0)
         c.seed = self._seed
@@ -344,32 +344,55 @@ class NUTS(HMC):
         c.C = self.C
         return c
 
+    def _tree_merge(self, t, rsum):
+        """rsum += rsub for the active chains and the two whole-tree U-turn dot products [C, 2]
+        (b2_nuts_tree_merge: one pass over [C, D])."""
+        C, D = self.C, self.D
+        dev = rsum.device
+        dots = torch.zeros(C, 2, dtype=rsum.dtype, device=dev)
+        lib = N.lib()
+        ws = N.workspace(dev, int(lib.b2_mcmc_workspace(C)), tag="mcmc")
+        N.check(lib.b2_nuts_tree_merge(t["rL"].data_ptr(), t["rR"].data_ptr(), t["minv"].data_ptr(),
+                                       t["minv"].stride(0), rsum.data_ptr(), t["rsub"].data_ptr(),
+                                       t["done"].data_ptr(), dots.data_ptr(), C, D, N._DTYPES[rsum.dtype],
+                                       ws.data_ptr(), ws.numel(), N.stream_ptr(dev)), "b2_nuts_tree_merge")
+        return dots
+
+    def _rows_copy(self, dst, src, mask):
+        """dst[c] = src[c] where mask[c] (b2_rows_copy_masked; only the selected rows move)."""
+        m8 = mask.to(torch.uint8)
+        N.check(N.lib().b2_rows_copy_masked(dst.data_ptr(), src.data_ptr(), m8.data_ptr(), dst.shape[0],
+                                            dst.shape[1], N._DTYPES[dst.dtype], N.stream_ptr(dst.device)),
+                "b2_rows_copy_masked")
+
     def _sample_lockstep_hier(self):
         """Same transition as ``_sample_lockstep`` (nuts.py:367-522 restated iteratively, all active
         chains sharing (depth, leaf)), but every leaf is ONE call of the fused kernel pair: the
         leapfrog with recomputed local gradients, the tree vectors, and the per-chain scalar logic
-        all stay on the device; the host loop only counts leaves.  Per tree end only the two
-        global-coordinate gradients are kept (``gsc``), not a gradient vector."""
+        all stay on the device; the host loop only counts leaves.  The two trajectory ends live in
+        two buffer sets and the end picked by ``dir`` is advanced in place (a doubling always extends
+        the trajectory), so nothing of size [C, D] is selected or merged back per depth; per end only
+        the two global-coordinate gradients are kept (``gsc``), not a gradient vector."""
         C, D = self.C, self.D
         dev, dtype = self._z.device, self._z.dtype
         eps_abs = self._adapter.step_size
         minv = self._adapter.inverse_mass.contiguous()
-        s = minv.sqrt()
         z0, U0 = self._z, self._U
         gsc0 = self._gsc if self._gsc is not None else self._g[:, :2].contiguous()
         ru = self._randn(C, D)
-        r = ru / s
+        r = ru * minv.rsqrt()
         energy0 = U0 + 0.5 * (ru * ru).sum(-1)
-        zl, rl, gl, rul = z0, r, gsc0, ru          # never written in place: torch.where makes the work copies
-        zr, rr, gr, rur = z0, r, gsc0, ru
-        zp, gp, Up = z0, gsc0, U0
-        rsum = ru.clone()
+        zp, gp, Up = z0.clone(), gsc0, U0
+        rsum = ru                                   # the tree's momentum sum starts as the initial leaf
         maxd = self._max_tree_depth
         u8 = dict(dtype=torch.uint8, device=dev)
         t = {
+            "zL": z0.clone(), "rL": r.clone(), "zR": z0.clone(), "rR": r, "gscL": gsc0.clone(),
+            "gscR": gsc0.clone(), "dir": torch.zeros(C, **u8),
             "minv": minv, "energy0": energy0.contiguous(),
             "rck": torch.empty(maxd + 1, C, D, dtype=dtype, device=dev),
             "sck": torch.empty(maxd + 1, C, D, dtype=dtype, device=dev),
+            "rsub": torch.empty(C, D, dtype=dtype, device=dev),
             "sum_accept": torch.zeros(C, dtype=dtype, device=dev),
             "num_prop": torch.zeros(C, dtype=dtype, device=dev),
             "done": torch.zeros(C, **u8), "diverged": torch.zeros(C, **u8), "take": torch.zeros(C, **u8),
@@ -378,7 +401,10 @@ class NUTS(HMC):
             "gsc_s": torch.empty(C, 2, dtype=dtype, device=dev),
             "U": torch.empty(C, dtype=dtype, device=dev), "Us": torch.empty(C, dtype=dtype, device=dev),
             "zs": torch.empty(C, D, dtype=dtype, device=dev),
+            "logw_sub": torch.empty(C, dtype=dtype, device=dev),
+            "eps": torch.empty(C, dtype=dtype, device=dev),
         }
+        st = {"c": self._lockstep_struct(t), "t": t}
         logw_tree = torch.zeros(C, dtype=dtype, device=dev)
         accepted = torch.zeros(C, dtype=torch.bool, device=dev)
         depth_reached = torch.zeros(C, dtype=torch.int32, device=dev)
@@ -387,44 +413,31 @@ class NUTS(HMC):
             if depth > 0 and bool(done.all()):
                 break
             go_right = self._rand(C) < 0.5
-            grm = go_right[:, None]
-            t["z"] = torch.where(grm, zr, zl).contiguous()
-            t["r"] = torch.where(grm, rr, rl).contiguous()
-            t["gsc"] = torch.where(grm, gr, gl).contiguous()
-            t["eps"] = torch.where(go_right, eps_abs, -eps_abs).contiguous()
-            t["rsub"] = torch.zeros(C, D, dtype=dtype, device=dev)
-            t["logw_sub"] = torch.full((C,), float("-inf"), dtype=dtype, device=dev)
+            t["dir"].copy_(go_right)
+            t["eps"].copy_(torch.where(go_right, eps_abs, -eps_abs))
+            t["logw_sub"].fill_(float("-inf"))
             t["take"].zero_()
-            st = {"c": self._lockstep_struct(t), "t": t}
             nleaves = 1 << depth
             for leaf in range(nleaves):
                 self._leaf_hier(st, leaf)
                 if (leaf & 15) == 15 and leaf + 1 < nleaves and bool(done.all()):
                     break
-            z, rcur, g = t["z"], t["r"], t["gsc"]
-            # the last drawn leaf of each chain has not been copied yet (the copy rides on the NEXT leaf)
-            zs = torch.where(t["take"].bool()[:, None], z, t["zs"])
             # ---- merge the finished subtree (chains cut short are already `done`) ---------------
             active = ~done.bool()
-            am = active[:, None]
-            right = am & grm
-            left = am & ~grm
-            ru_c = rcur * s
-            zr = torch.where(right, z, zr); rr = torch.where(right, rcur, rr)
-            gr = torch.where(right, g, gr); rur = torch.where(right, ru_c, rur)
-            zl = torch.where(left, z, zl); rl = torch.where(left, rcur, rl)
-            gl = torch.where(left, g, gl); rul = torch.where(left, ru_c, rul)
-            depth_reached = depth_reached + active.to(torch.int32)
             logw_sub = t["logw_sub"]
             acc_tree = active & (self._rand(C) < torch.exp(logw_sub - logw_tree))
             accepted = accepted | acc_tree
-            at = acc_tree[:, None]
-            zp = torch.where(at, zs, zp)
-            gp = torch.where(at, t["gsc_s"], gp)
+            # proposal hand-over; the last drawn leaf of a chain has not been copied into zs yet (the
+            # copy rides on the NEXT leaf), so those chains take it straight from the end that grew
+            last = t["take"].bool() & acc_tree
+            self._rows_copy(zp, t["zs"], acc_tree & ~last)
+            self._rows_copy(zp, t["zR"], last & go_right)
+            self._rows_copy(zp, t["zL"], last & ~go_right)
+            gp = torch.where(acc_tree[:, None], t["gsc_s"], gp)
             Up = torch.where(acc_tree, t["Us"], Up)
-            rsum = rsum + torch.where(am, t["rsub"], torch.zeros_like(rsum))
-            rho = rsum - 0.5 * (rul + rur)
-            turning_top = ((rul * rho).sum(-1) <= 0) | ((rur * rho).sum(-1) <= 0)
+            depth_reached = depth_reached + active.to(torch.int32)
+            dots = self._tree_merge(t, rsum)
+            turning_top = (dots <= 0).any(-1)
             logw_tree = torch.where(active & ~turning_top, _logaddexp(logw_tree, logw_sub), logw_tree)
             done |= (active & turning_top).to(torch.uint8)
         self._z, self._gsc, self._U = zp, gp, Up

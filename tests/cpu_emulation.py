@@ -107,13 +107,17 @@ def _leaf_vector(self, z, rcur, g, minv, active8, take8, rsub, zs, gs, rck, sck,
 
 def _leaf_hier(self, st, leaf):
     """torch stand-in for b2_nuts_leaf_hier (include/pyro_b200.h): one new leaf for every active
-    chain, state advanced in place, scalar tree logic included; the uniform for the multinomial draw
-    comes from the kernel's torch generator instead of Philox."""
+    chain, the end picked by ``dir`` advanced in place, scalar tree logic included; the uniform for
+    the multinomial draw comes from the kernel's torch generator instead of Philox."""
     t = st["t"]
     done = t["done"].bool()
     act = ~done
     am = act[:, None]
-    z, r, minv, eps = t["z"], t["r"], t["minv"], t["eps"]
+    right = t["dir"].bool()
+    rm = right[:, None]
+    z = torch.where(rm, t["zR"], t["zL"])
+    r = torch.where(rm, t["rR"], t["rL"])
+    minv, eps = t["minv"], t["eps"]
     tk = (t["take"].bool() & act)[:, None]
     t["zs"].copy_(torch.where(tk, z, t["zs"]))
     _, g_old = self.potential.value_and_grad(z)
@@ -123,13 +127,17 @@ def _leaf_hier(self, st, leaf):
     U2, g2 = self.potential.value_and_grad(z2)
     r2 = rh - 0.5 * e * g2
     ke = 0.5 * (minv * r2 * r2).sum(-1)
-    z.copy_(torch.where(am, z2, z))
-    r.copy_(torch.where(am, r2, r))
-    t["gsc"].copy_(torch.where(am, g2[:, :2], t["gsc"]))
+    for side, sel in (("R", am & rm), ("L", am & ~rm)):
+        t["z" + side].copy_(torch.where(sel, z2, t["z" + side]))
+        t["r" + side].copy_(torch.where(sel, r2, t["r" + side]))
+        t["gsc" + side].copy_(torch.where(sel, g2[:, :2], t["gsc" + side]))
     t["U"].copy_(torch.where(act, U2, t["U"]))
     ru = r2 * minv.sqrt()
     rsub = t["rsub"]
-    rsub.add_(torch.where(am, ru, torch.zeros_like(ru)))
+    if leaf == 0:
+        rsub.copy_(torch.where(am, ru, rsub))
+    else:
+        rsub.add_(torch.where(am, ru, torch.zeros_like(ru)))
     idx_max = bin(leaf >> 1).count("1")
     turn = torch.zeros(z.shape[0], dtype=torch.bool)
     rck, sck = t["rck"], t["sck"]
@@ -167,6 +175,21 @@ def _leaf_hier(self, st, leaf):
     t["take"].copy_(torch.where(act, take, t["take"].bool()).to(torch.uint8))
     t["diverged"].copy_((t["diverged"].bool() | div_now).to(torch.uint8))
     t["done"].copy_((done | div_now | (act & turn & ~div_now)).to(torch.uint8))
+
+
+def _tree_merge(self, t, rsum):
+    act = ~t["done"].bool()
+    am = act[:, None]
+    sq = t["minv"].sqrt()
+    ul, ur = t["rL"] * sq, t["rR"] * sq
+    rsum.copy_(torch.where(am, rsum + t["rsub"], rsum))
+    rho = rsum - 0.5 * (ul + ur)
+    dots = torch.stack([(ul * rho).sum(-1), (ur * rho).sum(-1)], dim=-1)
+    return torch.where(am, dots, torch.zeros_like(dots))
+
+
+def _rows_copy(self, dst, src, mask):
+    dst.copy_(torch.where(mask.bool()[:, None], src, dst))
 
 
 def _native_value_and_grad(self, z, active=None, out_grad=None):
@@ -250,8 +273,8 @@ def enabled():
     nuts.HMC._leapfrog = _leapfrog
     saved_leaf = nuts.NUTS._leaf_vector
     nuts.NUTS._leaf_vector = _leaf_vector
-    saved_leaf_hier = nuts.NUTS._leaf_hier
-    nuts.NUTS._leaf_hier = _leaf_hier
+    saved_leaf_hier = (nuts.NUTS._leaf_hier, nuts.NUTS._tree_merge, nuts.NUTS._rows_copy)
+    nuts.NUTS._leaf_hier, nuts.NUTS._tree_merge, nuts.NUTS._rows_copy = _leaf_hier, _tree_merge, _rows_copy
     ops.reduce_to = _reduce_to
     saved_rs = (ops.normal_rsample_score, ops.normal_rsample_backward, N.EMULATE_RSAMPLE)
     saved_comb = ops.elbo_combine
@@ -266,6 +289,6 @@ def enabled():
         ops.elbo_combine = saved_comb
         pdist._BernoulliLinear._fused_sum = saved_glm
         nuts.NUTS._leaf_vector = saved_leaf
-        nuts.NUTS._leaf_hier = saved_leaf_hier
+        nuts.NUTS._leaf_hier, nuts.NUTS._tree_merge, nuts.NUTS._rows_copy = saved_leaf_hier
         (ops.site_score, N.require_cuda, optim.ClippedAdam._launch, optim.AdagradRMSProp._launch,
          pot.NativePotential.value_and_grad, nuts.HMC._leapfrog, ops.reduce_to) = saved

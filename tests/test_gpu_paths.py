@@ -315,8 +315,11 @@ def test_fused_leaf_kernel_equals_generic_leaf(dtype, tol):
     eps = (torch.tensor([1e-3, -1e-3, 2e-3, -5e-4, 1e-3])).to(DEV, dtype)
     energy0 = U0 + 0.5 * (minv * r0 * r0).sum(-1)
     u8 = dict(dtype=torch.uint8, device=DEV)
-    t = {"minv": minv, "energy0": energy0, "z": z0.clone(), "r": r0.clone(), "gsc": g0[:, :2].contiguous().clone(),
-         "eps": eps, "rsub": torch.zeros(C, D, device=DEV, dtype=dtype),
+    # chains 0, 2, 4 grow the right end (eps > 0), chains 1, 3 the left end
+    dirv = (eps > 0).to(torch.uint8)
+    t = {"minv": minv, "energy0": energy0, "zL": z0.clone(), "rL": r0.clone(), "zR": z0.clone(), "rR": r0.clone(),
+         "gscL": g0[:, :2].contiguous().clone(), "gscR": g0[:, :2].contiguous().clone(), "dir": dirv,
+         "eps": eps, "rsub": torch.full((C, D), 7.0, device=DEV, dtype=dtype),   # stale: leaf 0 must overwrite
          "rck": torch.zeros(5, C, D, device=DEV, dtype=dtype), "sck": torch.zeros(5, C, D, device=DEV, dtype=dtype),
          "sum_accept": torch.zeros(C, device=DEV, dtype=dtype), "num_prop": torch.zeros(C, device=DEV, dtype=dtype),
          "done": torch.zeros(C, **u8), "diverged": torch.zeros(C, **u8), "take": torch.zeros(C, **u8),
@@ -325,6 +328,7 @@ def test_fused_leaf_kernel_equals_generic_leaf(dtype, tol):
          "Us": torch.zeros(C, device=DEV, dtype=dtype), "zs": torch.zeros(C, D, device=DEV, dtype=dtype),
          "logw_sub": torch.full((C,), float("-inf"), device=DEV, dtype=dtype)}
     st = {"c": k._lockstep_struct(t), "t": t}
+    rm = dirv.bool()[:, None]
     # generic twin
     z, r, g = z0.clone(), r0.clone(), g0.clone()
     rsub = torch.zeros(C, D, device=DEV, dtype=dtype)
@@ -338,10 +342,14 @@ def test_fused_leaf_kernel_equals_generic_leaf(dtype, tol):
         take8 = torch.zeros(C, **u8)
         turn = k._leaf_vector(z, r, g, minv, act8, take8, rsub, zs, gs, rck, sck, leaf)
         sc = lambda a: a.abs().max().clamp(min=1.0)  # noqa: E731
-        assert float((t["z"] - z).abs().max()) <= tol * float(sc(z)), leaf
-        assert float((t["r"] - r).abs().max()) <= tol * float(sc(r)) * 10, leaf
+        zf, rf = torch.where(rm, t["zR"], t["zL"]), torch.where(rm, t["rR"], t["rL"])
+        gf = torch.where(rm, t["gscR"], t["gscL"])
+        # the end that does not grow is untouched
+        assert torch.equal(torch.where(rm, t["zL"], t["zR"]), z0) and torch.equal(torch.where(rm, t["rL"], t["rR"]), r0)
+        assert float((zf - z).abs().max()) <= tol * float(sc(z)), leaf
+        assert float((rf - r).abs().max()) <= tol * float(sc(r)) * 10, leaf
         assert torch.allclose(t["U"], U, rtol=tol, atol=tol * float(sc(U))), leaf
-        assert torch.allclose(t["gsc"], g[:, :2], rtol=50 * tol, atol=50 * tol * float(sc(g[:, :2]))), leaf
+        assert torch.allclose(gf, g[:, :2], rtol=50 * tol, atol=50 * tol * float(sc(g[:, :2]))), leaf
         assert float((t["rsub"] - rsub).abs().max()) <= 20 * tol * float(sc(rsub)), leaf
         if leaf % 2 == 0:
             i = bin(leaf >> 1).count("1")
@@ -354,6 +362,25 @@ def test_fused_leaf_kernel_equals_generic_leaf(dtype, tol):
         assert not bool(turn.any()) and not bool(t["done"].any()) and not bool(t["diverged"].any()), leaf
     assert int(t["num_leapfrogs"].sum()) == 8 * C
     assert torch.allclose(t["num_prop"], torch.full_like(t["num_prop"], 8.0))
+    # root merge: rsum += rsub and the whole-tree U-turn products, against plain torch
+    rsum0 = torch.randn(C, D, device=DEV, dtype=dtype)
+    t["done"][1] = 1
+    rsum = rsum0.clone()
+    dots = k._tree_merge(t, rsum)
+    sq = minv.sqrt()
+    ul, ur = t["rL"] * sq, t["rR"] * sq
+    ref_sum = rsum0 + t["rsub"]
+    rho = ref_sum - 0.5 * (ul + ur)
+    ref = torch.stack([(ul * rho).sum(-1), (ur * rho).sum(-1)], -1)
+    live = torch.tensor([0, 2, 3, 4], device=DEV)
+    assert torch.allclose(rsum[live], ref_sum[live], rtol=tol, atol=tol)
+    assert torch.equal(rsum[1], rsum0[1])
+    assert torch.allclose(dots[live], ref[live], rtol=100 * tol, atol=100 * tol * float(ref.abs().max()))
+    # masked row copy
+    dst = torch.zeros(C, D, device=DEV, dtype=dtype)
+    mask = torch.tensor([1, 0, 0, 1, 0], device=DEV, dtype=torch.bool)
+    k._rows_copy(dst, z0, mask)
+    assert torch.equal(dst[mask], z0[mask]) and float(dst[~mask].abs().max()) == 0.0
 
 
 def test_fused_leaf_nuts_eight_schools_posterior():
