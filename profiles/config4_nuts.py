@@ -24,8 +24,18 @@ sig = (5 + 15 * torch.rand(J, generator=g)).to(dev)
 yy = (5 + 3 * torch.randn(J, generator=g)).to(dev) + sig * torch.randn(J, generator=g).to(dev)
 k = NUTS(potential_fn=HierNormalPotential(yy, sig, 10.0, 25.0), native_small=False, max_tree_depth=depth,
          fused_leaf=fused)
-mc = MCMC(k, num_samples=S, warmup_steps=W, num_chains=C, seed=0)
+import time  # noqa: E402
+marks = []
+
+
+def hook(kernel, z, stage, t):
+    torch.cuda.synchronize(dev)
+    marks.append((stage, t, time.perf_counter(), kernel.leapfrog_count()))
+
+
+mc = MCMC(k, num_samples=S, warmup_steps=W, num_chains=C, seed=0, hook_fn=hook if os.environ.get("B2_TRACE") else None)
 torch.cuda.synchronize(dev)
+t_start = time.perf_counter()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 mc.run()
@@ -33,6 +43,12 @@ e1.record()
 e1.synchronize()
 n = k.leapfrog_count()
 sec = e0.elapsed_time(e1) * 1e-3
+if marks:
+    prev_t, prev_n = t_start, 0
+    for stage, t, tm, nl in marks:
+        print("%s %d: %.1f ms, %d chain-leapfrogs (%.1f k/s)" % (stage, t, (tm - prev_t) * 1e3, nl - prev_n,
+                                                                 (nl - prev_n) / max(tm - prev_t, 1e-9) / 1e3))
+        prev_t, prev_n = tm, nl
 print(json.dumps({"config": "hier_normal J=1e6", "chains": C, "transitions": W + S, "max_tree_depth": depth,
                   "fused_leaf": fused, "chain_leapfrogs": n, "seconds": round(sec, 3),
                   "chain_leapfrog_per_sec": round(n / sec, 1),
