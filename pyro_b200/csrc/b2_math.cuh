@@ -153,11 +153,14 @@ B2_HD float fast_log1p_unit(float e) {
 }
 B2_HD double fast_log1p_unit(double e) { return log1p(e); }
 
-// lgamma(x) and digamma(x) for fp32, x > 0, sharing one upward shift to x >= 8 and Stirling /
-// asymptotic series (absolute error ~1e-6 for lgamma, relative ~1e-6 for digamma; inside the fp32
-// tolerance).  libm's lgammaf alone is ~100 instructions and made the Gamma/Beta/Poisson kernels
-// issue-bound at 10-25% of HBM peak (profiles/micro_logprob_r1_before_fastgamma.txt).
-// Non-positive arguments (never produced by valid parameters) take the accurate route.
+// lgamma(x), digamma(x) (and trigamma(x)) for fp32, x > 0: ONE upward shift by 4 when x < 4, then the
+// Stirling / asymptotic series at x >= 4 (truncation below 7e-8 there).  The shift is closed form:
+//   p = x(x+3),  (x)(x+1)(x+2)(x+3) = p(p+2),   sum_{i<4} 1/(x+i) = (2x+3)(2p+2) / (p(p+2))
+// so lgamma + digamma cost two logs and two reciprocals in total (libm's lgammaf alone is ~100
+// instructions and made the Gamma/Beta/Poisson kernels issue-bound at 10-25% of HBM peak,
+// profiles/micro_logprob_r1_before_fastgamma.txt; a per-unit shift loop to x >= 8 still left Gamma at
+// 44%).  Absolute error ~1e-6 for lgamma, relative ~1e-6 for digamma / trigamma: inside the fp32
+// tolerance.  Non-positive arguments (never produced by valid parameters) take the accurate route.
 template <bool WANT_PSI, bool WANT_TRI>
 B2_HD void lgamma_polygamma_f32(float x, float& lg, float& psi, float& tri) {
   if (!(x > 0.f) || x > 1e30f) {
@@ -166,20 +169,24 @@ B2_HD void lgamma_polygamma_f32(float x, float& lg, float& psi, float& tri) {
     if (WANT_TRI) tri = x - x == 0.f ? 1.f / (x * x) : x;  // invalid concentration: inf / NaN
     return;
   }
-  float prod = 1.f, acc = 0.f, acc2 = 0.f;
+  const bool shift = x < 4.f;
+  const float p = x * (x + 3.f);
+  const float prod = shift ? p * (p + 2.f) : 1.f;
+  float acc = 0.f, acc2 = 0.f;
+  if (WANT_PSI) {
+    const float rp = fast_rcp(prod);
+    acc = shift ? -(2.f * x + 3.f) * (2.f * p + 2.f) * rp : 0.f;
+  }
+  if (WANT_TRI) {
+    if (shift) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool small = x < 8.f;
-    if (small) {
-      prod *= x;
-      if (WANT_PSI || WANT_TRI) {
-        const float r = fast_rcp(x);
-        if (WANT_PSI) acc -= r;
-        if (WANT_TRI) acc2 += r * r;
+      for (int i = 0; i < 4; ++i) {
+        const float r = fast_rcp(x + (float)i);
+        acc2 += r * r;
       }
-      x += 1.f;
     }
   }
+  x = shift ? x + 4.f : x;
   const float lx = fast_log(x);
   const float inv = fast_rcp(x);
   const float inv2 = inv * inv;
@@ -396,6 +403,18 @@ struct Eval<kBeta, T, GRAD> {
     lgamma_digamma<T, GRAD>(c1 + c0, lgs, psum);
     lgamma_digamma<T, GRAD>(c1, lg1, ps1);
     lgamma_digamma<T, GRAD>(c0, lg0, ps0);
+    if (sizeof(T) == 4) {
+      const T lx = fast_log(x), l1 = fast_log(omx);
+      // xlogy semantics: a zero coefficient contributes 0 even when the log is -inf
+      o.lp = (((c1 == (T)1) ? (T)0 : (c1 - (T)1) * lx) + ((c0 == (T)1) ? (T)0 : (c0 - (T)1) * l1)) +
+             lgs - (lg1 + lg0);
+      if (GRAD) {
+        o.dx = (c1 - (T)1) * fast_rcp(x) - (c0 - (T)1) * fast_rcp(omx);
+        o.dp[0] = lx + psum - ps1;
+        o.dp[1] = l1 + psum - ps0;
+      }
+      return;
+    }
     o.lp = (xlogy(c1 - (T)1, x) + xlogy(c0 - (T)1, omx)) + lgs - (lg1 + lg0);
     if (GRAD) {
       o.dx = (c1 - (T)1) / x - (c0 - (T)1) / omx;

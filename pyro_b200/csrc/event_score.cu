@@ -50,6 +50,13 @@ __device__ __forceinline__ void batch_offsets(const EventArgs& a, int64_t row, i
                                               int64_t& op0, int64_t& op1, int64_t& om, int64_t& ou,
                                               int64_t& olp, int64_t& ogx, int64_t& ogp0,
                                               int64_t& ogp1) {
+  if (a.ndim <= 1) {
+    // the common case after the host merged the batch dims: one multiply per operand, no division
+    ox = row * a.x.st[0]; op0 = row * a.p0.st[0]; op1 = row * a.p1.st[0]; om = row * a.mask.st[0];
+    ou = row * a.up.st[0]; olp = row * a.lp.st[0]; ogx = row * a.gx.st[0]; ogp0 = row * a.gp0.st[0];
+    ogp1 = row * a.gp1.st[0];
+    return;
+  }
   ox = op0 = op1 = om = ou = olp = ogx = ogp0 = ogp1 = 0;
   int64_t rem = row;
   for (int d = a.ndim - 1; d >= 0; --d) {
@@ -96,7 +103,7 @@ __global__ void __launch_bounds__(256) dirichlet_kernel(const EventArgs a) {
     T s_xlogy = 0, s_conc = 0, s_lg = 0;
     for (int k = lane; k < a.K; k += G) {
       const T c = cp[op0 + k], x = xp[ox + k];
-      s_xlogy += xlogy(c - (T)1, x);
+      s_xlogy += (sizeof(T) == 4) ? ((c - (T)1 == (T)0) ? (T)0 : (c - (T)1) * fast_log(x)) : xlogy(c - (T)1, x);
       s_conc += c;
       T lgc, unused;
       lgamma_digamma<T, false>(c, lgc, unused);
@@ -172,6 +179,99 @@ __global__ void __launch_bounds__(256) categorical_kernel(const EventArgs a) {
         const T sm = b2_exp(lg[op0 + k] - lse);
         reinterpret_cast<T*>(a.gp0.ptr)[ogp0 + k] = m ? f * (((int64_t)k == v ? (T)1 : (T)0) - sm) : (T)0;
       }
+    }
+  }
+  __shared__ double smem[32];
+  double red[1] = {(double)acc};
+  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
+}
+
+// ---- small event sizes (K <= 32), batch dims merged to one: ONE THREAD PER ROW ----------------------
+// A row is K consecutive elements per operand, so a warp covers 32 consecutive rows = one contiguous
+// span of memory: every fetched line is fully used (through L1 across the k loop), the K special
+// functions of a row are independent work for one thread (ILP without shuffles), and there is no
+// per-row integer division.  The sub-warp-group kernels above measured 7-12% of the HBM peak at
+// K = 8 (profiles/micro_logprob_r1.txt).
+template <typename T>
+B2_HD T xlogy_fast(T c, T x) {
+  if (sizeof(T) == 4) return (c == (T)0) ? (T)0 : c * fast_log(x);
+  return xlogy(c, x);
+}
+
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(256) dirichlet_rowthread_kernel(const EventArgs a) {
+  const T* __restrict__ xp = reinterpret_cast<const T*>(a.x.ptr);
+  const T* __restrict__ cp = reinterpret_cast<const T*>(a.p0.ptr);
+  const int K = a.K;
+  T acc = (T)0;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.nbatch;
+       row += (int64_t)gridDim.x * blockDim.x) {
+    const T* x = xp + row * a.x.st[0];
+    const T* c = cp + row * a.p0.st[0];
+    T s_xlogy = 0, s_conc = 0, s_lg = 0;
+    for (int k = 0; k < K; ++k) {
+      const T ck = c[k];
+      s_xlogy += xlogy_fast(ck - (T)1, x[k]);
+      s_conc += ck;
+      T lgc, unused;
+      lgamma_digamma<T, false>(ck, lgc, unused);
+      s_lg += lgc;
+    }
+    T lgsum, psum;
+    lgamma_digamma<T, GRAD>(s_conc, lgsum, psum);
+    const T lp = s_xlogy + lgsum - s_lg;
+    const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[row * a.mask.st[0]] != 0 : true;
+    const T slp = m ? lp * (T)a.scale : (T)0;
+    acc += slp;
+    if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[row * a.lp.st[0]] = slp;
+    if (GRAD) {
+      T f = m ? (T)(a.weight * a.scale) : (T)0;
+      if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[row * a.up.st[0]];
+      T* gx = a.gx.ptr ? reinterpret_cast<T*>(a.gx.ptr) + row * a.gx.st[0] : nullptr;
+      T* gc = a.gp0.ptr ? reinterpret_cast<T*>(a.gp0.ptr) + row * a.gp0.st[0] : nullptr;
+      for (int k = 0; k < K; ++k) {
+        const T ck = c[k], xk = x[k];
+        if (gx) gx[k] = m ? f * (ck - (T)1) * fast_rcp(xk) : (T)0;
+        if (gc) {
+          T lgc, psc;
+          lgamma_digamma<T, true>(ck, lgc, psc);
+          gc[k] = m ? f * (fast_log(xk) + psum - psc) : (T)0;
+        }
+      }
+    }
+  }
+  __shared__ double smem[32];
+  double red[1] = {(double)acc};
+  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
+}
+
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(256) categorical_rowthread_kernel(const EventArgs a) {
+  const int64_t* __restrict__ vp = reinterpret_cast<const int64_t*>(a.x.ptr);
+  const T* __restrict__ lgp = reinterpret_cast<const T*>(a.p0.ptr);
+  const int K = a.K;
+  T acc = (T)0;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.nbatch;
+       row += (int64_t)gridDim.x * blockDim.x) {
+    const T* lg = lgp + row * a.p0.st[0];
+    T mx = -b2_inf<T>();
+    for (int k = 0; k < K; ++k) mx = b2_max(mx, lg[k]);
+    T se = 0;
+    for (int k = 0; k < K; ++k) se += fast_exp(lg[k] - mx);
+    const T lse = mx + fast_log(se);
+    const int64_t v = vp[row * a.x.st[0]];
+    const bool inb = v >= 0 && v < K;
+    const T lp = inb ? lg[inb ? v : 0] - lse : b2_nan<T>();
+    const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[row * a.mask.st[0]] != 0 : true;
+    const T slp = m ? lp * (T)a.scale : (T)0;
+    acc += slp;
+    if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[row * a.lp.st[0]] = slp;
+    if (GRAD && a.gp0.ptr) {
+      T f = m ? (T)(a.weight * a.scale) : (T)0;
+      if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[row * a.up.st[0]];
+      T* g = reinterpret_cast<T*>(a.gp0.ptr) + row * a.gp0.st[0];
+      for (int k = 0; k < K; ++k)
+        g[k] = m ? f * (((int64_t)k == v ? (T)1 : (T)0) - fast_exp(lg[k] - lse)) : (T)0;
     }
   }
   __shared__ double smem[32];
@@ -380,7 +480,8 @@ extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tenso
   a.out_sum = out_sum;
   a.partials = ws_partials(workspace);
   a.ticket = ws_ticket(workspace);
-  // drop size-1 batch dims (no merging: rows are decoded by division anyway)
+  // drop size-1 batch dims, then merge adjacent dims that every operand walks jointly (contiguous or
+  // jointly broadcast): the usual [rows] or [P, rows] batch becomes ONE dim, decoded by a multiply
   int cd = 0;
   int64_t nb = 1;
   int keep[B2_MAX_DIMS];
@@ -389,30 +490,48 @@ extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tenso
     if (value->shape[d] != 1) keep[cd++] = d;
   }
   if (cd > kMaxD) return B2_ERR_BAD_SHAPE;
+  const b2_tensor* ops[9] = {value, &params[0], n_params > 1 ? &params[1] : nullptr, mask, upstream,
+                             out_logprob, out_dvalue, out_dparams ? &out_dparams[0] : nullptr,
+                             (out_dparams && n_params > 1) ? &out_dparams[1] : nullptr};
+  int64_t shp[B2_MAX_DIMS], ost[9][B2_MAX_DIMS];
+  for (int i = 0; i < cd; ++i) {
+    shp[i] = value->shape[keep[i]];
+    for (int o = 0; o < 9; ++o) ost[o][i] = (ops[o] && ops[o]->ptr) ? ops[o]->stride[keep[i]] : 0;
+  }
+  for (int d = cd - 2; d >= 0; --d) {
+    bool ok = true;
+    for (int o = 0; o < 9 && ok; ++o) ok = ost[o][d] == ost[o][d + 1] * shp[d + 1];
+    if (!ok) continue;
+    shp[d] *= shp[d + 1];
+    for (int o = 0; o < 9; ++o) ost[o][d] = ost[o][d + 1];
+    for (int e = d + 1; e < cd - 1; ++e) {
+      shp[e] = shp[e + 1];
+      for (int o = 0; o < 9; ++o) ost[o][e] = ost[o][e + 1];
+    }
+    --cd;
+  }
   a.ndim = cd;
   a.nbatch = nb;
-  for (int i = 0; i < cd; ++i) a.shape[i] = value->shape[keep[i]];
-  auto fin = [&](EvOpnd& o, const b2_tensor* t) {
-    if (!t || !t->ptr) return;
-    o.ptr = t->ptr;
-    for (int i = 0; i < cd; ++i) o.st[i] = t->stride[keep[i]];
+  for (int i = 0; i < cd; ++i) a.shape[i] = shp[i];
+  auto fin = [&](EvOpnd& o, int k) {
+    if (!ops[k] || !ops[k]->ptr) return;
+    o.ptr = ops[k]->ptr;
+    for (int i = 0; i < cd; ++i) o.st[i] = ost[k][i];
   };
-  auto fout = [&](EvOut& o, const b2_tensor* t) {
-    if (!t || !t->ptr) return;
-    o.ptr = t->ptr;
-    for (int i = 0; i < cd; ++i) o.st[i] = t->stride[keep[i]];
+  auto fout = [&](EvOut& o, int k) {
+    if (!ops[k] || !ops[k]->ptr) return;
+    o.ptr = ops[k]->ptr;
+    for (int i = 0; i < cd; ++i) o.st[i] = ost[k][i];
   };
-  fin(a.x, value);
-  fin(a.p0, &params[0]);
-  if (n_params > 1) fin(a.p1, &params[1]);
-  fin(a.mask, mask);
-  fin(a.up, upstream);
-  fout(a.lp, out_logprob);
-  fout(a.gx, out_dvalue);
-  if (out_dparams) {
-    fout(a.gp0, &out_dparams[0]);
-    if (n_params > 1) fout(a.gp1, &out_dparams[1]);
-  }
+  fin(a.x, 0);
+  fin(a.p0, 1);
+  fin(a.p1, 2);
+  fin(a.mask, 3);
+  fin(a.up, 4);
+  fout(a.lp, 5);
+  fout(a.gx, 6);
+  fout(a.gp0, 7);
+  fout(a.gp1, 8);
   if (mask && mask->ptr && mask->dtype != B2_U8) return B2_ERR_BAD_DTYPE;
   const bool grad = a.gx.ptr || a.gp0.ptr || a.gp1.ptr;
   int lg = 0;
@@ -433,7 +552,14 @@ extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tenso
     if (grad) KERNEL<double, true><<<(unsigned)blocks, 256, 0, s>>>(a);             \
     else KERNEL<double, false><<<(unsigned)blocks, 256, 0, s>>>(a);                 \
   }
-  if (family == B2_DIRICHLET) { B2_EV_LAUNCH(dirichlet_kernel) }
+  const bool rowthread = cd <= 1 && event_size <= 32 && nb >= 4096 && family != B2_MVN_TRIL;
+  if (rowthread) {
+    blocks = (nb + 255) / 256;
+    if (blocks > cap * 2) blocks = cap * 2;
+    if (family == B2_DIRICHLET) { B2_EV_LAUNCH(dirichlet_rowthread_kernel) }
+    else { B2_EV_LAUNCH(categorical_rowthread_kernel) }
+  }
+  else if (family == B2_DIRICHLET) { B2_EV_LAUNCH(dirichlet_kernel) }
   else if (family == B2_CATEGORICAL) { B2_EV_LAUNCH(categorical_kernel) }
   else { B2_EV_LAUNCH(mvn_tril_kernel) }
 #undef B2_EV_LAUNCH

@@ -290,3 +290,42 @@ def test_elbo_combine(dtype):
     ref = sum(c * float(t.double()) for c, t in zip(coeffs, terms))
     assert out.shape == () and out.dtype == dtype
     assert abs(float(out) - ref) <= (1e-6 if dtype == torch.float32 else 1e-14) * abs(ref)
+
+
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-11, 1e-9), (torch.float32, 2e-5, 3e-4)])
+@pytest.mark.parametrize("K", [3, 8, 17])
+def test_event_families_row_per_thread_kernels(K, dtype, tol, gtol):
+    """Dirichlet / Categorical with many rows and a small event size take the one-thread-per-row
+    kernels (the reference fixtures, a few dozen rows, exercise the sub-warp-group kernels): log_prob,
+    fused sum and gradients against the oracle, including a concentration broadcast over the rows and
+    a [P, rows] batch that the host merges into one dim."""
+    torch.manual_seed(K)
+    rows = 5000
+    conc = (0.3 + 2 * torch.rand(rows, K)).to(DEV, dtype)
+    x = torch.distributions.Dirichlet(torch.ones(K)).sample((rows,)).clamp(min=1e-4).to(DEV, dtype)
+    x = x / x.sum(-1, keepdim=True)
+    for c in (conc, conc[0]):
+        cr = c.clone().requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        lp = dist.Dirichlet(cr).log_prob(xr)
+        co = c.double().cpu().requires_grad_(True)
+        xo = x.double().cpu().requires_grad_(True)
+        ref = odists.dirichlet(xo, co)
+        _close(lp, ref.detach(), tol)
+        w = torch.randn(rows, dtype=torch.float64)
+        g = torch.autograd.grad((lp * w.to(DEV, dtype)).sum(), [xr, cr])
+        go = torch.autograd.grad((ref * w).sum(), [xo, co])
+        _close(g[0], go[0], gtol)
+        _close(g[1], go[1], gtol * (1 if c.dim() == 2 else rows ** 0.5))
+    logits = torch.randn(2, rows, K).to(DEV, dtype)
+    idx = torch.randint(0, K, (2, rows), device=DEV)
+    lr = logits.clone().requires_grad_(True)
+    lp = dist.Categorical(logits=lr).log_prob(idx)
+    lo = logits.double().cpu().requires_grad_(True)
+    ref = odists.categorical(idx.cpu(), lo)
+    _close(lp, ref.detach(), tol)
+    (g,) = torch.autograd.grad(lp.sum(), lr)
+    (go,) = torch.autograd.grad(ref.sum(), lo)
+    _close(g, go, gtol)
+    s = dist.Categorical(logits=logits)._fused_sum(idx, None, 1.0, 1.0, 1.0, True)
+    assert abs(float(s) - float(ref.sum())) <= 20 * tol * abs(float(ref.sum()))
