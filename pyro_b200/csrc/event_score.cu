@@ -441,6 +441,266 @@ __global__ void reduce_to_finish_kernel(const ReduceArgs a) {
   reinterpret_cast<T*>(a.dst)[dof] = (T)s;
 }
 
+
+// ---- larger event sizes (K a multiple of 4, rows 16-byte aligned): 16-byte loads, two rows per group in
+// flight.  G = min(32, K/4) lanes own a row, each lane walks float4 / double2 chunks; one iteration
+// of a group handles rows (row, row + ngroups) so two independent chains of loads / special functions /
+// shuffles overlap.  The scalar group kernels measured 9-13% of the HBM peak at K = 64.
+template <typename T>
+struct RowVec {
+  static constexpr int V = VecOf<T>::N;
+};
+
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(256) dirichlet_vec_kernel(const EventArgs a) {
+  constexpr int V = VecOf<T>::N;
+  const int G = 1 << a.g_log2;
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> a.g_log2;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) >> a.g_log2;
+  const T* xp = reinterpret_cast<const T*>(a.x.ptr);
+  const T* cp = reinterpret_cast<const T*>(a.p0.ptr);
+  const int KV = a.K / V;
+  const int64_t nrows_pad = ((a.nbatch + 2 * ngroups - 1) / (2 * ngroups)) * (2 * ngroups);
+  T acc = (T)0;
+  for (int64_t row0 = gid; row0 < nrows_pad; row0 += 2 * ngroups) {
+    T s_xlogy[2] = {0, 0}, s_conc[2] = {0, 0}, s_lg[2] = {0, 0};
+    bool live[2];
+    int64_t rows[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      rows[u] = row0 + u * ngroups;
+      live[u] = rows[u] < a.nbatch;
+      if (!live[u]) rows[u] = 0;
+    }
+    for (int kv = lane; kv < KV; kv += G) {
+      Pack<T> cv[2], xv[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        cv[u] = ld_stream(cp + rows[u] * a.p0.st[0] + kv * V);
+        xv[u] = ld_stream(xp + rows[u] * a.x.st[0] + kv * V);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const T c = cv[u].v[j];
+          s_xlogy[u] += xlogy_fast(c - (T)1, xv[u].v[j]);
+          s_conc[u] += c;
+          T lgc, unused;
+          lgamma_digamma<T, false>(c, lgc, unused);
+          s_lg[u] += lgc;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      s_xlogy[u] = group_sum(s_xlogy[u], G);
+      s_conc[u] = group_sum(s_conc[u], G);
+      s_lg[u] = group_sum(s_lg[u], G);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t row = rows[u];
+      T lgsum, psum;
+      lgamma_digamma<T, GRAD>(s_conc[u], lgsum, psum);
+      const T lp = s_xlogy[u] + lgsum - s_lg[u];
+      const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[row * a.mask.st[0]] != 0 : true;
+      const T slp = (m && live[u]) ? lp * (T)a.scale : (T)0;
+      if (lane == 0 && live[u]) {
+        acc += slp;
+        if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[row * a.lp.st[0]] = slp;
+      }
+      if (GRAD && live[u]) {
+        T f = m ? (T)(a.weight * a.scale) : (T)0;
+        if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[row * a.up.st[0]];
+        for (int kv = lane; kv < KV; kv += G) {
+          const Pack<T> cv = ld_keep(cp + row * a.p0.st[0] + kv * V);
+          const Pack<T> xv = ld_keep(xp + row * a.x.st[0] + kv * V);
+          Pack<T> gxv, gcv;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const T c = cv.v[j], x = xv.v[j];
+            gxv.v[j] = m ? f * (c - (T)1) * fast_rcp(x) : (T)0;
+            T lgc, psc;
+            lgamma_digamma<T, true>(c, lgc, psc);
+            gcv.v[j] = m ? f * (fast_log(x) + psum - psc) : (T)0;
+          }
+          if (a.gx.ptr) st_stream(reinterpret_cast<T*>(a.gx.ptr) + row * a.gx.st[0] + kv * V, gxv);
+          if (a.gp0.ptr) st_stream(reinterpret_cast<T*>(a.gp0.ptr) + row * a.gp0.st[0] + kv * V, gcv);
+        }
+      }
+    }
+  }
+  __shared__ double smem[32];
+  double red[1] = {(double)acc};
+  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
+}
+
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(256) categorical_vec_kernel(const EventArgs a) {
+  constexpr int V = VecOf<T>::N;
+  const int G = 1 << a.g_log2;
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> a.g_log2;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) >> a.g_log2;
+  const int64_t* vp = reinterpret_cast<const int64_t*>(a.x.ptr);
+  const T* lgp = reinterpret_cast<const T*>(a.p0.ptr);
+  const int KV = a.K / V;
+  const int64_t nrows_pad = ((a.nbatch + 2 * ngroups - 1) / (2 * ngroups)) * (2 * ngroups);
+  T acc = (T)0;
+  for (int64_t row0 = gid; row0 < nrows_pad; row0 += 2 * ngroups) {
+    bool live[2];
+    int64_t rows[2];
+    T mx[2], se[2] = {0, 0};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      rows[u] = row0 + u * ngroups;
+      live[u] = rows[u] < a.nbatch;
+      if (!live[u]) rows[u] = 0;
+      mx[u] = -b2_inf<T>();
+    }
+    // online logsumexp: one pass over the logits (running max + rescaled sum), then a group merge
+    for (int kv = lane; kv < KV; kv += G) {
+      Pack<T> lv[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) lv[u] = ld_keep(lgp + rows[u] * a.p0.st[0] + kv * V);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        T cm = lv[u].v[0];
+#pragma unroll
+        for (int j = 1; j < V; ++j) cm = b2_max(cm, lv[u].v[j]);
+        const T nm = b2_max(mx[u], cm);
+        T s = (mx[u] == -b2_inf<T>()) ? (T)0 : se[u] * fast_exp(mx[u] - nm);
+#pragma unroll
+        for (int j = 0; j < V; ++j) s += fast_exp(lv[u].v[j] - nm);
+        se[u] = s;
+        mx[u] = nm;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const T gm = group_max(mx[u], G);
+      const T part = (mx[u] == -b2_inf<T>()) ? (T)0 : se[u] * fast_exp(mx[u] - gm);
+      se[u] = group_sum(part, G);
+      mx[u] = gm;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t row = rows[u];
+      const T* lg = lgp + row * a.p0.st[0];
+      const T lse = mx[u] + fast_log(se[u]);
+      const int64_t v = vp[row * a.x.st[0]];
+      const bool inb = v >= 0 && v < a.K;
+      const T lp = inb ? lg[inb ? v : 0] - lse : b2_nan<T>();
+      const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[row * a.mask.st[0]] != 0 : true;
+      const T slp = (m && live[u]) ? lp * (T)a.scale : (T)0;
+      if (lane == 0 && live[u]) {
+        acc += slp;
+        if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[row * a.lp.st[0]] = slp;
+      }
+      if (GRAD && live[u] && a.gp0.ptr) {
+        T f = m ? (T)(a.weight * a.scale) : (T)0;
+        if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[row * a.up.st[0]];
+        for (int kv = lane; kv < KV; kv += G) {
+          const Pack<T> lv = ld_keep(lg + kv * V);
+          Pack<T> gv;
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+            gv.v[j] = m ? f * (((int64_t)(kv * V + j) == v ? (T)1 : (T)0) - fast_exp(lv.v[j] - lse)) : (T)0;
+          st_stream(reinterpret_cast<T*>(a.gp0.ptr) + row * a.gp0.st[0] + kv * V, gv);
+        }
+      }
+    }
+  }
+  __shared__ double smem[32];
+  double red[1] = {(double)acc};
+  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
+}
+
+// ---- MVN, event size n <= 8: one thread per row ------------------------------------------------------
+// The warp-per-row kernel above spends 32 lanes and n warp reductions on a 2x2 .. 8x8 triangular
+// solve (1.5-4% of the HBM peak, profiles/micro_logprob_r1.txt).  For small n the whole solve fits
+// one thread's registers: z = L^-1 (x - mu) by forward substitution, w = L^-T z by back substitution,
+// all loops fully unrolled over NMAX with predicates on the runtime n; a warp covers 32 consecutive
+// rows, i.e. one contiguous span of each operand.
+template <typename T, bool GRAD, int NMAX>
+__global__ void __launch_bounds__(256) mvn_rowthread_kernel(const EventArgs a) {
+  const T* __restrict__ xp = reinterpret_cast<const T*>(a.x.ptr);
+  const T* __restrict__ mup = reinterpret_cast<const T*>(a.p0.ptr);
+  const T* __restrict__ Lp = reinterpret_cast<const T*>(a.p1.ptr);
+  const int n = a.K;
+  T acc = (T)0;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.nbatch;
+       row += (int64_t)gridDim.x * blockDim.x) {
+    const T* x = xp + row * a.x.st[0];
+    const T* mu = mup + row * a.p0.st[0];
+    const T* L = Lp + row * a.p1.st[0];
+    T z[NMAX], inv[NMAX];
+    T logdet = 0, m2 = 0;
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) {
+      z[i] = (T)0;
+      inv[i] = (T)0;
+      if (i < n) {
+        T part = x[i] - mu[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) part -= L[i * n + j] * z[j];
+        const T lii = L[i * n + i];
+        inv[i] = (T)1 / lii;
+        z[i] = part * inv[i];
+        logdet += (sizeof(T) == 4) ? fast_log(lii) : b2_log(lii);
+        m2 += z[i] * z[i];
+      }
+    }
+    const T lp = (T)-0.5 * ((T)n * ((T)2 * Consts<T>::kLogSqrt2Pi) + m2) - logdet;
+    const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[row * a.mask.st[0]] != 0 : true;
+    const T slp = m ? lp * (T)a.scale : (T)0;
+    acc += slp;
+    if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[row * a.lp.st[0]] = slp;
+    if (GRAD) {
+      T f = m ? (T)(a.weight * a.scale) : (T)0;
+      if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[row * a.up.st[0]];
+      T w[NMAX];
+#pragma unroll
+      for (int i = NMAX - 1; i >= 0; --i) {
+        w[i] = (T)0;
+        if (i < n) {
+          T part = z[i];
+#pragma unroll
+          for (int j = i + 1; j < NMAX; ++j)
+            if (j < n) part -= L[j * n + i] * w[j];
+          w[i] = part * inv[i];
+        }
+      }
+      T* gx = a.gx.ptr ? reinterpret_cast<T*>(a.gx.ptr) + row * a.gx.st[0] : nullptr;
+      T* gm = a.gp0.ptr ? reinterpret_cast<T*>(a.gp0.ptr) + row * a.gp0.st[0] : nullptr;
+      T* gL = a.gp1.ptr ? reinterpret_cast<T*>(a.gp1.ptr) + row * a.gp1.st[0] : nullptr;
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) {
+        if (i < n) {
+          if (gx) gx[i] = m ? -f * w[i] : (T)0;
+          if (gm) gm[i] = m ? f * w[i] : (T)0;
+          if (gL) {
+#pragma unroll
+            for (int j = 0; j < NMAX; ++j) {
+              if (j < n) {
+                T g = (T)0;
+                if (j < i) g = w[i] * z[j];
+                else if (j == i) g = w[i] * z[j] - inv[i];
+                gL[i * n + j] = m ? f * g : (T)0;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __shared__ double smem[32];
+  double red[1] = {(double)acc};
+  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -553,7 +813,42 @@ extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tenso
     else KERNEL<double, false><<<(unsigned)blocks, 256, 0, s>>>(a);                 \
   }
   const bool rowthread = cd <= 1 && event_size <= 32 && nb >= 4096 && family != B2_MVN_TRIL;
-  if (rowthread) {
+  // 16-byte path: event size a multiple of the vector width, every row of every float operand 16-byte aligned
+  bool vec_rows_ok = event_size > 32 && cd <= 1;
+  {
+    const int V = (dtype == B2_F32) ? 4 : 2;
+    if (event_size % V != 0) vec_rows_ok = false;
+    auto al = [&](const void* p, int64_t st) {
+      return !p || (reinterpret_cast<uintptr_t>(p) % 16 == 0 && st % V == 0);
+    };
+    vec_rows_ok = vec_rows_ok && al(a.p0.ptr, a.p0.st[0]) && al(a.gp0.ptr, a.gp0.st[0]);
+    if (family == B2_DIRICHLET) vec_rows_ok = vec_rows_ok && al(a.x.ptr, a.x.st[0]) && al(a.gx.ptr, a.gx.st[0]);
+  }
+  if (family == B2_MVN_TRIL && cd <= 1 && event_size <= 8 && nb >= 1024) {
+    blocks = (nb + 255) / 256;
+    if (blocks > cap * 2) blocks = cap * 2;
+    if (dtype == B2_F32) {
+      if (grad) mvn_rowthread_kernel<float, true, 8><<<(unsigned)blocks, 256, 0, s>>>(a);
+      else mvn_rowthread_kernel<float, false, 8><<<(unsigned)blocks, 256, 0, s>>>(a);
+    } else {
+      if (grad) mvn_rowthread_kernel<double, true, 8><<<(unsigned)blocks, 256, 0, s>>>(a);
+      else mvn_rowthread_kernel<double, false, 8><<<(unsigned)blocks, 256, 0, s>>>(a);
+    }
+  }
+  else if (family != B2_MVN_TRIL && cd <= 1 && !rowthread && vec_rows_ok) {
+    // lanes per row: K/V chunks, at most a warp
+    int lgv = 0;
+    const int V = (dtype == B2_F32) ? 4 : 2;
+    while (lgv < 5 && (1 << lgv) < event_size / V) ++lgv;
+    a.g_log2 = lgv;
+    const int64_t rpb = 256 >> lgv;
+    blocks = (nb + 2 * rpb - 1) / (2 * rpb);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (family == B2_DIRICHLET) { B2_EV_LAUNCH(dirichlet_vec_kernel) }
+    else { B2_EV_LAUNCH(categorical_vec_kernel) }
+  }
+  else if (rowthread) {
     blocks = (nb + 255) / 256;
     if (blocks > cap * 2) blocks = cap * 2;
     if (family == B2_DIRICHLET) { B2_EV_LAUNCH(dirichlet_rowthread_kernel) }

@@ -293,14 +293,14 @@ def test_elbo_combine(dtype):
 
 
 @pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-11, 1e-9), (torch.float32, 2e-5, 3e-4)])
-@pytest.mark.parametrize("K", [3, 8, 17])
-def test_event_families_row_per_thread_kernels(K, dtype, tol, gtol):
+@pytest.mark.parametrize("K,rows", [(3, 5000), (8, 5000), (17, 5000), (64, 700), (100, 300), (1000, 70)])
+def test_event_families_row_per_thread_kernels(K, rows, dtype, tol, gtol):
     """Dirichlet / Categorical with many rows and a small event size take the one-thread-per-row
     kernels (the reference fixtures, a few dozen rows, exercise the sub-warp-group kernels): log_prob,
     fused sum and gradients against the oracle, including a concentration broadcast over the rows and
-    a [P, rows] batch that the host merges into one dim."""
+    a [P, rows] batch that the host merges into one dim.  K > 32 (a multiple of 4) takes the 16-byte
+    vector kernels, two rows in flight per lane group."""
     torch.manual_seed(K)
-    rows = 5000
     conc = (0.3 + 2 * torch.rand(rows, K)).to(DEV, dtype)
     x = torch.distributions.Dirichlet(torch.ones(K)).sample((rows,)).clamp(min=1e-4).to(DEV, dtype)
     x = x / x.sum(-1, keepdim=True)
@@ -329,3 +329,29 @@ def test_event_families_row_per_thread_kernels(K, dtype, tol, gtol):
     _close(g, go, gtol)
     s = dist.Categorical(logits=logits)._fused_sum(idx, None, 1.0, 1.0, 1.0, True)
     assert abs(float(s) - float(ref.sum())) <= 20 * tol * abs(float(ref.sum()))
+
+
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-11, 1e-9), (torch.float32, 2e-5, 5e-4)])
+@pytest.mark.parametrize("n", [1, 2, 5, 8])
+def test_mvn_row_per_thread_kernel(n, dtype, tol, gtol):
+    """MultivariateNormal(scale_tril) with event size <= 8 and many rows: one thread per row (forward and
+    back substitution in registers) against the oracle, per-row and row-broadcast parameters."""
+    torch.manual_seed(n)
+    rows = 3000
+    A = torch.randn(rows, n, n)
+    L = torch.linalg.cholesky(A @ A.transpose(-1, -2) + n * torch.eye(n)).to(DEV, dtype)
+    mu = torch.randn(rows, n).to(DEV, dtype)
+    x = torch.randn(rows, n).to(DEV, dtype)
+    for mu_, L_ in ((mu, L), (mu[0], L[0])):
+        mr, Lr, xr = (t.clone().requires_grad_(True) for t in (mu_, L_, x))
+        lp = dist.MultivariateNormal(mr, scale_tril=Lr).log_prob(xr)
+        mo, Lo, xo = (t.double().cpu().requires_grad_(True) for t in (mu_, L_, x))
+        ref = odists.mvn_tril(xo, mo, Lo)
+        _close(lp, ref.detach(), tol)
+        w = torch.randn(rows, dtype=torch.float64)
+        g = torch.autograd.grad((lp * w.to(DEV, dtype)).sum(), [xr, mr, Lr])
+        go = torch.autograd.grad((ref * w).sum(), [xo, mo, Lo])
+        red = 1 if mu_.dim() == 2 else rows ** 0.5
+        _close(g[0], go[0], gtol)
+        _close(g[1], go[1], gtol * red)
+        _close(g[2], torch.tril(go[2]), gtol * red)
