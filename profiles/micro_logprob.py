@@ -74,7 +74,7 @@ for K in (8, 64, 1024):
     idx = torch.randint(0, K, (rows,), device=dev)
     timed("Categorical K=%d log_prob" % K, lambda: dist.Categorical(logits=logits).log_prob(idx), rows * (4 * K + 12))
 for n in (2, 8, 32):
-    rows = (1 << 22) // n
+    rows = (1 << 25) // (n * n)
     A = torch.randn(rows, n, n, device=dev)
     L = torch.linalg.cholesky(A @ A.transpose(-1, -2) + n * torch.eye(n, device=dev))
     mu, xv = torch.randn(rows, n, device=dev), torch.randn(rows, n, device=dev)

@@ -209,13 +209,29 @@ __global__ void __launch_bounds__(256) dirichlet_rowthread_kernel(const EventArg
     const T* x = xp + row * a.x.st[0];
     const T* c = cp + row * a.p0.st[0];
     T s_xlogy = 0, s_conc = 0, s_lg = 0;
-    for (int k = 0; k < K; ++k) {
-      const T ck = c[k];
-      s_xlogy += xlogy_fast(ck - (T)1, x[k]);
-      s_conc += ck;
-      T lgc, unused;
-      lgamma_digamma<T, false>(ck, lgc, unused);
-      s_lg += lgc;
+    if (a.g_log2 == 1) {
+      // rows are 16-byte aligned and K is a multiple of the vector width: one 16-byte load per chunk
+      constexpr int V = VecOf<T>::N;
+      for (int k = 0; k < K; k += V) {
+        const Pack<T> cv = ld_stream(c + k), xv = ld_stream(x + k);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          s_xlogy += xlogy_fast(cv.v[j] - (T)1, xv.v[j]);
+          s_conc += cv.v[j];
+          T lgc, unused;
+          lgamma_digamma<T, false>(cv.v[j], lgc, unused);
+          s_lg += lgc;
+        }
+      }
+    } else {
+      for (int k = 0; k < K; ++k) {
+        const T ck = c[k];
+        s_xlogy += xlogy_fast(ck - (T)1, x[k]);
+        s_conc += ck;
+        T lgc, unused;
+        lgamma_digamma<T, false>(ck, lgc, unused);
+        s_lg += lgc;
+      }
     }
     T lgsum, psum;
     lgamma_digamma<T, GRAD>(s_conc, lgsum, psum);
@@ -255,9 +271,26 @@ __global__ void __launch_bounds__(256) categorical_rowthread_kernel(const EventA
        row += (int64_t)gridDim.x * blockDim.x) {
     const T* lg = lgp + row * a.p0.st[0];
     T mx = -b2_inf<T>();
-    for (int k = 0; k < K; ++k) mx = b2_max(mx, lg[k]);
     T se = 0;
-    for (int k = 0; k < K; ++k) se += fast_exp(lg[k] - mx);
+    if (a.g_log2 == 1) {
+      // 16-byte loads, online logsumexp over the chunks (one pass over the row)
+      constexpr int V = VecOf<T>::N;
+      for (int k = 0; k < K; k += V) {
+        const Pack<T> lv = ld_keep(lg + k);
+        T cm = lv.v[0];
+#pragma unroll
+        for (int j = 1; j < V; ++j) cm = b2_max(cm, lv.v[j]);
+        const T nm = b2_max(mx, cm);
+        T sacc = (k == 0) ? (T)0 : se * fast_exp(mx - nm);
+#pragma unroll
+        for (int j = 0; j < V; ++j) sacc += fast_exp(lv.v[j] - nm);
+        se = sacc;
+        mx = nm;
+      }
+    } else {
+      for (int k = 0; k < K; ++k) mx = b2_max(mx, lg[k]);
+      for (int k = 0; k < K; ++k) se += fast_exp(lg[k] - mx);
+    }
     const T lse = mx + fast_log(se);
     const int64_t v = vp[row * a.x.st[0]];
     const bool inb = v >= 0 && v < K;
@@ -701,6 +734,98 @@ __global__ void __launch_bounds__(256) mvn_rowthread_kernel(const EventArgs a) {
   grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
 }
 
+
+// ---- MVN, 8 < n <= 32: one warp per row, the factor in registers ---------------------------------------
+// Lane j preloads COLUMN j of the row's scale_tril with n coalesced loads issued back to back
+// (Lc[r] = L[r][j]; identity outside n), so the triangular solves never wait on memory:
+//   forward  z = L^-1 (x - mu): pivot i needs <L[i][:i], z[:i]> = warp_sum(Lc[i] * z) over lanes < i;
+//            lane i then finishes z_i locally (it holds L_ii and its own residual);
+//   backward w = L^-T z: lane i accumulates s_i = sum_{j>i} L[j][i] w_j from ITS OWN column, one
+//            broadcast of w_j per pivot;
+//   dL[i][j] = f (w_i z_j - [i==j]/L_ii), written by column owners (coalesced rows).
+// The generic kernel above reloads L from memory inside the dependent pivot loop (7% of HBM at n=32).
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(256) mvn_warp32_kernel(const EventArgs a) {
+  constexpr int N = 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int n = a.K;
+  const T* xp = reinterpret_cast<const T*>(a.x.ptr);
+  const T* mup = reinterpret_cast<const T*>(a.p0.ptr);
+  const T* Lp = reinterpret_cast<const T*>(a.p1.ptr);
+  const int64_t nrows_pad = ((a.nbatch + nwarps - 1) / nwarps) * nwarps;
+  const bool in = lane < n;
+  T acc = (T)0;
+  for (int64_t row = wid; row < nrows_pad; row += nwarps) {
+    const bool live = row < a.nbatch;
+    int64_t ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1;
+    batch_offsets(a, live ? row : 0, ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1);
+    const T* L = Lp + op1;
+    T Lc[N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) Lc[r] = (r < n && in && lane <= r) ? L[(int64_t)r * n + lane] : ((r == lane) ? (T)1 : (T)0);
+    const T b = in ? xp[ox + lane] - mup[op0 + lane] : (T)0;
+    // diagonal of this lane's column index
+    T dg = (T)1;
+#pragma unroll
+    for (int r = 0; r < N; ++r) dg = (r == lane) ? Lc[r] : dg;
+    const T idg = (T)1 / dg;
+    T z = (T)0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (i < n) {  // uniform
+        const T part = warp_sum((lane < i) ? Lc[i] * z : (T)0);
+        if (lane == i) z = (b - part) * idg;
+      }
+    }
+    const T m2 = warp_sum(in ? z * z : (T)0);
+    const T logdet = warp_sum(in ? ((sizeof(T) == 4) ? fast_log(dg) : b2_log(dg)) : (T)0);
+    const T lp = (T)-0.5 * ((T)n * ((T)2 * Consts<T>::kLogSqrt2Pi) + m2) - logdet;
+    const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
+    const T slp = (m && live) ? lp * (T)a.scale : (T)0;
+    if (lane == 0 && live) {
+      acc += slp;
+      if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[olp] = slp;
+    }
+    if (GRAD) {
+      T f = m ? (T)(a.weight * a.scale) : (T)0;
+      if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[ou];
+      T s = (T)0, w = (T)0;
+#pragma unroll
+      for (int j = N - 1; j >= 0; --j) {
+        if (j < n) {
+          if (lane == j) w = (z - s) * idg;
+          const T wj = __shfl_sync(0xffffffffu, w, j);
+          if (lane < j) s += Lc[j] * wj;  // Lc[j] on lane i is L[j][i]
+        }
+      }
+      if (live && in) {
+        if (a.gx.ptr) reinterpret_cast<T*>(a.gx.ptr)[ogx + lane] = m ? -f * w : (T)0;
+        if (a.gp0.ptr) reinterpret_cast<T*>(a.gp0.ptr)[ogp0 + lane] = m ? f * w : (T)0;
+      }
+      if (a.gp1.ptr) {
+        T* gL = reinterpret_cast<T*>(a.gp1.ptr) + ogp1;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if (i < n) {
+            const T wi = __shfl_sync(0xffffffffu, w, i);
+            if (live && in) {
+              T g = (T)0;
+              if (lane < i) g = wi * z;
+              else if (lane == i) g = wi * z - idg;
+              gL[(int64_t)i * n + lane] = m ? f * g : (T)0;
+            }
+          }
+        }
+      }
+    }
+  }
+  __shared__ double smem[32];
+  double red[1] = {(double)acc};
+  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -835,6 +960,12 @@ extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tenso
       else mvn_rowthread_kernel<double, false, 8><<<(unsigned)blocks, 256, 0, s>>>(a);
     }
   }
+  else if (family == B2_MVN_TRIL && event_size <= 32) {
+    blocks = (nb + 7) / 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    B2_EV_LAUNCH(mvn_warp32_kernel)
+  }
   else if (family != B2_MVN_TRIL && cd <= 1 && !rowthread && vec_rows_ok) {
     // lanes per row: K/V chunks, at most a warp
     int lgv = 0;
@@ -849,6 +980,16 @@ extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tenso
     else { B2_EV_LAUNCH(categorical_vec_kernel) }
   }
   else if (rowthread) {
+    {
+      // g_log2 doubles as the "16-byte rows" flag of the row-per-thread kernels
+      const int V = (dtype == B2_F32) ? 4 : 2;
+      auto al = [&](const void* p, int64_t st) {
+        return !p || (reinterpret_cast<uintptr_t>(p) % 16 == 0 && st % V == 0);
+      };
+      bool v16 = event_size % V == 0 && al(a.p0.ptr, a.p0.st[0]);
+      if (family == B2_DIRICHLET) v16 = v16 && al(a.x.ptr, a.x.st[0]);
+      a.g_log2 = v16 ? 1 : 0;
+    }
     blocks = (nb + 255) / 256;
     if (blocks > cap * 2) blocks = cap * 2;
     if (family == B2_DIRICHLET) { B2_EV_LAUNCH(dirichlet_rowthread_kernel) }

@@ -332,10 +332,11 @@ def test_event_families_row_per_thread_kernels(K, rows, dtype, tol, gtol):
 
 
 @pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-11, 1e-9), (torch.float32, 2e-5, 5e-4)])
-@pytest.mark.parametrize("n", [1, 2, 5, 8])
+@pytest.mark.parametrize("n", [1, 2, 5, 8, 12, 32])
 def test_mvn_row_per_thread_kernel(n, dtype, tol, gtol):
-    """MultivariateNormal(scale_tril) with event size <= 8 and many rows: one thread per row (forward and
-    back substitution in registers) against the oracle, per-row and row-broadcast parameters."""
+    """MultivariateNormal(scale_tril) with many rows: event size <= 8 takes one thread per row (forward
+    and back substitution in registers), 8 < n <= 32 one warp per row with the factor's columns in
+    registers; against the oracle, per-row and row-broadcast parameters."""
     torch.manual_seed(n)
     rows = 3000
     A = torch.randn(rows, n, n)
