@@ -76,7 +76,9 @@ for K in (8, 64, 1024):
 for n in (2, 8, 32):
     rows = (1 << 25) // (n * n)
     A = torch.randn(rows, n, n, device=dev)
-    L = torch.linalg.cholesky(A @ A.transpose(-1, -2) + n * torch.eye(n, device=dev))
+    # cholesky returns column-major matrices; the kernels want row-major events (a one-off copy here, not timed)
+    L = torch.linalg.cholesky(A @ A.transpose(-1, -2) + n * torch.eye(n, device=dev)).contiguous()
+    assert L.stride()[-1] == 1
     mu, xv = torch.randn(rows, n, device=dev), torch.randn(rows, n, device=dev)
     timed("MVN n=%d log_prob (per-row scale_tril)" % n, lambda: dist.MultivariateNormal(mu, scale_tril=L).log_prob(xv),
           rows * (4 * n * n + 8 * n + 4))

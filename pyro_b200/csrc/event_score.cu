@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(256) categorical_rowthread_kernel(const EventA
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.nbatch;
        row += (int64_t)gridDim.x * blockDim.x) {
     const T* lg = lgp + row * a.p0.st[0];
+    const int64_t v = vp[row * a.x.st[0]];  // issued first: overlaps the logits loads
     T mx = -b2_inf<T>();
     T se = 0;
     if (a.g_log2 == 1) {
@@ -292,7 +293,6 @@ __global__ void __launch_bounds__(256) categorical_rowthread_kernel(const EventA
       for (int k = 0; k < K; ++k) se += fast_exp(lg[k] - mx);
     }
     const T lse = mx + fast_log(se);
-    const int64_t v = vp[row * a.x.st[0]];
     const bool inb = v >= 0 && v < K;
     const T lp = inb ? lg[inb ? v : 0] - lse : b2_nan<T>();
     const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[row * a.mask.st[0]] != 0 : true;
@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(256) dirichlet_vec_kernel(const EventArgs a) {
 template <typename T, bool GRAD>
 __global__ void __launch_bounds__(256) categorical_vec_kernel(const EventArgs a) {
   constexpr int V = VecOf<T>::N;
+  constexpr int UR = 4;  // rows in flight per lane group
   const int G = 1 << a.g_log2;
   const int lane = threadIdx.x & (G - 1);
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> a.g_log2;
@@ -580,26 +581,28 @@ __global__ void __launch_bounds__(256) categorical_vec_kernel(const EventArgs a)
   const int64_t* vp = reinterpret_cast<const int64_t*>(a.x.ptr);
   const T* lgp = reinterpret_cast<const T*>(a.p0.ptr);
   const int KV = a.K / V;
-  const int64_t nrows_pad = ((a.nbatch + 2 * ngroups - 1) / (2 * ngroups)) * (2 * ngroups);
+  const int64_t nrows_pad = ((a.nbatch + UR * ngroups - 1) / (UR * ngroups)) * (UR * ngroups);
   T acc = (T)0;
-  for (int64_t row0 = gid; row0 < nrows_pad; row0 += 2 * ngroups) {
-    bool live[2];
-    int64_t rows[2];
-    T mx[2], se[2] = {0, 0};
+  for (int64_t row0 = gid; row0 < nrows_pad; row0 += UR * ngroups) {
+    bool live[UR];
+    int64_t rows[UR], vidx[UR];
+    T mx[UR], se[UR];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UR; ++u) {
       rows[u] = row0 + u * ngroups;
       live[u] = rows[u] < a.nbatch;
       if (!live[u]) rows[u] = 0;
       mx[u] = -b2_inf<T>();
+      se[u] = (T)0;
+      vidx[u] = vp[rows[u] * a.x.st[0]];  // issued first: overlaps the logits stream
     }
     // online logsumexp: one pass over the logits (running max + rescaled sum), then a group merge
     for (int kv = lane; kv < KV; kv += G) {
-      Pack<T> lv[2];
+      Pack<T> lv[UR];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) lv[u] = ld_keep(lgp + rows[u] * a.p0.st[0] + kv * V);
+      for (int u = 0; u < UR; ++u) lv[u] = ld_keep(lgp + rows[u] * a.p0.st[0] + kv * V);
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < UR; ++u) {
         T cm = lv[u].v[0];
 #pragma unroll
         for (int j = 1; j < V; ++j) cm = b2_max(cm, lv[u].v[j]);
@@ -612,18 +615,18 @@ __global__ void __launch_bounds__(256) categorical_vec_kernel(const EventArgs a)
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UR; ++u) {
       const T gm = group_max(mx[u], G);
       const T part = (mx[u] == -b2_inf<T>()) ? (T)0 : se[u] * fast_exp(mx[u] - gm);
       se[u] = group_sum(part, G);
       mx[u] = gm;
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UR; ++u) {
       const int64_t row = rows[u];
       const T* lg = lgp + row * a.p0.st[0];
       const T lse = mx[u] + fast_log(se[u]);
-      const int64_t v = vp[row * a.x.st[0]];
+      const int64_t v = vidx[u];
       const bool inb = v >= 0 && v < a.K;
       const T lp = inb ? lg[inb ? v : 0] - lse : b2_nan<T>();
       const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[row * a.mask.st[0]] != 0 : true;
@@ -973,7 +976,8 @@ extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tenso
     while (lgv < 5 && (1 << lgv) < event_size / V) ++lgv;
     a.g_log2 = lgv;
     const int64_t rpb = 256 >> lgv;
-    blocks = (nb + 2 * rpb - 1) / (2 * rpb);
+    const int64_t ur = (family == B2_DIRICHLET) ? 2 : 4;  // rows in flight per lane group
+    blocks = (nb + ur * rpb - 1) / (ur * rpb);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (family == B2_DIRICHLET) { B2_EV_LAUNCH(dirichlet_vec_kernel) }
