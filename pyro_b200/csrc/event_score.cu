@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(256) dirichlet_vec_kernel(const EventArgs a) {
 template <typename T, bool GRAD>
 __global__ void __launch_bounds__(256) categorical_vec_kernel(const EventArgs a) {
   constexpr int V = VecOf<T>::N;
-  constexpr int UR = 4;  // rows in flight per lane group
+  constexpr int UR = 2;  // rows in flight per lane group (4 measured slower: 57% -> 41% at K = 1024)
   const int G = 1 << a.g_log2;
   const int lane = threadIdx.x & (G - 1);
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> a.g_log2;
@@ -976,7 +976,7 @@ extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tenso
     while (lgv < 5 && (1 << lgv) < event_size / V) ++lgv;
     a.g_log2 = lgv;
     const int64_t rpb = 256 >> lgv;
-    const int64_t ur = (family == B2_DIRICHLET) ? 2 : 4;  // rows in flight per lane group
+    const int64_t ur = 2;  // rows in flight per lane group (both kernels)
     blocks = (nb + ur * rpb - 1) / (ur * rpb);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
