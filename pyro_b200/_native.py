@@ -181,6 +181,7 @@ def stream_ptr(device=None):
 
 # ---- per-(device, stream) zero-initialised reduction workspace --------------------------------
 _workspaces = {}
+_retired = []
 
 
 def workspace(device, nbytes=None, tag="reduce"):
@@ -196,6 +197,8 @@ def workspace(device, nbytes=None, tag="reduce"):
         if capturing():
             raise RuntimeError("pyro_b200: workspace must be allocated before CUDA graph capture; "
                                "run one eager step first")
+        if ws is not None:
+            _retired.append(ws)   # captured CUDA graphs may still hold the old buffer's address
         ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws

@@ -81,7 +81,9 @@ def reduce_to(src, dst):
     dv = dst.reshape(_pad_shape(dst.shape, nd))
     sd = N.desc(src, shape)
     dd = N.desc(dv.expand(shape) if tuple(dv.shape) != shape else dv, shape)
-    ws = N.workspace(src.device)
+    # column reductions split the reduced rows over CTAs and keep [splits, numel(dst)] fp64 partials
+    need = min(256 + 8 * dst.numel() * 32, 64 << 20)
+    ws = N.workspace(src.device, max(need, int(N.lib().b2_site_score_workspace())))
     N.check(N.lib().b2_reduce_to(ctypes.byref(sd), ctypes.byref(dd), ws.data_ptr(), ws.numel(),
                                  N.stream_ptr(src.device)), "b2_reduce_to")
 

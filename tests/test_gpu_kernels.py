@@ -149,7 +149,9 @@ def test_kl_kernels(site_kernels, dtype, tol, gtol):
 
 
 @pytest.mark.parametrize("shape,dst_shape", [((7, 5, 3), (5, 3)), ((7, 5, 3), (7, 1, 3)), ((6, 4), (1, 4)),
-                                             ((1000, 33), (33,)), ((3, 100000), (3, 1)), ((64, 1, 32), (32,))])
+                                             ((1000, 33), (33,)), ((3, 100000), (3, 1)), ((64, 1, 32), (32,)),
+                                             ((300, 1000), (1000,)), ((64, 40, 50), (40, 50)), ((7, 5, 4096), (4096,)),
+                                             ((256, 61440), (61440,))])
 def test_reduce_to(shape, dst_shape):
     torch.manual_seed(0)
     src = torch.randn(shape, device=DEV, dtype=torch.float64)
