@@ -30,10 +30,10 @@ class TraceMeanField_ELBO(Trace_ELBO):
             loss = self.loss_and_grads_tensor(model, guide, *args, _no_backward=True, **kwargs)
         loss = torch_item(loss)
         warn_if_nan(loss, "loss")
-        return loss
+        return loss if loss is not None else 0.0
 
     def _mean_field_particle(self, model_trace, guide_trace):
-        """(elbo 0-d tensor, [unit-upstream terms])"""
+        """(loss contribution ``-elbo/P`` as a 0-d tensor, [unit-upstream terms])"""
         P = self.num_particles
         terms, elbo_terms = [], []
 
@@ -84,26 +84,26 @@ class TraceMeanField_ELBO(Trace_ELBO):
                         elbo_terms.append(c * lp.detach())
                         if lp.requires_grad:
                             terms.append((-c / P) * lp)
-        if len(elbo_terms) > 1:
-            elbo = torch.stack([e.reshape(()) for e in elbo_terms]).sum()
-        elif elbo_terms:
-            elbo = elbo_terms[0].reshape(())
-        else:
-            elbo = torch.zeros(())
-        return elbo, terms
+        if not elbo_terms:
+            return torch.zeros(()), terms
+        # loss contribution -elbo/P assembled on the device in one launch (b2_elbo_combine)
+        from ..distributions import _ops
+        ref = elbo_terms[0]
+        parts = [e.reshape(()).to(ref.dtype) if e.dtype != ref.dtype else e.reshape(()) for e in elbo_terms]
+        return _ops.elbo_combine(parts, [-1.0 / P] * len(parts)), terms
 
     def loss_and_grads_tensor(self, model, guide, *args, _no_backward=False, **kwargs):
-        loss = 0.0
+        loss = None
         for model_trace, guide_trace in self._get_traces(model, guide, args, kwargs):
             for name, site in guide_trace.nodes.items():
                 if site["type"] == "sample" and not getattr(site["fn"], "has_rsample", False):
                     raise ValueError("TraceMeanField_ELBO requires fully reparameterised guides; "
                                      "site '{}' is not".format(name))
-            elbo, terms = self._mean_field_particle(model_trace, guide_trace)
-            loss = loss + (-elbo / self.num_particles)
+            loss_particle, terms = self._mean_field_particle(model_trace, guide_trace)
+            loss = loss_particle if loss is None else loss + loss_particle
             trainable = any(site["type"] == "param" for trace in (model_trace, guide_trace)
                             for site in trace.nodes.values())
             if trainable and terms and not _no_backward:
                 from .trace_elbo import _one_like
                 torch.autograd.backward(terms, [_one_like(t) for t in terms], retain_graph=self.retain_graph)
-        return loss
+        return loss if loss is not None else 0.0
