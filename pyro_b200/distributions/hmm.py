@@ -43,11 +43,12 @@ class GaussianHMM(Distribution):
     support = constraints.independent(constraints.real, 2)
 
     def __init__(self, initial_dist, transition_matrix, transition_dist, observation_matrix,
-                 observation_dist, validate_args=None, duration=None, tf32=False):
+                 observation_dist, validate_args=None, duration=None, tf32=False, steady_state=True):
         hidden_dim, obs_dim = observation_matrix.shape[-2:]
         self.hidden_dim, self.obs_dim = hidden_dim, obs_dim
         self.duration = duration
         self.tf32 = tf32
+        self.steady_state = steady_state   # time-invariant parameters: blocked scan after the covariance converges
         self._m0, self._P0 = _loc_cov(initial_dist)
         self._F = transition_matrix
         self._bw, self._Q = _loc_cov(transition_dist)
@@ -83,9 +84,104 @@ class GaussianHMM(Distribution):
         old = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = bool(self.tf32)
         try:
+            if self.steady_state and T >= 64 and value.dim() == 2 and self._homogeneous():
+                return self._filter_steady(value, T)
             return self._filter(value, T)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = old
+
+    def _homogeneous(self):
+        """Time-invariant, unbatched parameters (BASELINE config 3): the covariance recursion does not
+        see the data and converges to the stationary Riccati solution."""
+        return (len(self.batch_shape) == 0 and self._m0.dim() == 1 and self._P0.dim() == 2
+                and self._F.dim() == 2 and self._H.dim() == 2 and self._bw.dim() == 1 and self._bv.dim() == 1
+                and self._Q.dim() == 2 and self._R.dim() == 2)
+
+    def _filter_steady(self, value, T):
+        """Same marginal likelihood for time-invariant parameters in two phases.
+
+        Phase 1 runs the exact recursion of ``_filter`` until the predicted covariance stops changing
+        (relative max-norm change <= 1e-13 in fp64, 3e-7 in fp32 -- below the rounding of the sum it
+        feeds).  From there the gain K, the innovation covariance S and the closed-loop matrix
+        ``A = (I - H K) F`` are constants, so the predicted means obey the LINEAR recurrence
+        ``m_{t+1} = m_t A + u_t`` with ``u_t = (x_t - b_v) K F + b_w``: phase 2 evaluates it as a
+        blocked scan -- B dense steps shared by all blocks, a carry over the block starts with A^B, and
+        one batched product with the stored powers -- i.e. O(sqrt(T)) sequential GEMMs instead of T
+        steps of ~20 small kernels.  The H^3 FLOPs of the skipped covariance steps are NOT performed
+        (report them as skipped, not as achieved)."""
+        F, Hm, bw, bv, Q, R = self._F, self._H, self._bw, self._bv, self._Q, self._R
+        O, Hd = self.obs_dim, self.hidden_dim
+        const = O * math.log(2 * math.pi)
+        tol = 1e-13 if value.dtype == torch.float64 else 3e-7
+        m = self._m0.unsqueeze(0)             # [1, H] predicted/filtered mean (row vector)
+        P = self._P0
+        ll = value.new_zeros(())
+        Pm_prev = None
+        t = 0
+        converged = False
+        while t < T:
+            m = m @ F + bw
+            Pm = F.transpose(-1, -2) @ P @ F + Q
+            if Pm_prev is not None and t >= 4:
+                with torch.no_grad():
+                    rel = float((Pm - Pm_prev).abs().max() / Pm.abs().max().clamp(min=1e-300))
+                if rel <= tol:
+                    converged = True
+                    break
+            PH = Pm @ Hm
+            S = Hm.transpose(-1, -2) @ PH + R
+            v = value[t:t + 1, :] - (m @ Hm + bv)
+            Ls = torch.linalg.cholesky(S)
+            vs = torch.linalg.solve_triangular(Ls, v.transpose(-1, -2), upper=False)
+            ll = ll - 0.5 * ((vs * vs).sum() + const) - Ls.diagonal().log().sum()
+            Kt = torch.cholesky_solve(PH.transpose(-1, -2), Ls)
+            m = m + v @ Kt
+            P = Pm - PH @ Kt
+            P = 0.5 * (P + P.transpose(-1, -2))
+            Pm_prev = Pm
+            t += 1
+        if not converged:
+            return ll
+        # ---- stationary phase: m holds the predicted mean of step t, Pm the stationary covariance ----
+        rem = T - t
+        PH = Pm @ Hm
+        S = Hm.transpose(-1, -2) @ PH + R
+        Ls = torch.linalg.cholesky(S)
+        Kt = torch.cholesky_solve(PH.transpose(-1, -2), Ls)            # [O, H]
+        KF = Kt @ F                                                    # [O, H]
+        A = F - Hm @ KF                                                # (I - H K) F
+        X = value[t:] - bv                                             # [rem, O]
+        U = X @ KF + bw                                                # [rem, H]
+        B = max(8, int(math.ceil(math.sqrt(rem))))
+        nblk = (rem + B - 1) // B
+        pad = nblk * B - rem
+        if pad:
+            U = torch.cat([U, U.new_zeros(pad, Hd)], dim=0)
+        Ub = U.reshape(nblk, B, Hd)
+        # local solutions with zero start, all blocks at once; powers of A alongside
+        w = U.new_zeros(nblk, Hd)
+        ap = torch.eye(Hd, dtype=A.dtype, device=A.device)
+        Ws, APs = [], []
+        for j in range(B):
+            Ws.append(w)
+            APs.append(ap)
+            w = w @ A + Ub[:, j]
+            ap = ap @ A
+        W = torch.stack(Ws, dim=1)                                     # [nblk, B, H]
+        AP = torch.stack(APs, dim=0)                                   # [B, H, H], AP[j] = A^j
+        AB = ap                                                        # A^B
+        starts = []
+        s_b = m                                                        # [1, H]
+        for b in range(nblk):
+            starts.append(s_b)
+            s_b = s_b @ AB + w[b:b + 1]
+        S0 = torch.cat(starts, dim=0)                                  # [nblk, H]
+        M = torch.einsum("bh,jhk->bjk", S0, AP) + W                    # predicted means [nblk, B, H]
+        M = M.reshape(nblk * B, Hd)[:rem]
+        V = X - M @ Hm                                                 # innovations [rem, O]
+        vs = torch.linalg.solve_triangular(Ls, V.transpose(-1, -2), upper=False)
+        ll = ll - 0.5 * ((vs * vs).sum() + rem * const) - rem * Ls.diagonal().log().sum()
+        return ll
 
     def _filter(self, value, T):
         O = self.obs_dim

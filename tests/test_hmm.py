@@ -44,3 +44,40 @@ def test_gaussian_hmm_matches_reference_cpu(tag):
 def test_gaussian_hmm_matches_reference_gpu(tag, dtype, tol):
     from conftest import device
     _run(tag, device(), dtype, tol)
+
+
+def _steady_vs_sequential(device, dtype, H, O, T, tol, gtol):
+    torch.manual_seed(H)
+    F = (0.5 * torch.randn(H, H, dtype=dtype) / H ** 0.5).to(device).requires_grad_(True)
+    Hm = torch.randn(H, O, dtype=dtype).to(device).requires_grad_(True)
+    tsc = (torch.randn(H, dtype=dtype) * 0.1).exp().to(device).requires_grad_(True)
+    osc = (torch.randn(O, dtype=dtype) * 0.1).exp().to(device).requires_grad_(True)
+    isc = torch.ones(H, dtype=dtype, device=device).requires_grad_(True)
+    bw = (0.1 * torch.randn(H, dtype=dtype)).to(device).requires_grad_(True)
+    data = torch.randn(T, O, dtype=dtype).to(device)
+    z = lambda n: torch.zeros(n, dtype=dtype, device=device)  # noqa: E731
+    out = []
+    for steady in (True, False):
+        d = dist.GaussianHMM(dist.Normal(z(H), isc).to_event(1), F, dist.Normal(bw, tsc).to_event(1), Hm,
+                             dist.Normal(z(O), osc).to_event(1), duration=T, steady_state=steady)
+        lp = d.log_prob(data)
+        out.append((float(lp), torch.autograd.grad(lp, [F, Hm, tsc, osc, isc, bw])))
+    (a, ga), (b, gb) = out
+    assert abs(a - b) <= tol * abs(b), (a, b)
+    for x, y in zip(ga, gb):
+        assert float((x - y).abs().max()) <= gtol * float(y.abs().max().clamp(min=1.0))
+
+
+@pytest.mark.parametrize("H,O,T", [(6, 2, 700), (12, 3, 1000), (5, 1, 64)])
+def test_steady_state_scan_equals_sequential_filter_cpu(H, O, T):
+    """Time-invariant parameters (BASELINE config 3's case): once the predicted covariance has converged
+    the filter switches to a blocked linear scan of the means; value and all parameter gradients equal
+    the step-by-step recursion (itself pinned against the reference by the goldens above)."""
+    _steady_vs_sequential("cpu", torch.float64, H, O, T, 1e-11, 1e-8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-11, 1e-8), (torch.float32, 1e-4, 2e-3)])
+def test_steady_state_scan_equals_sequential_filter_gpu(dtype, tol, gtol):
+    from conftest import device
+    _steady_vs_sequential(device(), dtype, 16, 3, 1200, tol, gtol)
