@@ -96,6 +96,7 @@ class SVI:
 
     def _eager_step(self, args, kwargs, want_tensor=False):
         loss, params = self._grads(args, kwargs, want_tensor)
+        self._last_params = params
         loss = self._allreduce(params, loss)
         self.optim(params)  # fused update; zeroes the gradients in the same pass
         return loss
@@ -196,16 +197,34 @@ class SVI:
             self._graph = graph
             self._graph_state = {"static_args": static_args, "loss": loss}
         else:
-            # the collective stays outside the graphs: capture the two halves around it
+            # The collective stays outside the graphs: capture the two halves around it.  The
+            # gradients are re-pointed to views of ONE flat buffer [loss, grad_1 .. grad_n], so the
+            # backward pass accumulates straight into the all-reduce payload and the optimiser reads
+            # it back in place -- no pack / unpack copies on either side of the collective.
             world = self._world()
+            live = [p for p in self._last_params if p.grad is not None]   # from the warm-up step above
+            total = 1 + sum(p.grad.numel() for p in live)
+            flat = torch.zeros(total, dtype=live[0].grad.dtype, device=dev)
+            off = 1
+            for p in live:
+                n = p.grad.numel()
+                p.grad = flat[off:off + n].view(p.grad.shape)
+                off += n
+            # one eager step on the new gradient storage: the optimiser rebuilds its pointer tables
+            # now, not during capture
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._eager_step(tuple(static_args), {}, want_tensor=True)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
             with torch.cuda.graph(graph):
-                loss, params = self._grads(tuple(static_args), {}, True)
-                flat = self._pack(params, loss)
+                loss, params2 = self._grads(tuple(static_args), {}, True)
+                flat[0:1].copy_(loss.detach().reshape(1).to(flat.dtype))
             graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph_b, pool=graph.pool()):
                 flat /= world
-                out = self._unpack(params, flat).clone()
-                self.optim(params)
+                out = flat[0].clone()
+                self.optim(params2)
             self._graph = graph
             self._graph_state = {"static_args": static_args, "loss": out, "flat": flat, "graph_b": graph_b}
         self._steps_done += 1  # the warm-up step above was a real optimisation step
