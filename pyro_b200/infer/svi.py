@@ -191,9 +191,18 @@ class SVI:
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         if self._world() == 1:
+            flush = getattr(self.optim, "flush_pending", None)
             with torch.cuda.graph(graph):
+                if flush is not None:
+                    # no stored gradients during the captured backward: autograd hands each parameter
+                    # its fresh gradient tensor (no accumulate launch per parameter); the optimiser's
+                    # pointer table is re-pointed below
+                    for p in self._last_params:
+                        p.grad = None
                 loss = self._eager_step(tuple(static_args), {}, want_tensor=True)
                 loss = loss.reshape(()) if isinstance(loss, torch.Tensor) else torch.as_tensor(loss, device=dev)
+            if flush is not None:
+                flush()
             self._graph = graph
             self._graph_state = {"static_args": static_args, "loss": loss}
         else:

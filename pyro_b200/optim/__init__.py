@@ -91,6 +91,14 @@ class PyroOptim:
         if table is not None and table["key"] == key:
             return table
         if N.capturing():
+            # Same parameters, new gradient tensors: the captured step cleared ``.grad`` so that
+            # autograd ASSIGNS fresh gradients (graph-pool tensors with replay-stable addresses)
+            # instead of launching one accumulate kernel per parameter.  The kernels read the gradient
+            # pointers from the device table at replay time, so the table's contents are re-pointed
+            # right after capture (``flush_pending``); nothing executes during capture itself.
+            if table is not None and [k[:2] for k in table["key"]] == [k[:2] for k in key]:
+                table["pending"] = list(ps)
+                return table
             raise RuntimeError("pyro_b200.optim: parameter set changed during CUDA graph capture")
         if table is not None:
             self._sync_to_host(table)
@@ -109,6 +117,17 @@ class PyroOptim:
         self._fill_scalars(table)
         self._tables[dtype] = table
         return table
+
+    def flush_pending(self):
+        """After a CUDA-graph capture: point the device tables at the gradient tensors the captured
+        backward pass produced."""
+        for table in self._tables.values():
+            ps = table.pop("pending", None)
+            if ps is None:
+                continue
+            ptrs = torch.tensor([p.grad.data_ptr() for p in ps], dtype=torch.int64)
+            table["g"].copy_(ptrs.to(table["device"]))
+            table["key"] = self._table_key(ps)
 
     def _fill_scalars(self, table):
         raise NotImplementedError
