@@ -518,11 +518,6 @@ __global__ void reduce_to_finish_kernel(const ReduceArgs a) {
 // flight.  G = min(32, K/4) lanes own a row, each lane walks float4 / double2 chunks; one iteration
 // of a group handles rows (row, row + ngroups) so two independent chains of loads / special functions /
 // shuffles overlap.  The scalar group kernels measured 9-13% of the HBM peak at K = 64.
-template <typename T>
-struct RowVec {
-  static constexpr int V = VecOf<T>::N;
-};
-
 template <typename T, bool GRAD>
 __global__ void __launch_bounds__(256) dirichlet_vec_kernel(const EventArgs a) {
   constexpr int V = VecOf<T>::N;
