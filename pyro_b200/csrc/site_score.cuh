@@ -485,10 +485,16 @@ __global__ void __launch_bounds__(kSmallThreads) site_small_kernel(const SiteArg
     for (int k = 0; k < NRED; ++k) finish_outputs<T>(a, k, red[k]);
   }
   if (GRAD) {
-    if (a.gx.mode == 3) small_reduce_out<T>(a, a.gx, slab);
+    // ONE copy of the reduction code, looped over the outputs: these kernels run from a cold
+    // instruction cache (ncu: stall_no_inst on top), so a second inlined copy costs more than the loop
+#pragma unroll 1
+    for (int k = 0; k <= NP; ++k) {
+      OutOpnd o = a.gx;
 #pragma unroll
-    for (int k = 0; k < NP; ++k)
-      if (a.gp[k].mode == 3) small_reduce_out<T>(a, a.gp[k], slab + (size_t)(1 + k) * n);
+      for (int j = 0; j < NP; ++j)
+        if (k == j + 1) o = a.gp[j];
+      if (o.mode == 3) small_reduce_out<T>(a, o, slab + (size_t)k * n);
+    }
   }
 }
 
