@@ -193,7 +193,7 @@ def roofline_for(path, X, y, particles, flush):
             dist.Bernoulli(logits=dist.linear_predictor(X, w, b))._fused_sum(y, None, 1.0, -1.0 / P, 1.0, True)
         ms = kernel_time_ms(fn, 20, flush)
         alg = n * D_FEAT * 4 + n * 4  # X and y once, for value AND gradient
-        name = "glm_bernoulli_mma_kernel (+2 finish kernels)"
+        name = "glm_bernoulli_mma_kernel + glm_finish_kernel"
     else:
         logits = torch.randn(P, n, device=dev).requires_grad_(True)
 

@@ -321,16 +321,22 @@ class NUTS(HMC):
 
     # ---- lockstep tree on the fused leaf kernel (hierarchical-Normal model class, any J) -----------------
     def _leaf_hier(self, st, leaf):
-        """One new leaf for every active chain: b2_nuts_leaf_hier (two launches, no tensor ops)."""
+        """One new leaf for every active chain: b2_nuts_leaf_hier (two launches, no tensor ops).  The
+        per-call host work is one ctypes call; everything constant over a subtree is cached in ``st``."""
+        call = st.get("call")
+        if call is None:
+            lib = N.lib()
+            dev = self._z.device
+            ws = N.workspace(dev, int(lib.b2_nuts_leaf_hier_workspace(self.C, self.D - 2)), tag="mcmc")
+            call = st["call"] = (lib.b2_nuts_leaf_hier, ctypes.byref(self.potential._model), ctypes.byref(st["c"]),
+                                 ws.data_ptr(), ws.numel(), N.stream_ptr(dev), ws)
+        fn, model, cst, wptr, wn, stream, _ = call
         idx_max = _popcount(leaf >> 1)
         even = leaf % 2 == 0
         nblk = 0 if even else _trailing_ones(leaf)
-        lib = N.lib()
-        dev = self._z.device
-        ws = N.workspace(dev, int(lib.b2_nuts_leaf_hier_workspace(self.C, self.D - 2)), tag="mcmc")
-        N.check(lib.b2_nuts_leaf_hier(ctypes.byref(self.potential._model), ctypes.byref(st["c"]), leaf,
-                                      idx_max if even else -1, idx_max, nblk, ws.data_ptr(), ws.numel(),
-                                      N.stream_ptr(dev)), "b2_nuts_leaf_hier")
+        rc = fn(model, cst, leaf, idx_max if even else -1, idx_max, nblk, wptr, wn, stream)
+        if rc:
+            N.check(rc, "b2_nuts_leaf_hier")
 
     def _lockstep_struct(self, t):
         c = N.b2_nuts_lockstep()
