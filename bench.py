@@ -295,7 +295,8 @@ def nuts_section(dev, quick=False):
             torch.cuda.synchronize(dev)
             marks["t"], marks["n"] = time.perf_counter(), kernel.leapfrog_count()
 
-    mc = MCMC(k, num_samples=S, warmup_steps=W, num_chains=C, seed=0, hook_fn=hook)
+    # config 4 keeps only mu and tau; every site's running mean / variance is streamed on the device
+    mc = MCMC(k, num_samples=S, warmup_steps=W, num_chains=C, seed=0, hook_fn=hook, save_params=["mu", "tau"])
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     mc.run()
@@ -310,7 +311,8 @@ def nuts_section(dev, quick=False):
         "incl_warmup": {"leapfrogs": n, "seconds": round(t1 - t0, 3), "leapfrog_per_sec": round(n / (t1 - t0), 1)},
         "path": "lockstep iterative tree, every leaf = b2_nuts_leaf_hier (fused leapfrog with recomputed local "
                 "gradients + tree vectors + scalar logic, 2 launches, ~40 B moved per chain-element); root merge "
-                "and proposal hand-over = b2_nuts_tree_merge / b2_rows_copy_masked; %d sampling transitions after "
+                "and proposal hand-over = b2_nuts_tree_merge / b2_rows_copy_masked; save_params=[mu, tau] + streamed "
+                "per-chain mean/variance of every site; %d sampling transitions after "
                 "%d warm-up, max_tree_depth 6 (bounded sample of config 4)" % (S, W)}
     # CPU baseline: oracle restatement of the reference sampler, config 1, one chain
     torch.set_num_threads(1)
@@ -367,7 +369,7 @@ def nuts_multirank(dev, rank, world):
 
     def make4():
         k = NUTS(potential_fn=HierNormalPotential(yy, sig, 10.0, 25.0), native_small=False, max_tree_depth=6)
-        return k, MCMC(k, num_samples=4, warmup_steps=6, num_chains=C * world, seed=0)
+        return k, MCMC(k, num_samples=4, warmup_steps=6, num_chains=C * world, seed=0, save_params=["mu", "tau"])
     timed("hier_normal_J1e6_%dchains" % (C * world), make4, "weak: %d chains per rank, 10 transitions, max_tree_depth 6" % C)
     out["hier_normal_J1e6_%dchains" % (C * world)]["algorithmic_GBps"] = round(
         out["hier_normal_J1e6_%dchains" % (C * world)]["leapfrog_per_sec"] * 16e6 / 1e9, 1)

@@ -23,7 +23,7 @@ def _dist_info():
 class MCMC:
     def __init__(self, kernel, num_samples, warmup_steps=None, initial_params=None, num_chains=1,
                  hook_fn=None, mp_context=None, disable_progbar=True, disable_validation=True,
-                 transforms=None, save_params=None, seed=0):
+                 transforms=None, save_params=None, seed=0, streaming_stats=None):
         self.kernel = kernel
         self.num_samples = num_samples
         self.warmup_steps = warmup_steps if warmup_steps is not None else num_samples
@@ -31,6 +31,12 @@ class MCMC:
         self.initial_params = initial_params
         self.hook_fn = hook_fn
         self.save_params = save_params
+        # BASELINE config 4 cannot keep its samples (1024 chains x 200 x 1e6 floats = 819 GB): with
+        # ``save_params`` only those sites' columns are stored (pyro/infer/mcmc/api.py:465), and the
+        # per-chain running mean / M2 of EVERY site are kept on the device (Welford; the role of
+        # pyro/infer/mcmc/api.py:653-794 StreamingMCMC + pyro/ops/streaming.py)
+        self.streaming = bool(save_params) if streaming_stats is None else bool(streaming_stats)
+        self._stream = None
         self.seed = seed
         self._samples = None   # local [C_local, T, D]
         self._diagnostics = None
@@ -53,7 +59,16 @@ class MCMC:
             if self.hook_fn is not None:
                 self.hook_fn(k, z, "Warmup", t)
         T = self.num_samples
-        if isinstance(k, NUTS) and getattr(k, "_use_native", False) and self.hook_fn is None:
+        pot = k.potential
+        cols = None
+        if self.save_params is not None:
+            idx = [torch.arange(k.D)[pot.sites[name][0]] for name in self.save_params]
+            cols = torch.cat(idx).to(k._z.device)
+        if self.streaming:
+            self._stream = {name: None for name in pot.sites}
+            self._stream_n = 0
+        if (isinstance(k, NUTS) and getattr(k, "_use_native", False) and self.hook_fn is None
+                and cols is None and not self.streaming):
             samples, acc, depth, div, steps = k.sample_native(T, collect=True)
             k._leap_dev = steps.sum() if getattr(k, "_leap_dev", None) is None else k._leap_dev + steps.sum()
             k._divergences += (div > 0).sum(0)
@@ -61,15 +76,62 @@ class MCMC:
             k._t += T
             self._samples = samples.transpose(0, 1).contiguous()
         else:
-            out = torch.empty(T, C, k.D, dtype=k._z.dtype, device=k._z.device)
+            width = k.D if cols is None else cols.numel()
+            out = torch.empty(T, C, width, dtype=k._z.dtype, device=k._z.device)
             for t in range(T):
                 z = k.sample()
-                out[t] = z
+                out[t] = z if cols is None else z.index_select(-1, cols)
+                if self.streaming:
+                    self._stream_update(pot, z)
                 if self.hook_fn is not None:
                     self.hook_fn(k, z, "Sample", t)
             self._samples = out.transpose(0, 1).contiguous()
+        self._cols = cols
         self._diagnostics = k.diagnostics()
         return self
+
+    # ---- streaming statistics ------------------------------------------------------------------------
+    def _stream_update(self, pot, z):
+        """Welford update (pyro/ops/welford.py:7-51 per element) of every site's constrained value,
+        per chain: state (mean, M2) lives on the device, nothing is stored per sample."""
+        self._stream_n += 1
+        n = self._stream_n
+        for name, info in pot.sites.items():
+            v = pot.unpack_site(name, z[..., info[0]])
+            st = self._stream[name]
+            if st is None:
+                self._stream[name] = [v.clone(), torch.zeros_like(v)]
+                continue
+            mean, m2 = st
+            delta = v - mean
+            mean += delta / n
+            m2 += delta * (v - mean)
+
+    def streaming_stats(self, pooled=True):
+        """Running statistics of every site over the kept transitions.  ``pooled=False``: this rank's
+        per-chain ``{"mean", "variance"}`` ``[C_local, *site_shape]``.  ``pooled=True``: mean and
+        (unbiased) variance over ALL chains of ALL ranks, combined on the device from the per-chain
+        (n, mean, M2) with two all-reduces."""
+        if self._stream is None:
+            raise RuntimeError("run MCMC with save_params=... or streaming_stats=True first")
+        n = self._stream_n
+        out = {}
+        for name, (mean, m2) in self._stream.items():
+            if not pooled:
+                out[name] = {"mean": mean, "variance": m2 / max(n - 1, 1), "n": n}
+                continue
+            chains = torch.tensor(float(mean.shape[0]), dtype=mean.dtype, device=mean.device)
+            msum = mean.sum(0)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(msum)
+                dist.all_reduce(chains)
+            gmean = msum / chains
+            ss = (m2 + n * (mean - gmean) ** 2).sum(0)
+            if self.world > 1:
+                dist.all_reduce(ss)
+            out[name] = {"mean": gmean, "variance": ss / (chains * n - 1).clamp(min=1), "n": int(chains) * n}
+        return out
 
     # ---- results -------------------------------------------------------------------------------------
     def _gathered(self):
@@ -82,10 +144,17 @@ class MCMC:
         return z
 
     def get_samples(self, num_samples=None, group_by_chain=False):
-        z = self._gathered()  # [C, T, D]
-        sites = self.kernel.potential.unpack(z)
+        z = self._gathered()  # [C, T, D]  (or [C, T, columns of save_params])
+        pot = self.kernel.potential
         if self.save_params is not None:
-            sites = {k: v for k, v in sites.items() if k in self.save_params}
+            sites, off = {}, 0
+            for name in self.save_params:
+                sl = pot.sites[name][0]
+                w = len(range(*sl.indices(self.kernel.D)))
+                sites[name] = pot.unpack_site(name, z[..., off:off + w])
+                off += w
+        else:
+            sites = pot.unpack(z)
         if not group_by_chain:
             sites = {k: v.reshape((-1,) + v.shape[2:]) for k, v in sites.items()}
         return sites

@@ -66,13 +66,13 @@ class NativePotential:
 
     def unpack(self, z):
         """``[..., D]`` unconstrained -> dict of constrained site values ``[..., *event_shape]``."""
-        out = {}
-        for name, (sl, transform, shape) in self.sites.items():
-            v = z[..., sl]
-            if transform == "exp":
-                v = v.exp()
-            out[name] = v.reshape(z.shape[:-1] + tuple(shape))
-        return out
+        return {name: self.unpack_site(name, z[..., sl]) for name, (sl, _, _) in self.sites.items()}
+
+    def unpack_site(self, name, u):
+        """Constrained value of ONE site from its unconstrained columns ``[..., n_site]``."""
+        _, transform, shape = self.sites[name]
+        v = u.exp() if transform == "exp" else u
+        return v.reshape(u.shape[:-1] + tuple(shape))
 
     def init_uniform(self, num_chains, radius=2.0, generator=None):
         return (torch.rand(num_chains, self.D, dtype=self.dtype, device=self.device,
@@ -213,12 +213,12 @@ class TracePotential:
         return U.detach(), g
 
     def unpack(self, z):
-        out = {}
-        lead = z.shape[:-1]
-        for name, (sl, ushape, vshape, batch_ndim) in self.sites.items():
-            u = z[..., sl].reshape(lead + ushape)
-            out[name] = self.transforms[name].inv(u)
-        return out
+        return {name: self.unpack_site(name, z[..., info[0]]) for name, info in self.sites.items()}
+
+    def unpack_site(self, name, u):
+        """Constrained value of ONE site from its unconstrained columns ``[..., n_site]``."""
+        _, ushape, vshape, batch_ndim = self.sites[name]
+        return self.transforms[name].inv(u.reshape(u.shape[:-1] + ushape))
 
     def init_uniform(self, num_chains, radius=2.0, generator=None):
         return (torch.rand(num_chains, self.D, dtype=self.dtype, device=self.device,

@@ -289,6 +289,42 @@ def test_fused_leaf_lockstep_driver_eight_schools(emu):
     assert kernel.leapfrog_count() > 6 * 250
 
 
+def test_save_params_and_streaming_statistics(emu):
+    """BASELINE config 4 cannot store its samples: with ``save_params`` only those sites are kept and
+    every site's per-chain running mean / variance is maintained on the device.  Same seed, two runs:
+    the kept sites equal the full run's, and the streaming statistics (per chain, and pooled over
+    chains) equal the statistics of the full run's stored samples."""
+    from pyro_b200.infer import MCMC, NUTS
+    from pyro_b200.infer.mcmc import HierNormalPotential
+    torch.set_default_dtype(torch.float64)
+    g = load_npz("mcmc.npz")
+    y, sigma = torch.as_tensor(g["es.y"]), torch.as_tensor(g["es.sigma"])
+
+    def run(**kw):
+        k = NUTS(potential_fn=HierNormalPotential(y, sigma, 10.0, 25.0), native_small=False)
+        mc = MCMC(k, num_samples=30, warmup_steps=25, num_chains=3, seed=5, **kw)
+        mc.run()
+        return mc
+
+    full = run()
+    lean = run(save_params=["mu", "tau"])
+    sf = full.get_samples(group_by_chain=True)
+    sl = lean.get_samples(group_by_chain=True)
+    assert set(sl) == {"mu", "tau"} and lean._samples.shape[-1] == 2
+    for name in ("mu", "tau"):
+        assert torch.equal(sl[name], sf[name])
+    per_chain = lean.streaming_stats(pooled=False)
+    pooled = lean.streaming_stats(pooled=True)
+    for name in ("mu", "tau", "eta"):
+        x = sf[name]                                   # [C, T, *shape]
+        assert torch.allclose(per_chain[name]["mean"], x.mean(1), atol=1e-10)
+        assert torch.allclose(per_chain[name]["variance"], x.var(1, unbiased=True), atol=1e-10)
+        flat = x.reshape((-1,) + x.shape[2:])
+        assert torch.allclose(pooled[name]["mean"], flat.mean(0), atol=1e-10)
+        assert torch.allclose(pooled[name]["variance"], flat.var(0, unbiased=True), atol=1e-10)
+        assert pooled[name]["n"] == flat.shape[0]
+
+
 def test_trace_potential_matches_reference(emu):
     """Generic model potential (model run under a chain plate, fused site scoring) == reference
     potential + gradient at the golden points."""

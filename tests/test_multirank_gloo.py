@@ -80,10 +80,17 @@ def _worker(rank, world, port, what, ret):
                 g = load_npz("mcmc.npz")
                 X, y = torch.as_tensor(g["lr.X"]), torch.as_tensor(g["lr.y"])
                 mc = MCMC(NUTS(potential_fn=LogisticPotential(X, y, 1.0), native_small=False),
-                          num_samples=20, warmup_steps=20, num_chains=6, seed=7)
+                          num_samples=20, warmup_steps=20, num_chains=6, seed=7, streaming_stats=True)
                 mc.run()
                 s = mc.get_samples(group_by_chain=True)["beta"]
-                ret[rank] = (tuple(s.shape), s[:, -1].numpy(), mc.local_chains)
+                # pooled streaming statistics (two all-reduces of per-chain Welford states) against the
+                # statistics of the all-gathered samples
+                st = mc.streaming_stats(pooled=True)["beta"]
+                flat = s.reshape(-1, s.shape[-1])
+                ok = (torch.allclose(st["mean"], flat.mean(0), atol=1e-10)
+                      and torch.allclose(st["variance"], flat.var(0, unbiased=True), atol=1e-10)
+                      and st["n"] == flat.shape[0])
+                ret[rank] = (tuple(s.shape), s[:, -1].numpy(), mc.local_chains, bool(ok))
     finally:
         dist.destroy_process_group()
 
@@ -123,7 +130,8 @@ def test_data_sharded_svi_matches_reference_trajectory():
 @pytest.mark.timeout(300)
 def test_chain_sharded_mcmc_gathers_all_chains():
     ret = _spawn("mcmc")
-    (shape0, last0, lc0), (shape1, last1, lc1) = ret[0], ret[1]
+    (shape0, last0, lc0, ok0), (shape1, last1, lc1, ok1) = ret[0], ret[1]
     assert shape0 == shape1 == (6, 20, 3) and lc0 == lc1 == 3
+    assert ok0 and ok1                                    # cross-rank pooled streaming statistics
     assert np.allclose(last0, last1)                      # both ranks see the same gathered chains
     assert not np.allclose(last0[:3], last0[3:])          # rank streams differ (seed + first chain id)
