@@ -269,6 +269,28 @@ def test_lockstep_nuts_recovers_posterior_logistic(emu):
     assert kernel.leapfrog_count() > 0
 
 
+def test_hmc_fixed_length_recovers_posterior_logistic(emu):
+    """Fixed-length HMC (pyro/infer/mcmc/hmc.py:371-438: momentum draw, masked per-chain step counts,
+    Metropolis correction, step-size / mass adaptation) on the 3-d logistic regression: posterior
+    moments agree with the oracle's recursive NUTS within MC error."""
+    from oracle import mcmc as omcmc
+    from pyro_b200.infer import HMC, MCMC
+    from pyro_b200.infer.mcmc import LogisticPotential
+    torch.set_default_dtype(torch.float64)
+    g = load_npz("mcmc.npz")
+    X, y = torch.as_tensor(g["lr.X"]), torch.as_tensor(g["lr.y"])
+    kernel = HMC(potential_fn=LogisticPotential(X, y, 1.0), step_size=0.1, trajectory_length=1.0)
+    mc = MCMC(kernel, num_samples=200, warmup_steps=100, num_chains=6, seed=4)
+    mc.run()
+    s = mc.get_samples()["beta"]
+    chain = omcmc.NUTSChain(omcmc.logistic_potential(X, y, 1.0), 3, seed=2)
+    ref, _ = chain.run(torch.zeros(3, dtype=torch.float64), 150, 600)
+    assert torch.allclose(s.mean(0), ref.mean(0), atol=0.12)
+    assert torch.allclose(s.std(0), ref.std(0), atol=0.08)
+    acc = torch.tensor(mc.diagnostics()["acceptance rate"])
+    assert float(acc.min()) > 0.5
+
+
 def test_fused_leaf_lockstep_driver_eight_schools(emu):
     """Host logic of the fused-leaf lockstep driver (``NUTS._sample_lockstep_hier``: per-depth
     merges, proposal flush, global-gradient bookkeeping) with the leaf kernel emulated: posterior of
