@@ -436,3 +436,30 @@ def test_fused_draw_graph_is_released(emu):
     del z, tag
     gc.collect()
     assert alive() is None
+
+
+def test_optimizer_repoints_gradient_table_after_capture(emu, monkeypatch):
+    """The captured SVI step lets autograd assign fresh gradient tensors; during capture the optimiser
+    must keep its device table (its ADDRESS is baked into the captured launch) and only re-point the
+    gradient pointers afterwards (``flush_pending``).  A changed parameter set during capture is refused."""
+    from pyro_b200 import _native as N
+    torch.set_default_dtype(torch.float64)
+    p, q = torch.randn(5, requires_grad=True), torch.randn(3, requires_grad=True)
+    store = pyro.get_param_store()
+    store._param_to_name[p], store._param_to_name[q] = "p", "q"
+    p.grad, q.grad = torch.ones(5), torch.ones(3)
+    opt = ClippedAdam({"lr": 0.01})
+    opt([p, q])
+    table = opt._tables[torch.float64]
+    g_addr = table["g"].data_ptr()
+    monkeypatch.setattr(N, "capturing", lambda: True)
+    p.grad, q.grad = torch.full((5,), 2.0), torch.full((3,), 2.0)      # what a grad-less backward leaves behind
+    opt([p, q])
+    assert opt._tables[torch.float64] is table and "pending" in table
+    with pytest.raises(RuntimeError):
+        opt([p])                                                       # different parameter set: refused
+    monkeypatch.setattr(N, "capturing", lambda: False)
+    opt.flush_pending()
+    assert "pending" not in table and table["g"].data_ptr() == g_addr
+    assert table["g"].tolist() == [p.grad.data_ptr(), q.grad.data_ptr()]
+    assert table["key"] == opt._table_key([p, q])
