@@ -201,3 +201,20 @@ def test_oracle_nuts_recovers_reference_posterior():
     assert abs(float(mu.mean()) - float(g["es.long.mu.mean"])) < 0.6
     assert abs(float(tau.mean()) - float(g["es.long.tau.mean"])) < 0.9
     assert 0.6 < np.mean(accs) < 0.99
+
+
+@pytest.mark.parametrize("tag", ["homog", "hetero", "wide"])
+def test_gaussian_hmm_first_principles_oracle(tag):
+    """oracle/hmm.py (dense joint Gaussian of the stacked observations -- neither the reference's
+    parallel scan nor the product's Kalman filter) against the reference's recorded log_prob
+    (tests/golden/hmm.npz; shapes of tests/distributions/test_hmm.py:424-555)."""
+    from oracle import hmm as ohmm
+    g = load_npz("hmm.npz")
+    P = {k: torch.as_tensor(g["%s.%s" % (tag, k)]) for k in
+         ("init_loc", "init_cov", "F", "trans_loc", "trans_cov", "Hm", "obs_loc", "obs_scale")}
+    value, ref = torch.as_tensor(g[tag + ".value"]), torch.as_tensor(g[tag + ".lp"])
+    R = torch.diag_embed(P["obs_scale"] ** 2)
+    seqs = value if value.dim() == 3 else value[None]
+    out = torch.stack([ohmm.gaussian_hmm_log_prob(P["init_loc"], P["init_cov"], P["F"], P["trans_loc"],
+                                                  P["trans_cov"], P["Hm"], P["obs_loc"], R, x) for x in seqs])
+    assert torch.allclose(out.reshape(ref.shape), ref, rtol=1e-10, atol=1e-9)
