@@ -81,3 +81,26 @@ def test_steady_state_scan_equals_sequential_filter_cpu(H, O, T):
 def test_steady_state_scan_equals_sequential_filter_gpu(dtype, tol, gtol):
     from conftest import device
     _steady_vs_sequential(device(), dtype, 16, 3, 1200, tol, gtol)
+
+
+def test_kalman_filter_against_first_principles_oracle_on_seeded_inputs():
+    """Beyond the goldens: random time-varying parameters, product filter vs oracle/hmm.py."""
+    from oracle import hmm as ohmm
+    torch.manual_seed(3)
+    T, Hd, O = 11, 4, 3
+    dt = torch.float64
+    F = 0.6 * torch.randn(T, Hd, Hd, dtype=dt)
+    Hm = torch.randn(T, Hd, O, dtype=dt)
+    bw, bv = torch.randn(T, Hd, dtype=dt), torch.randn(T, O, dtype=dt)
+    A = torch.randn(T, Hd, Hd, dtype=dt)
+    Q = A @ A.transpose(-1, -2) + 0.5 * torch.eye(Hd, dtype=dt)
+    osc = 0.5 + torch.rand(T, O, dtype=dt)
+    m0 = torch.randn(Hd, dtype=dt)
+    B = torch.randn(Hd, Hd, dtype=dt)
+    P0 = B @ B.T + torch.eye(Hd, dtype=dt)
+    x = torch.randn(T, O, dtype=dt)
+    d = dist.GaussianHMM(dist.MultivariateNormal(m0, covariance_matrix=P0), F,
+                         dist.MultivariateNormal(bw, covariance_matrix=Q), Hm,
+                         dist.Normal(bv, osc).to_event(1), duration=T)
+    ref = ohmm.gaussian_hmm_log_prob(m0, P0, F, bw, Q, Hm, bv, torch.diag_embed(osc ** 2), x)
+    assert abs(float(d.log_prob(x)) - float(ref)) <= 1e-9 * abs(float(ref))
