@@ -105,7 +105,11 @@ typedef struct {
                                     most B2_SITE_SMALL_N elements (tests cover both paths on the
                                     reference's small fixtures) */
 #define B2_FLAG_GLM_FP32 2       /* b2_glm_bernoulli_logits: fp32 SIMT contractions instead of the
-                                    TF32 tensor-core path */
+                                    tensor-core path */
+#define B2_FLAG_GLM_TF32 8       /* b2_glm_bernoulli_logits: single-pass TF32 logits (opt-in, ~1e-3
+                                    relative per logit) instead of the default 3xTF32 split */
+#define B2_FLAG_GLM_MMA_SYNC 16  /* b2_glm_bernoulli_logits: the legacy mma.sync kernel (single-pass
+                                    TF32) instead of the tcgen05/TMA kernel */
 
 /*
  * b2_site_score -- fused log_prob + score of one sample site for an elementwise family.
@@ -191,8 +195,11 @@ int b2_elbo_combine(const void* const* terms, const double* coeffs, int n, int d
  * X: [N,D] row-major fp32 (16-byte aligned), D in {4, 8, 16, 32}; W: [P,D]; b: [P] (nullable);
  * y: [N] fp32.
  * out_total (nullable): scalar, (=|+=) sum_coeff * scale * SUM_p sum_p[p].
- * For D == 32 the two contractions run on the tensor cores (TF32 operands, fp32 accumulate,
- * logits perturbed by ~1e-3 relative, unbiased); pass B2_FLAG_GLM_FP32 for the fp32 SIMT kernel.
+ * For D == 32 the two contractions run on the tcgen05 tensor cores out of TMA-staged tiles with
+ * TMEM accumulators (glm_tc.cu).  Default precision: logits by the error-compensated 3xTF32 split
+ * (fp32-exact to ~1e-6), gradient contraction in single-pass TF32 on round-to-nearest operands
+ * (unbiased; |err| <= 2^-11 SUM|g x|).  B2_FLAG_GLM_TF32: single-pass TF32 logits as well;
+ * B2_FLAG_GLM_MMA_SYNC: the round-1 mma.sync kernel; B2_FLAG_GLM_FP32: the fp32 SIMT kernel.
  * workspace: b2_glm_workspace() bytes, zero-initialised ONCE by the caller (its first 256 bytes
  * hold a ticket counter that the library leaves zeroed).  Two launches: the streaming kernel
  * and a finish kernel that sums the CTA partials in a fixed order (deterministic).

@@ -188,6 +188,10 @@ __global__ void __launch_bounds__(256) glm_finish_kernel(const float* __restrict
 int glm_mma_grid_x(int64_t N);
 void launch_glm_mma(const float* X, const float* y, const float* W, const float* b, int64_t N, int P,
                     float* partials, int gx, cudaStream_t s);
+// tcgen05 + TMA variant (glm_tc.cu)
+int glm_tc_grid_x(int64_t N);
+int launch_glm_tc(const float* X, const float* y, const float* W, const float* b, int64_t N, int P,
+                  float* partials, int gx, bool split3, cudaStream_t s);
 
 inline int glm_grid_x(int64_t N) {
   const int64_t ntiles = (N + kGlmTileRows - 1) / kGlmTileRows;
@@ -217,12 +221,18 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   if (reinterpret_cast<uintptr_t>(X) % 16 != 0) return B2_ERR_BAD_SHAPE;
   if (!workspace || workspace_bytes < b2_glm_workspace(N, D, P)) return B2_ERR_WORKSPACE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const bool use_mma = (D == 32) && !(flags & B2_FLAG_GLM_FP32);
-  const int gx = use_mma ? glm_mma_grid_x(N) : glm_grid_x(N);
+  const bool use_tensor = (D == 32) && !(flags & B2_FLAG_GLM_FP32);
+  const bool use_tc = use_tensor && !(flags & B2_FLAG_GLM_MMA_SYNC) &&
+                      reinterpret_cast<uintptr_t>(y) % 16 == 0 && N < ((int64_t)1 << 31);
+  const bool use_mma = use_tensor && !use_tc;
+  const int gx = use_tc ? glm_tc_grid_x(N) : (use_mma ? glm_mma_grid_x(N) : glm_grid_x(N));
   dim3 grid((unsigned)gx, (unsigned)((P + kGlmParticles - 1) / kGlmParticles), 1);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
   float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
-  if (use_mma) {
+  if (use_tc) {
+    const int rc = launch_glm_tc(X, y, W, b, N, P, partials, gx, !(flags & B2_FLAG_GLM_TF32), s);
+    if (rc != 0) return rc;
+  } else if (use_mma) {
     launch_glm_mma(X, y, W, b, N, P, partials, gx, s);
   } else
   switch (D) {

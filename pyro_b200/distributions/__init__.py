@@ -902,6 +902,11 @@ class LinearPredictor:
     ``w``: [D], [P, D] or [P, 1, D] (vectorised particles);  ``b``: None, [], [P] or [P, 1]."""
 
     def __init__(self, X, w, b=None, tensor_cores=True):
+        # latent values may arrive as lazy-aware SiteValue tensors (pyro_b200/lazy.py): score plain ones
+        if type(w).__name__ == "SiteValue":
+            w = w.as_subclass(torch.Tensor)
+        if type(b).__name__ == "SiteValue":
+            b = b.as_subclass(torch.Tensor)
         self.X, self.w, self.b = X, w, b
         self.tensor_cores = tensor_cores  # False: fp32 SIMT contractions (B2_FLAG_GLM_FP32)
         D = X.shape[-1]
@@ -956,11 +961,18 @@ class _GlmBernoulliFn(torch.autograd.Function):
         return None, None, None, dW, db
 
 
+def _lazy_of(logits):
+    if isinstance(logits, LinearPredictor):
+        return logits
+    return getattr(logits, "_lazy", None) if type(logits).__name__ == "LinearPredictorTensor" else None
+
+
 class _BernoulliLinear(Bernoulli):
-    """Bernoulli whose logits are a LinearPredictor (built by ``Bernoulli(logits=lazy)``)."""
+    """Bernoulli whose logits are a LinearPredictor (built by ``Bernoulli(logits=lazy)``, or by an
+    unchanged model whose ``w @ X.T + b`` was kept lazy by pyro_b200/lazy.py)."""
 
     def __init__(self, probs=None, logits=None, validate_args=None):
-        lazy = logits
+        lazy = _lazy_of(logits)
         self._lazy = lazy
         self.family = N.BERNOULLI_LOGITS
         self.param_names = ("logits",)
@@ -995,7 +1007,7 @@ class _BernoulliLinear(Bernoulli):
 
 def _bernoulli_new(cls, probs=None, logits=None, validate_args=None):
     # ``Bernoulli(logits=LinearPredictor)`` builds the fused-GLM subclass
-    if cls is Bernoulli and isinstance(logits, LinearPredictor):
+    if cls is Bernoulli and _lazy_of(logits) is not None:
         return object.__new__(_BernoulliLinear)
     return object.__new__(cls)
 

@@ -11,6 +11,9 @@ from .. import poutine
 from ..primitives import plate
 
 
+LAZY_LINEAR = True   # hand latent values to the model as lazy-aware tensors (pyro_b200/lazy.py)
+
+
 def get_importance_trace(graph_type, max_plate_nesting, model, guide, args, kwargs, detach=False,
                          score=True):
     """Run the guide, replay the model against it, prune subsample sites.  With ``score`` the
@@ -19,8 +22,20 @@ def get_importance_trace(graph_type, max_plate_nesting, model, guide, args, kwar
     guide_trace = poutine.trace(guide, graph_type=graph_type).get_trace(*args, **kwargs)
     if detach:
         guide_trace.detach_()
-    model_trace = poutine.trace(poutine.replay(model, trace=guide_trace),
-                                graph_type=graph_type).get_trace(*args, **kwargs)
+    if not score and LAZY_LINEAR:
+        # the model sees latent values as SiteValue tensors, so an unchanged `w @ X.T + b` likelihood
+        # reaches the fused GLM kernel (pyro_b200/lazy.py); plain tensors again before scoring
+        from ..lazy import unwrap_site_values, wrap_site_values
+        wrap_site_values(guide_trace)
+        try:
+            model_trace = poutine.trace(poutine.replay(model, trace=guide_trace),
+                                        graph_type=graph_type).get_trace(*args, **kwargs)
+        finally:
+            unwrap_site_values(guide_trace)
+        unwrap_site_values(model_trace)
+    else:
+        model_trace = poutine.trace(poutine.replay(model, trace=guide_trace),
+                                    graph_type=graph_type).get_trace(*args, **kwargs)
     check_model_guide_match(model_trace, guide_trace, max_plate_nesting)
     guide_trace = poutine.prune_subsample_sites(guide_trace)
     model_trace = poutine.prune_subsample_sites(model_trace)
