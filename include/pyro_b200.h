@@ -108,6 +108,8 @@ typedef struct {
                                     tensor-core path */
 #define B2_FLAG_GLM_TF32 8       /* b2_glm_bernoulli_logits: single-pass TF32 logits (opt-in, ~1e-3
                                     relative per logit) instead of the default 3xTF32 split */
+#define B2_FLAG_GLM_3XTF32 32    /* b2_glm_bernoulli_logits: split X as well as W (every logit exact to
+                                    ~1e-6; the default splits W only, see below) */
 #define B2_FLAG_GLM_MMA_SYNC 16  /* b2_glm_bernoulli_logits: the legacy mma.sync kernel (single-pass
                                     TF32) instead of the tcgen05/TMA kernel */
 
@@ -196,9 +198,11 @@ int b2_elbo_combine(const void* const* terms, const double* coeffs, int n, int d
  * y: [N] fp32.
  * out_total (nullable): scalar, (=|+=) sum_coeff * scale * SUM_p sum_p[p].
  * For D == 32 the two contractions run on the tcgen05 tensor cores out of TMA-staged tiles with
- * TMEM accumulators (glm_tc.cu).  Default precision: logits by the error-compensated 3xTF32 split
- * (fp32-exact to ~1e-6), gradient contraction in single-pass TF32 on round-to-nearest operands
- * (unbiased; |err| <= 2^-11 SUM|g x|).  B2_FLAG_GLM_TF32: single-pass TF32 logits as well;
+ * TMEM accumulators (glm_tc.cu).  Default precision: W is split hi + lo (two TF32 MMAs per k-step), which
+ * removes the only error that is COHERENT over rows (a rounded W shifts every row's logit the same way
+ * and survives the N-term sums); X and g = y - sigmoid are rounded to nearest TF32 (incoherent, averages
+ * as 1/sqrt(N)): sum_p, dW, db agree with an fp64 evaluation to ~1e-6 / ~1e-5 relative at N = 1e6.
+ * B2_FLAG_GLM_3XTF32: X split as well (every logit fp32-exact); B2_FLAG_GLM_TF32: single-pass TF32;
  * B2_FLAG_GLM_MMA_SYNC: the round-1 mma.sync kernel; B2_FLAG_GLM_FP32: the fp32 SIMT kernel.
  * workspace: b2_glm_workspace() bytes, zero-initialised ONCE by the caller (its first 256 bytes
  * hold a ticket counter that the library leaves zeroed).  Two launches: the streaming kernel

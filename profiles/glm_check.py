@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pyro_b200 import _native as N  # noqa: E402
 
-VARIANTS = {"tc_3xtf32": 0, "tc_tf32": N.B2_FLAG_GLM_TF32, "mma_sync": N.B2_FLAG_GLM_MMA_SYNC,
+VARIANTS = {"tc_wsplit": 0, "tc_3xtf32": N.B2_FLAG_GLM_3XTF32, "tc_tf32": N.B2_FLAG_GLM_TF32, "mma_sync": N.B2_FLAG_GLM_MMA_SYNC,
             "fp32_simt": N.B2_FLAG_GLM_FP32}
 
 
@@ -111,8 +111,24 @@ def main():
         except Exception as e:  # noqa: BLE001
             print("TIME %-10s FAILED: %s" % (name, e))
             ok = False
+    if "--trace" in sys.argv:
+        buf = torch.zeros(64, 16, dtype=torch.int64, device=dev)
+        os.environ["B2_GLM_TC_TRACE"] = str(buf.data_ptr())
+        for name in ("tc_wsplit", "tc_3xtf32"):
+            buf.zero_()
+            call, _ = run(X, y, W, b, VARIANTS[name])
+            call()
+            torch.cuda.synchronize()
+            t = buf.cpu()
+            t0 = int(t[0, 0])
+            print("TRACE %s: rows = tile, cols = [tma_issue, mma_xready, mma_d1empty, mma_g1_issued, mma_gfull, "
+                  "mma_g2_issued, split_xfull, split_tempty, split_done, epi_d1full, epi_ld_done, epi_gempty, epi_end w0, w4, w3, w7] "
+                  "(SM cycles since first TMA issue)" % name)
+            for it in range(0, 40):
+                print("  %2d " % it + " ".join("%7d" % (int(v) - t0 if int(v) else -1) for v in t[it, :16]))
+        os.environ.pop("B2_GLM_TC_TRACE", None)
     if "--dbg" in sys.argv:
-        for dbg in (0, 1, 2, 3, 4, 8, 16, 7, 12, 15, 31):
+        for dbg in (0, 1, 2, 3, 4):
             os.environ["B2_GLM_TC_DEBUG"] = str(dbg)
             call, _ = run(X, y, W, b, 0)
             for _ in range(3):
@@ -128,7 +144,8 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1) * 1e3)
             ts.sort()
-            print("DBG mask %2d: median %.1f us (eager, incl. finish + launch gaps)" % (dbg, ts[len(ts) // 2]))
+            print("DBG epilogue variant %d (0 full, 1 no LG2, 2 no RCP, 3 no MUFU, 4 no stores): median %.1f us "
+                  "(eager, incl. finish + launch gaps)" % (dbg, ts[len(ts) // 2]))
         os.environ.pop("B2_GLM_TC_DEBUG", None)
     print("GLM_CHECK", "OK" if ok else "FAIL", time.strftime("%H:%M:%S"))
 

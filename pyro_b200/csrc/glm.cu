@@ -191,7 +191,7 @@ void launch_glm_mma(const float* X, const float* y, const float* W, const float*
 // tcgen05 + TMA variant (glm_tc.cu)
 int glm_tc_grid_x(int64_t N);
 int launch_glm_tc(const float* X, const float* y, const float* W, const float* b, int64_t N, int P,
-                  float* partials, int gx, bool split3, cudaStream_t s);
+                  float* partials, int gx, int mode, cudaStream_t s);
 
 inline int glm_grid_x(int64_t N) {
   const int64_t ntiles = (N + kGlmTileRows - 1) / kGlmTileRows;
@@ -230,7 +230,9 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
   float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   if (use_tc) {
-    const int rc = launch_glm_tc(X, y, W, b, N, P, partials, gx, !(flags & B2_FLAG_GLM_TF32), s);
+    // default: W split; below 64 Ki rows the incoherent X rounding has not averaged out yet -> full 3xTF32
+    const int mode = (flags & B2_FLAG_GLM_TF32) ? 0 : (((flags & B2_FLAG_GLM_3XTF32) || N < 65536) ? 2 : 1);
+    const int rc = launch_glm_tc(X, y, W, b, N, P, partials, gx, mode, s);
     if (rc != 0) return rc;
   } else if (use_mma) {
     launch_glm_mma(X, y, W, b, N, P, partials, gx, s);

@@ -57,7 +57,8 @@ class HMC:
                  num_steps=None, adapt_step_size=True, adapt_mass_matrix=True, full_mass=False,
                  transforms=None, max_plate_nesting=None, jit_compile=False, jit_options=None,
                  ignore_jit_warnings=False, target_accept_prob=0.8, init_strategy=None,
-                 min_stepsize=1e-10, max_stepsize=1e10):
+                 min_stepsize=1e-10, max_stepsize=1e10, compile_model=True):
+        self.compile_model = compile_model   # recognise native model classes (infer/mcmc/compile.py)
         if not ((model is None) ^ (potential_fn is None)):
             raise ValueError("Only one of `model` or `potential_fn` must be specified.")
         if full_mass:
@@ -98,8 +99,12 @@ class HMC:
         self._warmup_steps = warmup_steps
         self.C = num_chains
         if self.potential is None:
-            self.potential = TracePotential(self.model, args, kwargs, num_chains,
-                                            max_plate_nesting=self.max_plate_nesting)
+            native = None
+            if getattr(self, "compile_model", True):
+                from .compile import recognise
+                native = recognise(self.model, args, kwargs)
+            self.potential = native if native is not None else TracePotential(
+                self.model, args, kwargs, num_chains, max_plate_nesting=self.max_plate_nesting)
         pot = self.potential
         if isinstance(pot, TracePotential):
             pot.C = num_chains

@@ -84,13 +84,16 @@ class HierNormalPotential(NativePotential):
     ``mu ~ Normal(0, s_mu)``, ``tau ~ HalfCauchy(s_tau)``, ``eta ~ Normal(0,1)[J]``,
     ``obs ~ Normal(mu + tau*eta, sigma)``;  z = [mu, log tau, eta]."""
 
-    def __init__(self, y, sigma, s_mu=10.0, s_tau=25.0):
+    def __init__(self, y, sigma, s_mu=10.0, s_tau=25.0, names=("mu", "tau", "eta"), shapes=((1,), (1,))):
         N.require_cuda(y, "HierNormalPotential")
         y = y.contiguous()
         sigma = sigma.to(y.dtype).contiguous()
         J = y.numel()
-        sites = {"mu": (slice(0, 1), "identity", (1,)), "tau": (slice(1, 2), "exp", (1,)),
-                 "eta": (slice(2, 2 + J), "identity", (J,))}
+        # ``names`` / ``shapes``: the site names and the (mu, tau) value shapes of the user's model when
+        # the class was recognised from a model (infer/mcmc/compile.py)
+        sites = {names[0]: (slice(0, 1), "identity", tuple(shapes[0])),
+                 names[1]: (slice(1, 2), "exp", tuple(shapes[1])),
+                 names[2]: (slice(2, 2 + J), "identity", (J,))}
         super().__init__(N.MODEL_HIER_NORMAL, y.dtype, y.device, J, J + 2, y, sigma, (s_mu, s_tau), sites)
 
 

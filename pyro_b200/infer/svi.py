@@ -15,6 +15,8 @@ from .elbo import ELBO
 
 
 class SVI:
+    _poutine = poutine   # pyro_b200/bind.py substitutes the reference's poutine for reference models
+
     def __init__(self, model, guide, optim, loss, loss_and_grads=None, num_samples=0, num_steps=0,
                  **kwargs):
         if num_steps:
@@ -54,7 +56,7 @@ class SVI:
     # ---- one eager step -----------------------------------------------------------------------------
     def _grads(self, args, kwargs, want_tensor=True):
         """Phase 1: loss + gradients.  Returns (loss, [unconstrained parameters touched])."""
-        with poutine.trace(param_only=True) as param_capture:
+        with self._poutine.trace(param_only=True) as param_capture:
             if want_tensor and self._loss_and_grads_tensor is not None:
                 loss = self._loss_and_grads_tensor(self.model, self.guide, *args, **kwargs)
             else:

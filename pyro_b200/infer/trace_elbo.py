@@ -152,25 +152,35 @@ class Trace_ELBO(ELBO):
         loss = _ops.elbo_combine(parts, [-c / P for c in coeffs])
         return loss, terms
 
+    def _score_and_backward(self, model_trace, guide_trace, allow_general=False):
+        """Score one (model, guide) trace pair with the fused kernels and run the backward of the
+        surrogate loss; returns this pair's loss contribution (0-d device tensor), or None when a guide
+        site has no reparameterised sampler and ``allow_general`` is false (pyro_b200/bind.py then hands
+        the pair to the reference algorithm)."""
+        trainable = any(site["type"] == "param" for trace in (model_trace, guide_trace)
+                        for site in trace.nodes.values())
+        if _all_reparam(guide_trace):
+            loss_particle, terms = self._fused_particle(model_trace, guide_trace)
+            if trainable and terms:
+                # every term's upstream gradient is exactly 1 (contract of the fused nodes);
+                # pass one cached ones-scalar instead of letting autograd fill a new one per term
+                ones = [_one_like(t) for t in terms]
+                torch.autograd.backward(terms, ones, retain_graph=self.retain_graph)
+            return loss_particle
+        if not allow_general:
+            return None
+        loss_particle, surrogate = self._differentiable_loss_particle(model_trace, guide_trace)
+        loss_particle = loss_particle / self.num_particles
+        if trainable and getattr(surrogate, "requires_grad", False):
+            (surrogate / self.num_particles).backward(retain_graph=self.retain_graph)
+        return loss_particle
+
     def loss_and_grads_tensor(self, model, guide, *args, **kwargs):
         """Like ``loss_and_grads`` but returns the loss as a 0-d DEVICE tensor without
         synchronising (used by the graph-captured step)."""
         loss = None
         for model_trace, guide_trace in self._get_traces(model, guide, args, kwargs):
-            trainable = any(site["type"] == "param" for trace in (model_trace, guide_trace)
-                            for site in trace.nodes.values())
-            if _all_reparam(guide_trace):
-                loss_particle, terms = self._fused_particle(model_trace, guide_trace)
-                if trainable and terms:
-                    # every term's upstream gradient is exactly 1 (contract of the fused nodes);
-                    # pass one cached ones-scalar instead of letting autograd fill a new one per term
-                    ones = [_one_like(t) for t in terms]
-                    torch.autograd.backward(terms, ones, retain_graph=self.retain_graph)
-            else:
-                loss_particle, surrogate = self._differentiable_loss_particle(model_trace, guide_trace)
-                loss_particle = loss_particle / self.num_particles
-                if trainable and getattr(surrogate, "requires_grad", False):
-                    (surrogate / self.num_particles).backward(retain_graph=self.retain_graph)
+            loss_particle = self._score_and_backward(model_trace, guide_trace, allow_general=True)
             loss = loss_particle if loss is None else loss + loss_particle
         return loss if loss is not None else 0.0
 

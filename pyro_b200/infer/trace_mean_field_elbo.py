@@ -92,18 +92,22 @@ class TraceMeanField_ELBO(Trace_ELBO):
         parts = [e.reshape(()).to(ref.dtype) if e.dtype != ref.dtype else e.reshape(()) for e in elbo_terms]
         return _ops.elbo_combine(parts, [-1.0 / P] * len(parts)), terms
 
+    def _score_and_backward(self, model_trace, guide_trace, allow_general=False, _no_backward=False):
+        for name, site in guide_trace.nodes.items():
+            if site["type"] == "sample" and not getattr(site["fn"], "has_rsample", False):
+                raise ValueError("TraceMeanField_ELBO requires fully reparameterised guides; "
+                                 "site '{}' is not".format(name))
+        loss_particle, terms = self._mean_field_particle(model_trace, guide_trace)
+        trainable = any(site["type"] == "param" for trace in (model_trace, guide_trace)
+                        for site in trace.nodes.values())
+        if trainable and terms and not _no_backward:
+            from .trace_elbo import _one_like
+            torch.autograd.backward(terms, [_one_like(t) for t in terms], retain_graph=self.retain_graph)
+        return loss_particle
+
     def loss_and_grads_tensor(self, model, guide, *args, _no_backward=False, **kwargs):
         loss = None
         for model_trace, guide_trace in self._get_traces(model, guide, args, kwargs):
-            for name, site in guide_trace.nodes.items():
-                if site["type"] == "sample" and not getattr(site["fn"], "has_rsample", False):
-                    raise ValueError("TraceMeanField_ELBO requires fully reparameterised guides; "
-                                     "site '{}' is not".format(name))
-            loss_particle, terms = self._mean_field_particle(model_trace, guide_trace)
+            loss_particle = self._score_and_backward(model_trace, guide_trace, _no_backward=_no_backward)
             loss = loss_particle if loss is None else loss + loss_particle
-            trainable = any(site["type"] == "param" for trace in (model_trace, guide_trace)
-                            for site in trace.nodes.values())
-            if trainable and terms and not _no_backward:
-                from .trace_elbo import _one_like
-                torch.autograd.backward(terms, [_one_like(t) for t in terms], retain_graph=self.retain_graph)
         return loss if loss is not None else 0.0

@@ -22,6 +22,7 @@ class PyroOptim:
     """Base: bookkeeping shared by the fused optimisers."""
 
     _state_names = ()
+    _store = staticmethod(get_param_store)   # pyro_b200/bind.py points this at the reference's param store
 
     def __init__(self, optim_args, clip_args=None):
         if not (callable(optim_args) or isinstance(optim_args, dict)):
@@ -37,7 +38,7 @@ class PyroOptim:
     # ---- per-parameter hyper-parameters ---------------------------------------------------------
     def _args_for(self, param):
         if callable(self.pt_optim_args):
-            name = get_param_store().param_name(param)
+            name = self._store().param_name(param)
             return dict(self.pt_optim_args(name))
         return dict(self.pt_optim_args)
 
@@ -45,7 +46,7 @@ class PyroOptim:
         if self.pt_clip_args is None:
             return None
         if callable(self.pt_clip_args):
-            return self.pt_clip_args(get_param_store().param_name(param))
+            return self.pt_clip_args(self._store().param_name(param))
         return self.pt_clip_args
 
     def _init_param(self, p):
@@ -54,7 +55,7 @@ class PyroOptim:
     def _ensure(self, p):
         if p not in self._host:
             self._host[p] = self._init_param(p)
-            name = get_param_store().param_name(p)
+            name = self._store().param_name(p)
             waiting = self._state_waiting_to_be_consumed.pop(name, None)
             if waiting is not None:
                 self._load_one(p, waiting)
@@ -150,14 +151,14 @@ class PyroOptim:
             self._sync_to_host(table)
         out = {}
         for p in self._host:
-            out[get_param_store().param_name(p)] = self._state_dict_one(p)
+            out[self._store().param_name(p)] = self._state_dict_one(p)
         return out
 
     def set_state(self, state_dict):
         self._state_waiting_to_be_consumed.update(state_dict)
         # parameters already being optimised take their state immediately
         for p in list(self._host):
-            name = get_param_store().param_name(p)
+            name = self._store().param_name(p)
             if name in self._state_waiting_to_be_consumed:
                 self._load_one(p, self._state_waiting_to_be_consumed.pop(name))
         self._tables = {}
