@@ -301,6 +301,8 @@ def _load():
                                           potential_fn=potential_fn, **kwargs) \
                 if model is None else None
             self._model = model
+            self.model = None         # pyro/infer/mcmc/api.py:377 reads these two attributes
+            self.transforms = {}      # sample() already returns constrained values
             self._kwargs = kwargs
             self._num_chains = num_chains
             self._seed = seed

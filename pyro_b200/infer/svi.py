@@ -147,53 +147,81 @@ class SVI:
         if kwargs:
             raise ValueError("graph-captured SVI steps take tensor positional arguments only")
         if self._graph is None:
-            self._capture_graph(args)
+            # the capturing call: ONE real (eager) update whose loss is returned, then the capture itself,
+            # which records kernels without running them -- exactly one update per step() call, as in
+            # pyro/infer/svi.py:134-162
+            return self._capture_graph(args)
         st = self._graph_state
         if len(args) != len(st["static_args"]):
             raise ValueError("graph-captured SVI step called with a different number of arguments")
-        for a, s in zip(args, st["static_args"]):
+        for i, (a, s) in enumerate(zip(args, st["static_args"])):
             if isinstance(a, torch.Tensor):
                 if a.shape != s.shape or a.dtype != s.dtype:
                     raise ValueError("graph-captured SVI step called with different argument shapes")
                 if a.data_ptr() != s.data_ptr():
+                    if not st["owned"][i]:
+                        # the graph reads the caller's FIRST tensor in place (zero-copy for a resident data
+                        # set).  A different tensor now arrives: never overwrite the caller's memory --
+                        # re-capture once with private input buffers, then copy into those every step.
+                        self._graph = None
+                        self._graph_state = None
+                        return self._capture_graph(args, private=True)
                     s.copy_(a, non_blocking=True)
             elif a != s:
                 raise ValueError("non-tensor argument of a graph-captured SVI step changed")
+        if getattr(self.optim, "graph_epoch", 0) != st["optim_epoch"]:
+            # optimiser state was replaced (set_state / load): its device tables moved
+            self._graph = None
+            self._graph_state = None
+            return self._capture_graph(args, private=any(st["owned"]))
         if st.get("graph_b") is None:
             self._graph.replay()
             return st["loss"]
-        # multi-rank: [graph A: loss + grads + pack] -> NCCL all-reduce (eager) -> [graph B: unpack + optimiser]
+        # multi-rank: [graph A: loss + grads into the flat payload] -> NCCL all-reduce -> [graph B: optimiser]
         import torch.distributed as dist
         self._graph.replay()
         dist.all_reduce(st["flat"], op=dist.ReduceOp.SUM)
         st["graph_b"].replay()
         return st["loss"]
 
-    def _capture_graph(self, args):
+    def _capture_graph(self, args, private=False):
+        """Run ONE eager step on ``args`` (its loss is the return value of this call), then capture the
+        step into a CUDA graph.  Capture records kernels without executing them, so parameters and
+        optimiser state advance exactly once."""
         dev = None
         for a in args:
             if isinstance(a, torch.Tensor) and a.is_cuda:
                 dev = a.device
         if dev is None:
             raise RuntimeError("graph capture needs CUDA tensor arguments")
-        static_args = []
-        for a in args:
-            if isinstance(a, torch.Tensor):
-                static_args.append(a if a.is_cuda else a.to(dev))
-            else:
-                static_args.append(a)
         if self._loss_and_grads_tensor is None:
             raise RuntimeError("this loss cannot be captured (no loss_and_grads_tensor)")
-        # one more eager step on a side stream so every lazily created buffer exists
+        static_args, owned = [], []
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if private or not a.is_cuda:
+                    static_args.append(a.to(dev, copy=True))
+                    owned.append(True)
+                else:
+                    static_args.append(a)           # zero-copy: read in place, never written
+                    owned.append(False)
+            else:
+                static_args.append(a)
+                owned.append(True)
+        # the real step of this call, on a side stream so that every lazily created buffer exists
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            self._eager_step(tuple(static_args), {}, want_tensor=True)
+            eager_loss = self._eager_step(tuple(static_args), {}, want_tensor=True)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        if isinstance(eager_loss, torch.Tensor):
+            eager_loss = eager_loss.detach().clone()
         graph = torch.cuda.CUDAGraph()
+        flush = getattr(self.optim, "flush_pending", None)
+        state = {"static_args": static_args, "owned": owned,
+                 "optim_epoch": getattr(self.optim, "graph_epoch", 0)}
         if self._world() == 1:
-            flush = getattr(self.optim, "flush_pending", None)
             with torch.cuda.graph(graph):
                 if flush is not None:
                     # no stored gradients during the captured backward: autograd hands each parameter
@@ -205,15 +233,14 @@ class SVI:
                 loss = loss.reshape(()) if isinstance(loss, torch.Tensor) else torch.as_tensor(loss, device=dev)
             if flush is not None:
                 flush()
-            self._graph = graph
-            self._graph_state = {"static_args": static_args, "loss": loss}
+            state["loss"] = loss
         else:
             # The collective stays outside the graphs: capture the two halves around it.  The
             # gradients are re-pointed to views of ONE flat buffer [loss, grad_1 .. grad_n], so the
             # backward pass accumulates straight into the all-reduce payload and the optimiser reads
             # it back in place -- no pack / unpack copies on either side of the collective.
             world = self._world()
-            live = [p for p in self._last_params if p.grad is not None]   # from the warm-up step above
+            live = [p for p in self._last_params if p.grad is not None]   # from the eager step above
             total = 1 + sum(p.grad.numel() for p in live)
             flat = torch.zeros(total, dtype=live[0].grad.dtype, device=dev)
             off = 1
@@ -221,13 +248,11 @@ class SVI:
                 n = p.grad.numel()
                 p.grad = flat[off:off + n].view(p.grad.shape)
                 off += n
-            # one eager step on the new gradient storage: the optimiser rebuilds its pointer tables
-            # now, not during capture
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                self._eager_step(tuple(static_args), {}, want_tensor=True)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
+            # the optimiser builds its pointer tables for the new gradient storage now (no launch),
+            # not during capture
+            prepare = getattr(self.optim, "prepare", None)
+            if prepare is not None:
+                prepare(live)
             with torch.cuda.graph(graph):
                 loss, params2 = self._grads(tuple(static_args), {}, True)
                 flat[0:1].copy_(loss.detach().reshape(1).to(flat.dtype))
@@ -236,6 +261,7 @@ class SVI:
                 flat /= world
                 out = flat[0].clone()
                 self.optim(params2)
-            self._graph = graph
-            self._graph_state = {"static_args": static_args, "loss": out, "flat": flat, "graph_b": graph_b}
-        self._steps_done += 1  # the warm-up step above was a real optimisation step
+            state.update({"loss": out, "flat": flat, "graph_b": graph_b})
+        self._graph = graph
+        self._graph_state = state
+        return eager_loss

@@ -18,7 +18,12 @@ def _kl_site_args(model_site, guide_site):
     scale = model_site["scale"]
     mask = model_site["mask"]
     if isinstance(scale, torch.Tensor):
-        scale = float(scale) if scale.numel() == 1 else None
+        # tensor-valued scale: reference path (keeps it differentiable; no device sync, capture-safe)
+        from .. import _native as N
+        if scale.numel() != 1 or scale.requires_grad or (scale.is_cuda and N.capturing()):
+            scale = None
+        else:
+            scale = float(scale)
     if mask is True:
         mask = None
     return scale, mask

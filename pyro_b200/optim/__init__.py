@@ -33,6 +33,8 @@ class PyroOptim:
         self.pt_clip_args = clip_args
         self._host = {}      # param -> {"args": dict, "step": int, "lr": float, tensors...}
         self._tables = {}    # dtype -> table dict
+        self._retired = []   # replaced tables: a captured CUDA graph may still read their device arrays
+        self.graph_epoch = 0  # bumped when state is replaced; SVI re-captures its graph when it changes
         self._state_waiting_to_be_consumed = {}
 
     # ---- per-parameter hyper-parameters ---------------------------------------------------------
@@ -83,6 +85,18 @@ class PyroOptim:
             table = self._table_for(dtype, ps)
             self._launch(table)
 
+    def prepare(self, params):
+        """Build the device tables for ``params`` (with their CURRENT gradient tensors) without launching
+        anything -- used before a CUDA-graph capture so that the capture itself allocates nothing."""
+        params = [p for p in params if p.grad is not None]
+        by_dtype = {}
+        for p in params:
+            N.require_cuda(p, type(self).__name__)
+            self._ensure(p)
+            by_dtype.setdefault(p.dtype, []).append(p)
+        for dtype, ps in by_dtype.items():
+            self._table_for(dtype, ps)
+
     def _table_key(self, ps):
         return tuple((id(p), p.data_ptr(), p.grad.data_ptr()) for p in ps)
 
@@ -103,6 +117,8 @@ class PyroOptim:
             raise RuntimeError("pyro_b200.optim: parameter set changed during CUDA graph capture")
         if table is not None:
             self._sync_to_host(table)
+            self._retired.append(table)   # keep its device arrays alive (baked into captured graphs)
+            del self._retired[:-8]
         dev = ps[0].device
         n = len(ps)
 
@@ -161,7 +177,16 @@ class PyroOptim:
             name = self._store().param_name(p)
             if name in self._state_waiting_to_be_consumed:
                 self._load_one(p, self._state_waiting_to_be_consumed.pop(name))
-        self._tables = {}
+        # The device tables are refreshed IN PLACE (step counts, learning rates, hyper-parameters): a
+        # captured CUDA graph reads them through baked-in addresses, so they must neither move nor be
+        # freed.  ``graph_epoch`` additionally tells SVI to re-capture.
+        for table in self._tables.values():
+            old = {k: table[k] for k in ("hyper", "lrs", "steps") if k in table}
+            self._fill_scalars(table)
+            for k, t_old in old.items():
+                t_old.copy_(table[k])
+                table[k] = t_old
+        self.graph_epoch += 1
 
     def save(self, filename):
         with open(filename, "wb") as f:

@@ -162,7 +162,13 @@ def _fused(site, weight, sum_coeff, unit=True, claim=False):
     scale = site["scale"]
     mask = site["mask"]
     if isinstance(scale, torch.Tensor):
-        if scale.numel() != 1:
+        # a tensor-valued scale stays on the reference path (materialised log_prob * scale keeps the
+        # scale differentiable, pyro/distributions/util.py:311-328); float() would also synchronise
+        # the device and is illegal during graph capture
+        if scale.numel() != 1 or scale.requires_grad:
+            return None
+        from .. import _native as N
+        if scale.is_cuda and N.capturing():
             return None
         scale = float(scale)
     if mask is False:

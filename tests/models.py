@@ -43,7 +43,8 @@ def logistic_model_sharded(X, y, idx, n_total):
     w = pyro.sample("w", dist.Normal(X.new_zeros(D), X.new_ones(D)).to_event(1))
     b = pyro.sample("b", dist.Normal(X.new_zeros(()), X.new_full((), 10.0)))
     with pyro.plate("data", n_total, subsample=idx):
-        pyro.sample("y", dist.Bernoulli(logits=dist.linear_predictor(X, w, b)), obs=y)
+        logits = w.squeeze(-2) @ X.T + b if w.dim() > 1 else X @ w + b
+        pyro.sample("y", dist.Bernoulli(logits=logits), obs=y)
 
 
 def logistic_guide_sharded(X, y, idx, n_total):
