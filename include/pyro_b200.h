@@ -169,6 +169,20 @@ int b2_event_score(int family, const b2_tensor* value, const b2_tensor* params, 
                    size_t workspace_bytes, void* stream);
 
 /*
+ * b2_normal_rsample -- reparameterised Normal draw with the noise generated in the kernel (Philox4x32-10),
+ * fused with the site's own log density: z = loc + eps*scale, eps ~ N(0,1), *out_sum = SUM log Normal(z).
+ * Replaces torch.randn + addcmul (torch/distributions/normal.py:82-85) and the guide site's
+ * log_prob + sum (pyro/poutine/trace_struct.py:264-278) -- SURVEY.md 8(f) row 1.
+ * loc, scale: broadcast views over `shape` (element strides, 0 = broadcast); z, eps: contiguous outputs
+ * of prod(shape) <= B2_RSAMPLE_MAX_N elements (one CTA); out_sum: 0-d, same dtype.
+ * rng_state: device array of two uint64 {seed, launch counter}; the kernel increments the counter, so a
+ * replayed CUDA graph draws fresh noise with no host-side RNG bookkeeping.
+ */
+#define B2_RSAMPLE_MAX_N 65536
+int b2_normal_rsample(const b2_tensor* loc, const b2_tensor* scale, int ndim, const int64_t* shape, void* z,
+                      void* eps, void* out_sum, void* rng_state, void* stream);
+
+/*
  * b2_reduce_to -- sum a strided full-shape tensor down to an output whose zero strides mark the
  * reduced dims (the "sum_to_size" the fused kernels do not cover in-kernel).
  */

@@ -31,6 +31,8 @@ NORMAL, BERNOULLI_LOGITS, GAMMA, BETA, POISSON, CAUCHY, HALFCAUCHY, EXPONENTIAL,
     HALFNORMAL, BERNOULLI_PROBS, UNIFORM, KL_NORMAL_NORMAL, KL_GAMMA_GAMMA, NORMAL_RSAMPLE, \
     NORMAL_RSAMPLE_BWD = range(16)
 FUSED_DRAW = True         # Normal.rsample draws and scores in one kernel (b2 family 14)
+PHILOX_DRAW = True        # ... and generates its noise in that kernel (b2_normal_rsample) instead of torch.randn
+RSAMPLE_MAX_N = 65536
 EMULATE_RSAMPLE = False   # tests/cpu_emulation.py flips this to exercise the fused-draw host logic on CPU
 SITE_SMALL_N = 8192   # B2_SITE_SMALL_N: one-CTA kernel with fused stored-shape gradient reductions
 DIRICHLET, CATEGORICAL, MVN_TRIL = 32, 33, 34
@@ -79,6 +81,7 @@ SIGNATURES = {
     "b2_event_score": (_i32, [_i32, _tp, _tp, _i32, _i32, _tp, _f64, _tp, _f64, _f64, _i32, _tp,
                               _vp, _tp, _tp, _vp, _sz, _vp]),
     "b2_reduce_to": (_i32, [_tp, _tp, _vp, _sz, _vp]),
+    "b2_normal_rsample": (_i32, [_tp, _tp, _i32, ctypes.POINTER(ctypes.c_int64), _vp, _vp, _vp, _vp, _vp]),
     "b2_elbo_combine": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "b2_glm_bernoulli_logits": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32,
                                        _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -221,7 +221,11 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   if (reinterpret_cast<uintptr_t>(X) % 16 != 0) return B2_ERR_BAD_SHAPE;
   if (!workspace || workspace_bytes < b2_glm_workspace(N, D, P)) return B2_ERR_WORKSPACE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const bool use_tensor = (D == 32) && !(flags & B2_FLAG_GLM_FP32);
+  // below 8 Ki rows the single-pass TF32 gradient contraction has not averaged its operand rounding
+  // (2^-12 relative per term) below the fp32 tolerance yet: those sizes take the exact fp32 SIMT kernel
+  // unless a tensor-core variant is asked for explicitly
+  const bool forced_tc = flags & (B2_FLAG_GLM_TF32 | B2_FLAG_GLM_3XTF32 | B2_FLAG_GLM_MMA_SYNC);
+  const bool use_tensor = (D == 32) && !(flags & B2_FLAG_GLM_FP32) && (N >= 8192 || forced_tc);
   const bool use_tc = use_tensor && !(flags & B2_FLAG_GLM_MMA_SYNC) &&
                       reinterpret_cast<uintptr_t>(y) % 16 == 0 && N < ((int64_t)1 << 31);
   const bool use_mma = use_tensor && !use_tc;

@@ -77,6 +77,12 @@ struct Philox {
   // standard normal (Box-Muller, one value per call; simple and branch-free)
   template <typename T>
   B2_HD T normal() {
+    if (sizeof(T) == 4) {
+      // fp32 draws: single-precision Box-Muller (the fp64 transcendental path costs ~10x on this part)
+      const float u1 = ((float)(next_u32() >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float u2 = ((float)(next_u32() >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      return (T)(sqrtf(-2.0f * logf(u1)) * cosf(6.2831853071795865f * u2));
+    }
     const double u1 = ((double)(next_u32() >> 8) + 0.5) * (1.0 / 16777216.0);
     const double u2 = ((double)(next_u32() >> 8) + 0.5) * (1.0 / 16777216.0);
     return (T)(sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2));

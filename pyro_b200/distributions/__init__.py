@@ -284,6 +284,16 @@ class Normal(_Elementwise):
         claim it instead of launching a scoring kernel, and the backward of the pair is one kernel
         that hands (d/dloc, d/dscale) back in their stored shapes."""
         shape = self.shape(sample_shape)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if (N.FUSED_DRAW and N.PHILOX_DRAW and self.loc.is_cuda and 0 < n <= N.RSAMPLE_MAX_N and len(shape) <= 6
+                and self.loc.dtype == self.scale.dtype):
+            # noise generated inside the draw kernel (Philox): no randn launch, graph-replay safe
+            coeff = _Coeff()
+            z, lq = _NormalRsampleFn.apply(coeff, self.loc, self.scale, None, torch.Size(shape))
+            z._b2_rsample = _RsampleTag(self.loc, self.scale, lq, coeff)
+            return z
         eps = torch.randn(shape, dtype=self.loc.dtype, device=self.loc.device)
         return self.rsample_with_noise(eps)
 
@@ -292,7 +302,7 @@ class Normal(_Elementwise):
         if not N.FUSED_DRAW or (not eps.is_cuda and not N.EMULATE_RSAMPLE):
             return torch.addcmul(self.loc, eps, self.scale)   # plain draw; scored later by b2_site_score
         coeff = _Coeff()
-        z, lq = _NormalRsampleFn.apply(coeff, self.loc, self.scale, eps)
+        z, lq = _NormalRsampleFn.apply(coeff, self.loc, self.scale, eps, None)
         z._b2_rsample = _RsampleTag(self.loc, self.scale, lq, coeff)
         return z
 
@@ -319,8 +329,11 @@ class _RsampleTag:
 
 class _NormalRsampleFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, coeff, loc, scale, eps):
-        z, lq = _ops.normal_rsample_score(loc, scale, eps)
+    def forward(ctx, coeff, loc, scale, eps, shape):
+        if eps is None:
+            z, lq, eps = _ops.normal_rsample_philox(loc, scale, shape)
+        else:
+            z, lq = _ops.normal_rsample_score(loc, scale, eps)
         ctx.coeff = coeff
         ctx.save_for_backward(eps, loc, scale)
         ctx.set_materialize_grads(False)
@@ -337,7 +350,7 @@ class _NormalRsampleFn(torch.autograd.Function):
         c = ctx.coeff.value if glq is not None else 0.0
         gloc, gscale = _ops.normal_rsample_backward(gz, eps, loc, scale, c,
                                                     ctx.needs_input_grad[1], ctx.needs_input_grad[2])
-        return None, gloc, gscale, None
+        return None, gloc, gscale, None, None
 
 
 def claim_rsample_score(fn, value, coeff):

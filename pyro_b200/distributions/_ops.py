@@ -357,6 +357,43 @@ def normal_rsample_score(loc, scale, eps):
     return z, lq
 
 
+_RNG_STATE = {}
+
+
+def rng_state(device):
+    """Per-device {seed, launch counter} of the in-kernel Philox draws, seeded from torch's current seed
+    on first use (``pyro_b200.set_rng_seed`` / ``torch.manual_seed`` before the first draw selects the
+    stream).  The kernels advance the counter themselves."""
+    key = (device.type, device.index)
+    st = _RNG_STATE.get(key)
+    if st is None:
+        st = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+        _RNG_STATE[key] = st
+    return st
+
+
+def reseed(seed):
+    """Restart the in-kernel Philox streams (called by ``pyro_b200.set_rng_seed``)."""
+    for st in _RNG_STATE.values():
+        st.copy_(torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
+
+
+def normal_rsample_philox(loc, scale, shape):
+    """(z, lq, eps): the draw, the 0-d sum of its log density and the noise it used -- ONE launch, noise
+    from Philox inside the kernel (b2_normal_rsample)."""
+    shape = tuple(shape)
+    dev, dtype = loc.device, loc.dtype
+    z = torch.empty(shape, dtype=dtype, device=dev)
+    eps = torch.empty(shape, dtype=dtype, device=dev)
+    lq = torch.empty((), dtype=dtype, device=dev)
+    ld, sd = N.desc(loc, shape), N.desc(scale, shape)
+    shp = (ctypes.c_int64 * max(1, len(shape)))(*shape)
+    N.check(N.lib().b2_normal_rsample(ctypes.byref(ld), ctypes.byref(sd), len(shape), shp, z.data_ptr(),
+                                      eps.data_ptr(), lq.data_ptr(), rng_state(dev).data_ptr(),
+                                      N.stream_ptr(dev)), "b2_normal_rsample")
+    return z, lq, eps
+
+
 def normal_rsample_backward(gz, eps, loc, scale, c, need_loc, need_scale):
     """Gradients of L w.r.t. (loc, scale) given gz = dL/dz and c = coefficient of sum log q(z) in L,
     reduced to the stored shapes, one launch for small sites (family NORMAL_RSAMPLE_BWD)."""

@@ -253,15 +253,39 @@ class SVI:
             prepare = getattr(self.optim, "prepare", None)
             if prepare is not None:
                 prepare(live)
-            with torch.cuda.graph(graph):
-                loss, params2 = self._grads(tuple(static_args), {}, True)
-                flat[0:1].copy_(loss.detach().reshape(1).to(flat.dtype))
-            graph_b = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph_b, pool=graph.pool()):
-                flat /= world
-                out = flat[0].clone()
-                self.optim(params2)
-            state.update({"loss": out, "flat": flat, "graph_b": graph_b})
+            import os
+            import torch.distributed as dist
+            single = None
+            if os.environ.get("B2_NCCL_IN_GRAPH", "1") == "1" and dist.get_backend() == "nccl":
+                # ONE graph for the whole step: NCCL collectives are capturable, so the all-reduce of the
+                # [loss, grads] payload sits between the backward and the optimiser inside the graph and a
+                # replay is a single launch (no host round trip between two graphs).
+                try:
+                    g1 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1):
+                        loss, params2 = self._grads(tuple(static_args), {}, True)
+                        flat[0:1].copy_(loss.detach().reshape(1).to(flat.dtype))
+                        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                        flat /= world
+                        out = flat[0].clone()
+                        self.optim(params2)
+                    single = (g1, out)
+                except Exception:  # noqa: BLE001 -- fall back to the two-graph form below
+                    single = None
+                    torch.cuda.synchronize(dev)
+            if single is not None:
+                graph, out = single
+                state.update({"loss": out, "flat": flat, "graph_b": None, "nccl_in_graph": True})
+            else:
+                with torch.cuda.graph(graph):
+                    loss, params2 = self._grads(tuple(static_args), {}, True)
+                    flat[0:1].copy_(loss.detach().reshape(1).to(flat.dtype))
+                graph_b = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_b, pool=graph.pool()):
+                    flat /= world
+                    out = flat[0].clone()
+                    self.optim(params2)
+                state.update({"loss": out, "flat": flat, "graph_b": graph_b, "nccl_in_graph": False})
         self._graph = graph
         self._graph_state = state
         return eager_loss

@@ -10,6 +10,8 @@ def set_rng_seed(rng_seed):
     torch.manual_seed(rng_seed)
     random.seed(rng_seed)
     np.random.seed(rng_seed)
+    from .distributions import _ops
+    _ops.reseed(rng_seed)   # the in-kernel Philox streams of the fused draws
 
 
 def get_rng_state():

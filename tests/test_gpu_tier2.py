@@ -322,11 +322,16 @@ def test_glm_kernel_full_size_against_oracle(flag_name, tol_sum, tol_g):
     assert torch.equal(sum_p, sum2)
 
 
-@pytest.mark.parametrize("n,P,bias", [(1, 1, True), (127, 3, False), (128, 64, True), (129, 65, True),
-                                      (70001, 64, True), (5000, 130, False)])
-def test_glm_tc_kernel_ragged_shapes_against_oracle(n, P, bias):
+@pytest.mark.parametrize("n,P,bias,flag", [(1, 1, True, "B2_FLAG_GLM_3XTF32"), (127, 3, False, "B2_FLAG_GLM_3XTF32"),
+                                           (128, 64, True, "B2_FLAG_GLM_3XTF32"), (129, 65, True, "B2_FLAG_GLM_3XTF32"),
+                                           (1, 1, True, None), (5000, 130, False, None),
+                                           (8192, 64, True, None), (70001, 64, True, None), (65535, 130, False, None)])
+def test_glm_tc_kernel_ragged_shapes_against_oracle(n, P, bias, flag):
     """Edge cases of the tiled kernel: a single row, one row short of / one past a 128-row tile, ragged
-    particle slabs (65, 130), no bias."""
+    particle slabs (65, 130), no bias.  With an explicit tensor-core flag the tcgen05 kernel runs at any
+    size and its gradient contraction is single-pass TF32 on round-to-nearest operands: the tolerance is
+    2^-11 of the LARGEST TERM budget (5e-4 x scale) for tiny N, where nothing averages; the default
+    dispatch (flag None: exact fp32 SIMT below 8 Ki rows, tcgen05 above) must meet the fp32 tolerances."""
     if EMULATE:
         pytest.skip("kernel test")
     from pyro_b200 import _native as N
@@ -347,10 +352,12 @@ def test_glm_tc_kernel_ragged_shapes_against_oracle(n, P, bias):
     db = torch.empty(P, device=DEV)
     ws = N.workspace(torch.device(DEV), int(N.lib().b2_glm_workspace(n, D, P)), tag="glm_ragged")
     N.check(N.lib().b2_glm_bernoulli_logits(Xg.data_ptr(), yg.data_ptr(), Wg.data_ptr(),
-                                            bg.data_ptr() if bias else None, n, D, P, 1.0, 1.0, 1.0, 0,
+                                            bg.data_ptr() if bias else None, n, D, P, 1.0, 1.0, 1.0,
+                                            getattr(N, flag) if flag else 0,
                                             sum_p.data_ptr(), None, dW.data_ptr(), db.data_ptr(), ws.data_ptr(),
                                             ws.numel(), N.stream_ptr(torch.device(DEV))), "b2_glm_bernoulli_logits")
     torch.cuda.synchronize()
+    tol_g = 5e-4 if flag else 2e-4
     assert float((sum_p.double().cpu() - s_ref).abs().max()) <= 2e-5 * max(1.0, float(s_ref.abs().max()))
-    assert float((dW.double().cpu() - gW).abs().max()) <= 2e-4 * max(1.0, float(gW.abs().max()))
-    assert float((db.double().cpu() - gb).abs().max()) <= 2e-4 * max(1.0, float(gb.abs().max()))
+    assert float((dW.double().cpu() - gW).abs().max()) <= tol_g * max(1.0, float(gW.abs().max()))
+    assert float((db.double().cpu() - gb).abs().max()) <= tol_g * max(1.0, float(gb.abs().max()))
