@@ -749,6 +749,15 @@ def main():
             for vp in ("site", "glm"):
                 if vp in variants and "error" not in variants[vp]:
                     variants[vp]["roofline"] = roofline_for(vp, X, y, P_local, flush)
+            # the per-family fused log_prob table (SURVEY.md 8d "micro log_prob"): HBM GB/s on the
+            # algorithmic bytes vs the measured copy peak, re-measured by the driver every round
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "profiles"))
+                import micro_logprob
+                variants["micro"] = micro_logprob.run(verbose=False)
+                torch.cuda.empty_cache()
+            except Exception as e:  # pragma: no cover
+                variants["micro"] = {"error": repr(e)[:200]}
             out["variants"] = variants
         v, cms, threads, _ = cpu_reference(a.cpu_steps, 1)
         out["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": cpu_reference.kind,

@@ -247,18 +247,21 @@ struct VecBody {
 // Vectors in flight per operand per thread.  Forward-only fp32 kernels are pure streams: 4 vectors
 // (measured 87% of the HBM copy peak for Normal).  Kernels that also write gradients carry more
 // live registers; 2 vectors keep them at 3 resident CTAs per SM.
-template <typename T, bool GRAD>
+// One-parameter families (Bernoulli, Poisson, Exponential, ...) have few live registers even with the
+// gradient outputs, so their fp32 gradient kernels also keep 4 vectors in flight (round 2: the
+// [64, 1e6] Bernoulli site of config 2's generic path was latency-limited at 0.53 of the HBM peak).
+template <int NP, typename T, bool GRAD>
 struct VecUnroll {
-  static constexpr int U = (sizeof(T) == 4 && !GRAD) ? 4 : 2;
-  static constexpr int kMinBlocks = (sizeof(T) == 8 && GRAD) ? 2 : 3;
+  static constexpr int U = (sizeof(T) == 4 && (!GRAD || NP <= 1)) ? 4 : 2;
+  static constexpr int kMinBlocks = (sizeof(T) == 8 && GRAD) ? 2 : ((GRAD && NP <= 1) ? 2 : 3);
 };
 
 // Loop nest: column chunks outermost (U vectors per thread, then a one-vector tail), rows inside.
 template <int FAM, typename T, bool GRAD, bool MASKUP>
-__global__ void __launch_bounds__(256, VecUnroll<T, GRAD>::kMinBlocks) site_vec_kernel(const SiteArgs a) {
+__global__ void __launch_bounds__(256, VecUnroll<FamilyTraits<FAM>::kNumParams, T, GRAD>::kMinBlocks) site_vec_kernel(const SiteArgs a) {
   constexpr int NP = FamilyTraits<FAM>::kNumParams;
   constexpr int V = VecOf<T>::N;
-  constexpr int U = VecUnroll<T, GRAD>::U;
+  constexpr int U = VecUnroll<NP, T, GRAD>::U;
   constexpr int NRED = GRAD ? 2 + NP : 1;
 
   const int TX = 1 << a.tx_log2;
@@ -508,7 +511,7 @@ int launch_site(const SiteArgs& a, int kind, cudaStream_t stream) {
     site_small_kernel<FAM, T, GRAD><<<1, threads, 0, stream>>>(a);
   } else if (kind == kSiteVec) {
     constexpr int V = VecOf<T>::N;
-    constexpr int U = VecUnroll<T, GRAD>::U;
+    constexpr int U = VecUnroll<FamilyTraits<FAM>::kNumParams, T, GRAD>::U;
     const int64_t CV = a.C / V;
     const int TX = 1 << a.tx_log2, TY = 256 / TX;
     // enough CTAs for ~4 waves of resident blocks; each thread then owns >= U vectors per row

@@ -81,14 +81,16 @@ class GaussianHMM(Distribution):
 
     def log_prob(self, value):
         T = value.shape[-2]
-        old = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = bool(self.tf32)
-        try:
-            if self.steady_state and T >= 64 and value.dim() == 2 and self._homogeneous():
-                return self._filter_steady(value, T)
-            return self._filter(value, T)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = old
+        # The GEMMs follow the AMBIENT ``torch.backends.cuda.matmul.allow_tf32`` setting in both the
+        # forward and the autograd backward pass (default: fp32).  No global flag is touched here: a
+        # forward-only toggle would leave the backward at a different precision and is not thread-safe
+        # (ADVICE r1).  ``tf32=True`` is honoured only by asserting that the caller enabled it.
+        if self.tf32 and not torch.backends.cuda.matmul.allow_tf32:
+            raise ValueError("GaussianHMM(tf32=True): enable torch.backends.cuda.matmul.allow_tf32 around the "
+                             "whole forward AND backward pass yourself")
+        if self.steady_state and T >= 64 and value.dim() == 2 and self._homogeneous():
+            return self._filter_steady(value, T)
+        return self._filter(value, T)
 
     def _homogeneous(self):
         """Time-invariant, unbatched parameters (BASELINE config 3): the covariance recursion does not
