@@ -269,6 +269,14 @@ def _load():
         def step(self, *args, **kwargs):
             return own_svi.SVI.step(self, *args, **kwargs)
 
+        def _capture_graph(self, args, private=False):
+            # torch.distributions' argument validation reads `valid.all()` back to the host, which a
+            # capturing stream forbids.  The first (eager) step ran with the user's validation setting;
+            # the captured step is recorded without it (pyro.validation_enabled is the reference's own
+            # switch, pyro/__init__.py) -- the analogue of JitTrace_ELBO's ignore_jit_warnings.
+            with pyro.validation_enabled(False):
+                return own_svi.SVI._capture_graph(self, args, private=private)
+
     # ---- MCMC --------------------------------------------------------------------------------------------
     class _PotentialFn(torch.autograd.Function):
         @staticmethod

@@ -247,13 +247,13 @@ struct VecBody {
 // Vectors in flight per operand per thread.  Forward-only fp32 kernels are pure streams: 4 vectors
 // (measured 87% of the HBM copy peak for Normal).  Kernels that also write gradients carry more
 // live registers; 2 vectors keep them at 3 resident CTAs per SM.
-// One-parameter families (Bernoulli, Poisson, Exponential, ...) have few live registers even with the
-// gradient outputs, so their fp32 gradient kernels also keep 4 vectors in flight (round 2: the
-// [64, 1e6] Bernoulli site of config 2's generic path was latency-limited at 0.53 of the HBM peak).
+// (Round 2 tried 4 vectors in flight for the one-parameter gradient kernels as well: 128 registers, 2 CTAs
+// per SM, and no gain -- Bernoulli 67.9 -> 69.8 %, HalfCauchy 71.2 -> 69.5 %, Exponential 65.7 -> 64.3 % of
+// the HBM peak -- so the policy stays as it was.)
 template <int NP, typename T, bool GRAD>
 struct VecUnroll {
-  static constexpr int U = (sizeof(T) == 4 && (!GRAD || NP <= 1)) ? 4 : 2;
-  static constexpr int kMinBlocks = (sizeof(T) == 8 && GRAD) ? 2 : ((GRAD && NP <= 1) ? 2 : 3);
+  static constexpr int U = (sizeof(T) == 4 && !GRAD) ? 4 : 2;
+  static constexpr int kMinBlocks = (sizeof(T) == 8 && GRAD) ? 2 : 3;
 };
 
 // Loop nest: column chunks outermost (U vectors per thread, then a one-vector tail), rows inside.

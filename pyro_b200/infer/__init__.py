@@ -4,3 +4,5 @@ from .svi import SVI  # noqa: F401
 from .trace_elbo import JitTrace_ELBO, Trace_ELBO  # noqa: F401
 from .trace_mean_field_elbo import TraceMeanField_ELBO  # noqa: F401
 from .mcmc import HMC, MCMC, NUTS  # noqa: F401
+from .renyi_elbo import RenyiELBO  # noqa: F401
+from .predictive import Predictive  # noqa: F401

@@ -102,11 +102,44 @@ class WelfordDiag:
         return cov
 
 
+class WelfordFull:
+    """Per-chain running covariance of ``[C, D]`` samples (pyro/ops/welford.py:7-51, ``diagonal=False``)."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self._mean = 0.0
+        self._m2 = 0.0
+        self.n_samples = 0
+
+    def update(self, sample):
+        self.n_samples += 1
+        delta_pre = sample - self._mean
+        self._mean = self._mean + delta_pre / self.n_samples
+        delta_post = sample - self._mean
+        self._m2 = self._m2 + delta_pre.unsqueeze(-1) * delta_post.unsqueeze(-2)
+
+    def get_covariance(self, regularize=True):
+        if self.n_samples < 2:
+            raise RuntimeError("Insufficient samples to estimate covariance")
+        cov = self._m2 / (self.n_samples - 1)
+        if regularize:
+            n = self.n_samples
+            cov = (n / (n + 5.0)) * cov
+            shrink = 1e-3 * (5.0 / (n + 5.0))
+            cov = cov + shrink * torch.eye(cov.shape[-1], dtype=cov.dtype, device=cov.device)
+        return cov
+
+
 class WarmupAdapter:
-    """Step-size and diagonal-mass adaptation for ``C`` chains."""
+    """Step-size and mass adaptation for ``C`` chains (diagonal mass; with ``full_mass`` the dense
+    covariance of each window is handed to ``mass_update_fn`` as its Cholesky factor)."""
 
     def __init__(self, num_chains, dim, dtype, device, step_size=1.0, adapt_step_size=True,
-                 target_accept_prob=0.8, adapt_mass_matrix=True):
+                 target_accept_prob=0.8, adapt_mass_matrix=True, full_mass=False, mass_update_fn=None):
+        self.full_mass = full_mass
+        self._mass_update_fn = mass_update_fn
         self.C, self.D = num_chains, dim
         self.dtype, self.device = dtype, device
         self.adapt_step_size = adapt_step_size
@@ -117,7 +150,7 @@ class WarmupAdapter:
         self.inverse_mass = torch.ones(num_chains, dim, dtype=dtype, device=device)
         self._adaptation_disabled = not (adapt_step_size or adapt_mass_matrix)
         self._da = DualAveraging(num_chains, device) if adapt_step_size else None
-        self._welford = WelfordDiag()
+        self._welford = WelfordFull() if full_mass else WelfordDiag()
         self._warmup_steps = None
         self._schedule = []
         self._current_window = 0
@@ -153,8 +186,9 @@ class WarmupAdapter:
             _, log_step_size_avg = self._da.get_state()
             self.step_size = torch.exp(log_step_size_avg).to(self.dtype)
 
-    def step(self, t, z, accept_prob):
-        """``t``: transition index (0-based); ``z`` ``[C, D]``; ``accept_prob`` ``[C]``."""
+    def step(self, t, z, accept_prob, z_model=None):
+        """``t``: transition index (0-based); ``z`` ``[C, D]`` in kernel coordinates; ``accept_prob`` ``[C]``;
+        ``z_model``: the same state in the model's coordinates when they differ (``full_mass``)."""
         if t >= self._warmup_steps or self._adaptation_disabled:
             return
         window = self._schedule[self._current_window]
@@ -163,7 +197,7 @@ class WarmupAdapter:
         if self.adapt_step_size:
             self._update_step_size(accept_prob)
         if mass_phase:
-            self._welford.update(z.detach())
+            self._welford.update((z_model if z_model is not None else z).detach())
         if t == window.end:
             if self._current_window == num_windows - 1:
                 self._current_window += 1
@@ -172,7 +206,13 @@ class WarmupAdapter:
             if self._current_window == 0:
                 self._current_window += 1
                 return
-            if mass_phase:
+            if mass_phase and self.full_mass:
+                cov = self._welford.get_covariance(regularize=True).to(self.dtype)
+                z = self._mass_update_fn(torch.linalg.cholesky(cov))   # kernel state in the new coordinates
+                self._welford.reset()
+                if self.adapt_step_size:
+                    self.reset_step_size_adaptation(z)
+            elif mass_phase:
                 self.inverse_mass = self._welford.get_covariance(regularize=True).to(self.dtype)
                 self._welford.reset()
                 if self.adapt_step_size:

@@ -26,7 +26,7 @@ import torch
 
 from ... import _native as N
 from .adaptation import WarmupAdapter
-from .potential import HierNormalPotential, NativePotential, TracePotential
+from .potential import HierNormalPotential, NativePotential, TracePotential, WhitenedPotential
 
 _MAX_SLICED_ENERGY = 1000.0
 
@@ -61,9 +61,11 @@ class HMC:
         self.compile_model = compile_model   # recognise native model classes (infer/mcmc/compile.py)
         if not ((model is None) ^ (potential_fn is None)):
             raise ValueError("Only one of `model` or `potential_fn` must be specified.")
-        if full_mass:
-            raise NotImplementedError("dense mass matrices are outside the scope of pyro_b200 "
-                                      "(diagonal mass only, see DESIGN.md)")
+        # dense mass matrix (pyro/infer/mcmc/adaptation.py:238-392 BlockMassMatrix with full_mass=True):
+        # run unit-mass dynamics in the whitened coordinates z = A z', A = chol(adapted covariance) --
+        # identical trajectories, U-turn decisions and acceptance to mass matrix M = (A A^T)^-1 on z
+        # (potential.WhitenedPotential); every kernel stays on its diagonal/identity-mass path
+        self.full_mass = bool(full_mass)
         self.model = model
         self.potential = potential_fn
         self.step_size = step_size
@@ -108,6 +110,10 @@ class HMC:
         pot = self.potential
         if isinstance(pot, TracePotential):
             pot.C = num_chains
+        if self.full_mass and not isinstance(pot, WhitenedPotential):
+            if pot.dim > 4096:
+                raise ValueError("full_mass=True needs a [chains, D, D] factor; D = %d is too large" % pot.dim)
+            pot = self.potential = WhitenedPotential(pot)
         self.D = pot.dim
         dev, dtype = pot.device, pot.dtype
         N.require_cuda(torch.empty(0, device=dev), "MCMC kernels (model / potential data)")
@@ -134,7 +140,8 @@ class HMC:
         self._adapter = WarmupAdapter(num_chains, self.D, dtype, dev, step_size=self.step_size,
                                       adapt_step_size=self.adapt_step_size,
                                       target_accept_prob=self.target_accept_prob,
-                                      adapt_mass_matrix=self.adapt_mass_matrix)
+                                      adapt_mass_matrix=self.adapt_mass_matrix, full_mass=self.full_mass,
+                                      mass_update_fn=self._set_whitening if self.full_mass else None)
         self._adapter.configure(warmup_steps, find_reasonable_step_size_fn=self._find_reasonable_step_size)
         if self.adapt_step_size:
             self._adapter.reset_step_size_adaptation(z)
@@ -144,6 +151,19 @@ class HMC:
 
     @property
     def initial_params(self):
+        return self._out(self._z)
+
+    def _out(self, z):
+        """Kernel coordinates -> the model's unconstrained coordinates (identity unless full_mass)."""
+        return self.potential.to_original(z) if self.full_mass else z
+
+    def _set_whitening(self, A):
+        """Adopt a new whitening factor ``A`` [C, D, D] (end of a mass-adaptation window): the current
+        state is re-expressed in the new coordinates and its potential / gradient re-evaluated."""
+        z_orig = self.potential.to_original(self._z)
+        self.potential.set_factor(A)
+        self._z = self.potential.from_original(z_orig)
+        self._U, self._g = self.potential.value_and_grad(self._z)
         return self._z
 
     # ---- pieces --------------------------------------------------------------------------------
@@ -232,7 +252,7 @@ class HMC:
         self._g = torch.where(accept[:, None], g, g0)
         self._U = torch.where(accept, U, U0)
         self._post_transition(accept_prob, accept, delta > _MAX_SLICED_ENERGY)
-        return self._z
+        return self._out(self._z)
 
     def _post_transition(self, accept_prob, accepted, diverging):
         self._t += 1
@@ -242,7 +262,8 @@ class HMC:
             self._divergences += diverging.long()
         else:
             n = self._t
-            self._adapter.step(self._t, self._z, accept_prob)  # nuts.py:519 passes the incremented t
+            self._adapter.step(self._t, self._z, accept_prob,   # nuts.py:519 passes the incremented t
+                               z_model=self._out(self._z) if self.full_mass else None)
         self._mean_accept += (accept_prob.double() - self._mean_accept) / n
 
     def logging(self):
@@ -578,7 +599,7 @@ class NUTS(HMC):
         accept_prob = sum_accept / num_prop.clamp(min=1)
         self._last_depth = depth_reached
         self._post_transition(accept_prob, accepted, diverged)
-        return self._z
+        return self._out(self._z)
 
     def leapfrog_count(self):
         """Chain-leapfrogs performed so far (one device read)."""

@@ -226,3 +226,64 @@ class TracePotential:
     def init_uniform(self, num_chains, radius=2.0, generator=None):
         return (torch.rand(num_chains, self.D, dtype=self.dtype, device=self.device,
                            generator=generator) * 2 - 1) * radius
+
+
+class WhitenedPotential:
+    """``U'(z') = U(A z')`` for a per-chain lower-triangular factor ``A`` [C, D, D].
+
+    Hamiltonian dynamics with mass matrix ``M = (A A^T)^-1`` on ``z`` are unit-mass dynamics on
+    ``z' = A^-1 z`` (momenta map as ``r' = A^T r``; kinetic energy, the leapfrog map, the energy error and
+    the U-turn products ``rho . M^-1 r`` are all invariant), so a DENSE adapted mass matrix
+    (pyro/infer/mcmc/adaptation.py:238-392, ``full_mass=True``) costs two batched mat-vecs per potential
+    evaluation here and every integrator / tree kernel stays on its identity-mass path.
+    ``A`` is the Cholesky factor of the regularised sample covariance of a warm-up window
+    (pyro/ops/welford.py:27-51 with ``diagonal=False``), i.e. the reference's inverse mass matrix."""
+
+    def __init__(self, base):
+        self.base = base
+        self.A = None   # identity until the first mass-adaptation window closes
+        self.sites = base.sites
+
+    @property
+    def dim(self):
+        return self.base.dim
+
+    @property
+    def dtype(self):
+        return self.base.dtype
+
+    @property
+    def device(self):
+        return self.base.device
+
+    def set_factor(self, A):
+        self.A = A.contiguous()
+
+    def to_original(self, zp):
+        if self.A is None:
+            return zp
+        if zp.dim() == 2:
+            return torch.bmm(self.A, zp.unsqueeze(-1)).squeeze(-1)
+        # [C, T, D] sample arrays
+        return torch.einsum("cij,ctj->cti", self.A, zp)
+
+    def from_original(self, z):
+        if self.A is None:
+            return z
+        return torch.linalg.solve_triangular(self.A, z.unsqueeze(-1), upper=False).squeeze(-1)
+
+    def value_and_grad(self, zp, active=None, out_grad=None):
+        z = self.to_original(zp).contiguous()
+        U, g = self.base.value_and_grad(z, active)
+        if self.A is not None:
+            g = torch.bmm(self.A.transpose(-1, -2), g.unsqueeze(-1)).squeeze(-1)
+        return U, g
+
+    def unpack(self, z):
+        return self.base.unpack(z)
+
+    def unpack_site(self, name, u):
+        return self.base.unpack_site(name, u)
+
+    def init_uniform(self, num_chains, radius=2.0, generator=None):
+        return self.base.init_uniform(num_chains, radius=radius, generator=generator)

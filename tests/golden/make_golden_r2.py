@@ -1,0 +1,68 @@
+"""Round-2 additions to the golden fixtures (same recipe as make_golden.py: the UNMODIFIED reference imported
+from /root/reference + the opt_einsum stand-in; run in the build container):
+
+    python tests/golden/make_golden_r2.py
+
+  renyi.npz    RenyiELBO (alpha = 0.5 and 2.0, 4 vectorised particles) loss and parameter gradients on a
+               Normal regression with injected guide noise (pyro/infer/renyi_elbo.py)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "opt_einsum_standin"))
+sys.path.insert(0, "/root/reference")
+
+import pyro  # noqa: E402
+import pyro.distributions as dist  # noqa: E402
+import pyro.poutine as poutine  # noqa: E402
+from pyro.infer import RenyiELBO  # noqa: E402
+
+assert pyro.__version__ == "1.9.1"
+torch.set_default_dtype(torch.float64)
+
+
+def renyi():
+    torch.manual_seed(3)
+    N, D, P = 12, 3, 4
+    X = torch.randn(N, D)
+    y = X @ torch.tensor([0.5, -1.0, 0.25]) + 0.3 * torch.randn(N)
+    eps = torch.randn(P, 1, D)
+    out = {"X": X.numpy(), "y": y.numpy(), "eps": eps.numpy(), "P": P}
+
+    def model(X, y):
+        w = pyro.sample("w", dist.Normal(torch.zeros(D), torch.ones(D)).to_event(1))
+        with pyro.plate("data", N):
+            mean = (X * w).sum(-1) if w.dim() == 1 else (w * X).sum(-1)   # w: [P, 1, D] -> [P, N]
+            pyro.sample("obs", dist.Normal(mean, 0.5), obs=y)
+
+    class Inject(poutine.messenger.Messenger):
+        def _pyro_sample(self, msg):
+            if msg["name"] == "w" and not msg["is_observed"]:
+                base = msg["fn"].base_dist
+                msg["value"] = base.loc + eps * base.scale
+
+    def guide(X, y):
+        m = pyro.param("m", torch.tensor([0.1, -0.2, 0.3]))
+        s = pyro.param("s", torch.tensor([0.5, 0.7, 0.9]), constraint=dist.constraints.positive)
+        with Inject():
+            pyro.sample("w", dist.Normal(m, s).to_event(1))
+
+    for alpha in (0.5, 2.0):
+        pyro.clear_param_store()
+        elbo = RenyiELBO(alpha=alpha, num_particles=P, vectorize_particles=True, max_plate_nesting=1)
+        loss = elbo.loss_and_grads(model, guide, X, y)
+        store = pyro.get_param_store()
+        out["loss_%g" % alpha] = loss
+        out["grad_m_%g" % alpha] = store["m"].unconstrained().grad.numpy().copy()
+        out["grad_s_%g" % alpha] = store["s"].unconstrained().grad.numpy().copy()
+        out["value_%g" % alpha] = elbo.loss(model, guide, X, y)
+    np.savez(os.path.join(HERE, "renyi.npz"), **out)
+    print({k: (v if np.ndim(v) == 0 else np.asarray(v).shape) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    renyi()

@@ -361,3 +361,9 @@ def test_glm_tc_kernel_ragged_shapes_against_oracle(n, P, bias, flag):
     assert float((sum_p.double().cpu() - s_ref).abs().max()) <= 2e-5 * max(1.0, float(s_ref.abs().max()))
     assert float((dW.double().cpu() - gW).abs().max()) <= tol_g * max(1.0, float(gW.abs().max()))
     assert float((db.double().cpu() - gb).abs().max()) <= tol_g * max(1.0, float(gb.abs().max()))
+
+
+def test_full_mass_nuts_correlated_posterior_gpu():
+    """``NUTS(full_mass=True)`` (dense mass matrix via whitened coordinates) on the device."""
+    from test_host_logic_cpu import _full_mass_case
+    _full_mass_case(DEV)
