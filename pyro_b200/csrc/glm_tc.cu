@@ -47,6 +47,7 @@
 //
 // Determinism: every CTA writes its partials once; glm_finish_kernel adds them in a fixed order.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda/std/type_traits>
 #include <stdlib.h>
 
@@ -76,17 +77,26 @@ constexpr uint32_t kXtStage = 4 * kXtBlock;                   // 20 KB
 // the N-term sums); X is rounded to nearest in place (incoherent, averages as 1/sqrt(N)).
 // MODE 2: full 3xTF32 (X split as well): every logit exact to ~1e-6, at the price of a shallower TMA
 // ring (the X_lo tiles take the shared memory of two X stages).
+// MODE 3: logits as MODE 1; GEMM 2 in BF16 (kind::f16, K = 16 per instruction) on MN-major operands -- g and
+// X keep their natural [row][column] layout (no transposition pass, vector stores), half the bytes, half the
+// MMAs.  Operand rounding 2^-9 (round to nearest, unbiased): used from 256 Ki rows up, where it has averaged
+// out far below the fp32 gradient tolerance (tests/test_gpu_tier2.py measures it at N = 1e6).
 template <int MODE>
 struct Layout {
+  static constexpr bool kBf16 = (MODE == 3);
   static constexpr int kStagesX = (MODE == 2) ? 2 : 4;             // TMA ring: X tile (hi in place) + y
   static constexpr int kStagesL = (MODE == 2) ? 2 : 0;             // X_lo ring
-  static constexpr int kStagesT = 3;                               // X^T (+ y) ring: split pass -> GEMM 2
+  static constexpr int kStagesT = 3;                               // GEMM 2 B-operand (+ y) ring: split pass -> GEMM 2
                                                                    // (>= 3: GEMM 1 runs two tiles ahead)
+  static constexpr uint32_t kXtStage = kBf16 ? kTile : b2::tc::kXtStage;   // bf16 [128 n][64 cols] = 16 KB
+  static constexpr uint32_t kGBuf = kBf16 ? kTile : b2::tc::kGBuf;         // bf16 [128 n][64 p]   = 16 KB
   static constexpr uint32_t OFF_X = 0;
   static constexpr uint32_t OFF_XLO = OFF_X + kStagesX * kTile;
   static constexpr uint32_t OFF_XT = OFF_XLO + kStagesL * kTile;   // [stage][kb 4][d 32 + 8 ones][32 n] fp32
   static constexpr uint32_t OFF_G = OFF_XT + kStagesT * kXtStage;
-  static constexpr uint32_t OFF_WHI = OFF_G + 2 * kGBuf;           // [p 64][32 d] SW128, 8 KB
+  // the g buffers double as the [128][65] fp32 scratch of the final reduction (33 280 bytes)
+  static constexpr uint32_t kGRegion = (2 * kGBuf > 34816u) ? 2 * kGBuf : 34816u;
+  static constexpr uint32_t OFF_WHI = OFF_G + kGRegion;           // [p 64][32 d] SW128, 8 KB
   static constexpr uint32_t OFF_WLO = OFF_WHI + 8192;
   static constexpr uint32_t OFF_WB = OFF_WLO + 8192;               // bias tile (k = 0: b_hi, k = 1: b_lo)
   static constexpr uint32_t OFF_ONES = OFF_WB + 8192;              // 4 KB of 1.0f (no-swizzle operand)
@@ -95,7 +105,8 @@ struct Layout {
   static constexpr uint32_t OFF_BAR = OFF_YX + kStagesX * 512;
   static constexpr uint32_t kSmemBytes = OFF_BAR + 256 + 1024;     // + slack for the 1024-byte alignment
 };
-static_assert(Layout<1>::kSmemBytes <= 232448 && Layout<2>::kSmemBytes <= 232448, "shared memory budget");
+static_assert(Layout<1>::kSmemBytes <= 232448 && Layout<2>::kSmemBytes <= 232448 &&
+                  Layout<3>::kSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots (8 bytes each)
 enum : int {
@@ -178,6 +189,20 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with BF16 operands (format code 1), both MN-major (bits 15 / 16), fp32 accumulate
+__host__ __device__ constexpr uint32_t idesc_bf16_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -223,7 +248,19 @@ __device__ __forceinline__ float tf32_rn(float x) {
 
 // B elements at once, stage by stage: the MUFU results are consumed a whole stage (>= B instructions)
 // after they were issued, so their latency is covered inside the warp instead of by warp switching.
-template <bool MASK, int B>
+// g[n][p] as bf16, natural layout (MN-major A operand of the BF16 GEMM 2): 8 values = one 16-byte chunk
+__device__ __forceinline__ void store_g_bf16(uint8_t* gt, int r, int chunk, const float (&g)[8]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(g[0], g[1]), b = __floats2bfloat162_rn(g[2], g[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(g[4], g[5]), d = __floats2bfloat162_rn(g[6], g[7]);
+  uint4 v;
+  v.x = *reinterpret_cast<uint32_t*>(&a);
+  v.y = *reinterpret_cast<uint32_t*>(&b);
+  v.z = *reinterpret_cast<uint32_t*>(&c);
+  v.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(gt + r * 128 + ((chunk ^ (r & 7)) << 4)) = v;
+}
+
+template <bool MASK, int B, bool RAW = false>
 __device__ __forceinline__ void epi_batch(const uint32_t* lr, float y, float vw, float* acc, float* g) {
   float e[B], den[B], inv[B], lg[B];
 #pragma unroll
@@ -255,7 +292,7 @@ __device__ __forceinline__ void epi_batch(const uint32_t* lr, float y, float vw,
     } else {
       acc[j] = fmaf(lg[j], -0.6931471805599453f, acc[j]);
     }
-    g[j] = tf32_rn(gg);
+    g[j] = RAW ? gg : tf32_rn(gg);
   }
 }
 
@@ -270,6 +307,9 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 #define TRACE(it_, k_) do { if (tr && (it_) < 64) trace[(it_) * 16 + (k_)] = clock64(); } while (0)
   constexpr int SX = L::kStagesX;
   constexpr int kStagesT = L::kStagesT;
+  constexpr bool BF = L::kBf16;              // GEMM 2 in BF16 on MN-major operands
+  constexpr int LM = BF ? 1 : MODE;          // precision mode of the logits (GEMM 1)
+  constexpr uint32_t kXtStage = L::kXtStage, kGBuf = L::kGBuf;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -318,7 +358,7 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       const int p = e >> 5, d = e & 31;
       const int gp = slab * kP + p;
       const float w = (gp < P) ? W[(int64_t)gp * kD + d] : 0.f;
-      const float hi = (MODE >= 1) ? tf32_trunc(w) : tf32_rn(w);
+      const float hi = (LM >= 1) ? tf32_trunc(w) : tf32_rn(w);
       const int off = p * 32 + ((((d >> 2) ^ (p & 7)) << 2) | (d & 3));   // float index, 128B swizzle
       whi[off] = hi;
       wlo[off] = w - hi;
@@ -332,10 +372,21 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     }
     float* ones = reinterpret_cast<float*>(sm + L::OFF_ONES);
     for (int e = tid; e < 1024; e += kThreads) ones[e] = 1.f;
-    // rows 32..39 of every X^T k-block are ones: GEMM 2 then yields db in columns 32..39 of D2
-    for (int e = tid; e < kStagesT * 4 * 256; e += kThreads) {
-      const int blk = e >> 8, w = e & 255;
-      reinterpret_cast<float*>(sm + L::OFF_XT + blk * kXtBlock + kD * 128)[w] = 1.f;
+    if (!BF) {
+      // rows 32..39 of every X^T k-block are ones: GEMM 2 then yields db in columns 32..39 of D2
+      for (int e = tid; e < kStagesT * 4 * 256; e += kThreads) {
+        const int blk = e >> 8, w = e & 255;
+        reinterpret_cast<float*>(sm + L::OFF_XT + blk * kXtBlock + kD * 128)[w] = 1.f;
+      }
+    } else {
+      // bf16 B operand [128 n][64 columns]: columns 0..31 = x (split pass), column 32 = 1 (-> db in column
+      // 32 of D2), columns 33..63 = 0.  The constant chunks 4..7 of every row are written once here
+      // (16-byte chunk c of row n sits at chunk position c ^ (n & 7): 128-byte swizzle).
+      for (int e = tid; e < kStagesT * kRows * 4; e += kThreads) {
+        const int stg = e / (kRows * 4), rr = (e / 4) % kRows, c = 4 + (e & 3);
+        uint4 v = make_uint4(c == 4 ? 0x00003f80u : 0u, 0u, 0u, 0u);   // bf16 1.0 = 0x3f80 in element 0
+        *reinterpret_cast<uint4*>(sm + L::OFF_XT + stg * kXtStage + rr * 128 + ((c ^ (rr & 7)) << 4)) = v;
+      }
     }
   }
   fence_proxy_async();
@@ -375,7 +426,7 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const uint64_t d_xl0 = desc_sw128(base + L::OFF_XLO);
     const uint64_t d_g0 = desc_sw128(base + L::OFF_G);
     const uint64_t d_xt0 = desc_sw128(base + L::OFF_XT);
-    constexpr int kG1 = (MODE == 2) ? 12 : (MODE == 1 ? 8 : 4);   // data MMAs of GEMM 1
+    constexpr int kG1 = (LM == 2) ? 12 : (LM == 1 ? 8 : 4);   // data MMAs of GEMM 1
     constexpr int n_g1 = kG1 + 1;                                 // + the bias MMA (a zero tile without bias)
 
     // i-th MMA of GEMM 1 (i is a compile-time constant after unrolling); d1 / ax / al: accumulator and
@@ -394,7 +445,7 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     auto g1_commit = [&](int it) {
       tc_commit(bar(BAR_D1FULL + (it & 1)));
       tc_commit(bar(BAR_XEMPTY + it % SX));
-      if (MODE == 2) tc_commit(bar(BAR_LEMPTY + (it & 1)));
+      if (LM == 2) tc_commit(bar(BAR_LEMPTY + (it & 1)));
     };
     auto g1_wait = [&](int it) {
       mbar_wait(bar(BAR_XREADY + it % SX), (it / SX) & 1);
@@ -414,6 +465,23 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       const uint64_t db0 = d_xt0 + (uint64_t)((uint32_t)st * (kXtStage >> 4));
       const uint32_t acc0 = j > 0 ? 1u : 0u;
       int gi = 0;
+      if (BF) {
+        // 8 MMAs of K = 16 rows (2048 bytes of both MN-major tiles per step), one accumulator
+        constexpr uint32_t id2b = idesc_bf16_mn(64, 64);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          mma_bf16(tmem + kColD2, da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), id2b, k > 0 ? 1u : acc0);
+          if (WITH_G1) {
+            const int upto = ((k + 1) * n_g1 + 7) >> 3;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              if (gi < upto) {
+                g1_mma(gi, d1, ax, al);
+                ++gi;
+              }
+          }
+        }
+      } else {
 #pragma unroll
       for (int sstep = 0; sstep < 4; ++sstep) {
 #pragma unroll
@@ -431,6 +499,7 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
               }
           }
         }
+      }
       }
       if (WITH_G1) g1_commit(it);
       tc_commit(bar(BAR_TEMPTY + st));
@@ -478,7 +547,7 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       if (r == 0) TRACE(it, 6);
       mbar_wait(bar(BAR_TEMPTY + st), (ut & 1) ^ 1);           // GEMM 2 of tile it-3 released X^T[st]
       if (r == 0) TRACE(it, 7);
-      if (MODE == 2) mbar_wait(bar(BAR_LEMPTY + (it & 1)), ((it >> 1) & 1) ^ 1);
+      if (LM == 2) mbar_wait(bar(BAR_LEMPTY + (it & 1)), ((it >> 1) & 1) ^ 1);
       float4* xhi = reinterpret_cast<float4*>(sm + L::OFF_X + sx * kTile);
       float4* xlo = reinterpret_cast<float4*>(sm + L::OFF_XLO + (it & 1) * kTile);
       float* xt = reinterpret_cast<float*>(sm + L::OFF_XT + st * kXtStage + kb * kXtBlock);
@@ -490,7 +559,7 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int idx = r * 8 + (c ^ (r & 7));      // 16-byte chunk holding d = 4c .. 4c+3 of row r
         const float4 v = xhi[idx];
         float x[4] = {v.x, v.y, v.z, v.w};
-        if (MODE == 2) {
+        if (LM == 2) {
           float4 h, l;
           h.x = tf32_trunc(v.x); h.y = tf32_trunc(v.y); h.z = tf32_trunc(v.z); h.w = tf32_trunc(v.w);
           l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
@@ -503,11 +572,21 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           for (int q = 0; q < 4; ++q) x[q] = tf32_rn(x[q]);
           xhi[idx] = make_float4(x[0], x[1], x[2], x[3]);
         }
+        if (BF) {
+          // natural layout, bf16: columns 4c .. 4c+3 of row r -> 8 bytes inside 16-byte chunk c/2
+          __nv_bfloat162 lo2 = __floats2bfloat162_rn(v.x, v.y), hi2 = __floats2bfloat162_rn(v.z, v.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+          *reinterpret_cast<uint2*>(sm + L::OFF_XT + st * kXtStage + r * 128 + (((c >> 1) ^ (r & 7)) << 4) +
+                                    (c & 1) * 8) = pk;
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int d = c * 4 + q;
-          // X^T[d][n = r]: row d of k-block kb, 16-byte chunk (lane >> 2) ^ (d & 7), element lane & 3
-          xt[d * 32 + (((((r & 31) >> 2) ^ (d & 7)) << 2) | (r & 3))] = x[q];
+          for (int q = 0; q < 4; ++q) {
+            const int d = c * 4 + q;
+            // X^T[d][n = r]: row d of k-block kb, 16-byte chunk (lane >> 2) ^ (d & 7), element lane & 3
+            xt[d * 32 + (((((r & 31) >> 2) ^ (d & 7)) << 2) | (r & 3))] = x[q];
+          }
         }
       }
       fence_proxy_async();
@@ -562,18 +641,24 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 #pragma unroll
         for (int j0 = 0; j0 < kEpiCols; j0 += 8) {
           float g[8];
-          epi_batch<false, 8>(lr + j0, y, 1.f, acc + j0, g);
+          epi_batch<false, 8, BF>(lr + j0, y, 1.f, acc + j0, g);
+          if (BF) store_g_bf16(gt, r, part * (kEpiCols / 8) + (j0 >> 3), g);
+          else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<float*>(gt + gofs[j] + (j0 + j) * 128) = g[j];
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<float*>(gt + gofs[j] + (j0 + j) * 128) = g[j];
+          }
         }
       } else {
         const float vw = (row0 + r < N) ? 1.f : 0.f;
 #pragma unroll
         for (int j0 = 0; j0 < kEpiCols; j0 += 8) {
           float g[8];
-          epi_batch<true, 8>(lr + j0, y, vw, acc + j0, g);
+          epi_batch<true, 8, BF>(lr + j0, y, vw, acc + j0, g);
+          if (BF) store_g_bf16(gt, r, part * (kEpiCols / 8) + (j0 >> 3), g);
+          else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<float*>(gt + gofs[j] + (j0 + j) * 128) = g[j];
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<float*>(gt + gofs[j] + (j0 + j) * 128) = g[j];
+          }
         }
       }
       fence_proxy_async();
@@ -598,7 +683,7 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       for (int d = 0; d < 32; ++d) dwf[d] = 0.f;
       const uint32_t t2 = tmem + ((uint32_t)(sub * 32) << 16);
 #pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
+      for (int kb = 0; kb < (BF ? 1 : 4); ++kb) {
         uint32_t dw[32], dbv[8];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -609,7 +694,7 @@ glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
               "=r"(dw[14]), "=r"(dw[15]), "=r"(dw[16]), "=r"(dw[17]), "=r"(dw[18]), "=r"(dw[19]), "=r"(dw[20]),
               "=r"(dw[21]), "=r"(dw[22]), "=r"(dw[23]), "=r"(dw[24]), "=r"(dw[25]), "=r"(dw[26]), "=r"(dw[27]),
               "=r"(dw[28]), "=r"(dw[29]), "=r"(dw[30]), "=r"(dw[31])
-            : "r"(t2 + kColD2 + (uint32_t)kb * 40u)
+            : "r"(t2 + kColD2 + (uint32_t)kb * 40u)      // BF: one accumulator, dW in columns 0..31, db in 32
             : "memory");
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=r"(dbv[0]), "=r"(dbv[1]), "=r"(dbv[2]), "=r"(dbv[3]), "=r"(dbv[4]), "=r"(dbv[5]),
@@ -708,13 +793,17 @@ int launch_glm_tc(const float* X, const float* y, const float* W, const float* b
                          (int)Layout<1>::kSmemBytes);
     cudaFuncSetAttribute(glm_bernoulli_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)Layout<2>::kSmemBytes);
+    cudaFuncSetAttribute(glm_bernoulli_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)Layout<3>::kSmemBytes);
     attr_set = true;
   }
   dim3 grid((unsigned)gx, (unsigned)((P + kP - 1) / kP), 1);
   // B2_GLM_TC_TRACE = device address (decimal) of a 64 x 16 int64 buffer for the event trace of CTA 0
   const char* tr_env = getenv("B2_GLM_TC_TRACE");
   long long* trace = tr_env ? reinterpret_cast<long long*>(strtoull(tr_env, nullptr, 10)) : nullptr;
-  if (mode == 2)
+  if (mode == 3)
+    glm_bernoulli_tc_kernel<3><<<grid, kThreads, Layout<3>::kSmemBytes, s>>>(mx, my, W, b, N, P, partials, trace);
+  else if (mode == 2)
     glm_bernoulli_tc_kernel<2><<<grid, kThreads, Layout<2>::kSmemBytes, s>>>(mx, my, W, b, N, P, partials, trace);
   else if (mode == 1)
     glm_bernoulli_tc_kernel<1><<<grid, kThreads, Layout<1>::kSmemBytes, s>>>(mx, my, W, b, N, P, partials, trace);

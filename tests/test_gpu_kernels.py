@@ -12,7 +12,7 @@ import pytest
 import torch
 
 import pyro_b200.distributions as dist
-from conftest import device, load_npz
+from conftest import EMULATE, device, load_npz
 from oracle import dists as odists
 from pyro_b200.distributions import _ops
 
@@ -267,6 +267,7 @@ def test_fused_draw_step_equals_sitewise_step():
     res = []
     for fused in (True, False):
         N.FUSED_DRAW = fused
+        N.PHILOX_DRAW = False      # both runs take their noise from torch.randn (same seed -> same draws)
         try:
             pyro.clear_param_store()
             torch.manual_seed(7)
@@ -277,9 +278,52 @@ def test_fused_draw_step_equals_sitewise_step():
             res.append((loss, grads))
         finally:
             N.FUSED_DRAW = True
+            N.PHILOX_DRAW = True
     assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[1][0])
     for k in res[0][1]:
         assert torch.allclose(res[0][1][k], res[1][1][k], rtol=2e-4, atol=2e-4 * float(res[1][1][k].abs().max())), k
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_philox_draw_kernel(dtype):
+    """b2_normal_rsample: z = loc + eps * scale for the eps it returns, the 0-d sum equals the oracle's Normal
+    log density of z, the noise is standard normal (goodness of fit in the style of
+    tests/distributions/test_distributions.py:138-164), consecutive launches and CUDA-graph replays draw
+    fresh noise (the kernel advances its own counter), and reseeding reproduces the stream."""
+    if EMULATE:
+        pytest.skip("kernel test")
+    import pyro_b200 as pyro
+    from oracle import dists as od
+    pyro.set_rng_seed(11)
+    loc = torch.randn(7, 1, 33, device=DEV, dtype=dtype)
+    scale = torch.rand(33, device=DEV, dtype=dtype) + 0.5
+    shape = (5, 7, 4, 33)
+    z, lq, eps = _ops.normal_rsample_philox(loc, scale, shape)
+    assert torch.allclose(z, loc + eps * scale, rtol=1e-6 if dtype == torch.float32 else 1e-14)
+    ref = od.normal(z.double().cpu(), loc.double().cpu().expand(shape), scale.double().cpu().expand(shape)).sum()
+    assert abs(float(lq) - float(ref)) <= (2e-5 if dtype == torch.float32 else 1e-10) * abs(float(ref))
+    z2, _, eps2 = _ops.normal_rsample_philox(loc, scale, shape)
+    assert not torch.equal(eps, eps2)
+    big = torch.cat([_ops.normal_rsample_philox(loc[:1, :, :1] * 0, scale[:1] * 0 + 1, (64, 1024))[2].reshape(-1)
+                     for _ in range(8)]).double().cpu()
+    n = big.numel()
+    assert abs(float(big.mean())) < 5 / n ** 0.5 and abs(float(big.var()) - 1) < 5 * (2 / n) ** 0.5
+    assert abs(float((big ** 3).mean())) < 5 * (15 / n) ** 0.5 and abs(float((big ** 4).mean()) - 3) < 5 * (96 / n) ** 0.5
+    assert abs(float((big.abs() < 1).double().mean()) - 0.682689) < 5 * (0.2171 / n) ** 0.5
+    # graph replay: fresh noise every replay
+    g = torch.cuda.CUDAGraph()
+    _ops.normal_rsample_philox(loc, scale, shape)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        zg, _, eg = _ops.normal_rsample_philox(loc, scale, shape)
+    g.replay()
+    a = eg.clone()
+    g.replay()
+    assert not torch.equal(a, eg)
+    # reseeding reproduces the stream
+    pyro.set_rng_seed(11)
+    _, _, again = _ops.normal_rsample_philox(loc, scale, shape)
+    assert torch.equal(again, eps)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
