@@ -299,12 +299,14 @@ def test_philox_draw_kernel(dtype):
     scale = torch.rand(33, device=DEV, dtype=dtype) + 0.5
     shape = (5, 7, 4, 33)
     z, lq, eps = _ops.normal_rsample_philox(loc, scale, shape)
-    assert torch.allclose(z, loc + eps * scale, rtol=1e-6 if dtype == torch.float32 else 1e-14)
+    tol = 2e-6 if dtype == torch.float32 else 1e-14     # the kernel contracts the multiply-add
+    assert torch.allclose(z, loc + eps * scale, rtol=tol, atol=tol)
     ref = od.normal(z.double().cpu(), loc.double().cpu().expand(shape), scale.double().cpu().expand(shape)).sum()
     assert abs(float(lq) - float(ref)) <= (2e-5 if dtype == torch.float32 else 1e-10) * abs(float(ref))
     z2, _, eps2 = _ops.normal_rsample_philox(loc, scale, shape)
     assert not torch.equal(eps, eps2)
-    big = torch.cat([_ops.normal_rsample_philox(loc[:1, :, :1] * 0, scale[:1] * 0 + 1, (64, 1024))[2].reshape(-1)
+    zero, one = torch.zeros((), device=DEV, dtype=dtype), torch.ones((), device=DEV, dtype=dtype)
+    big = torch.cat([_ops.normal_rsample_philox(zero, one, (64, 1024))[2].reshape(-1)
                      for _ in range(8)]).double().cpu()
     n = big.numel()
     assert abs(float(big.mean())) < 5 / n ** 0.5 and abs(float(big.var()) - 1) < 5 * (2 / n) ** 0.5
