@@ -110,8 +110,8 @@ typedef struct {
                                     relative per logit) instead of the default 3xTF32 split */
 #define B2_FLAG_GLM_3XTF32 32    /* b2_glm_bernoulli_logits: split X as well as W (every logit exact to
                                     ~1e-6; the default splits W only, see below) */
-#define B2_FLAG_GLM_TF32_GRAD 64 /* b2_glm_bernoulli_logits: keep the gradient contraction in TF32 at every
-                                    size (from 256 Ki rows the default runs it in BF16) */
+#define B2_FLAG_GLM_BF16_GRAD 64 /* b2_glm_bernoulli_logits (opt-in): gradient contraction in BF16 on MN-major
+                                    operands -- 10 % faster, operand rounding 2^-9 (see below) */
 #define B2_FLAG_GLM_MMA_SYNC 16  /* b2_glm_bernoulli_logits: the legacy mma.sync kernel (single-pass
                                     TF32) instead of the tcgen05/TMA kernel */
 
@@ -218,8 +218,10 @@ int b2_elbo_combine(const void* const* terms, const double* coeffs, int n, int d
  * removes the only error that is COHERENT over rows (a rounded W shifts every row's logit the same way
  * and survives the N-term sums); X and g = y - sigmoid are rounded to nearest TF32 (incoherent, averages
  * as 1/sqrt(N)): sum_p, dW, db agree with an fp64 evaluation to ~1e-6 / ~1e-5 relative at N = 1e6.
- * From 256 Ki rows the gradient contraction runs in BF16 on MN-major operands (no transposition pass;
- * operand rounding 2^-9 unbiased, measured 3e-5 relative on dW at N = 1e6); B2_FLAG_GLM_TF32_GRAD keeps TF32.
+ * B2_FLAG_GLM_BF16_GRAD (opt-in): the gradient contraction in BF16 on MN-major operands (no transposition
+ * pass, half the MMAs): 90 instead of 100 us at N = 1e6; operand rounding 2^-9, unbiased -- 3e-5 of the largest
+ * entry on dW for generic W, but a noise floor of ~1e-3 sqrt(N) that shows when the gradient itself is ~sqrt(N)
+ * (balanced data, near a stationary point), which is why it is not the default.
  * B2_FLAG_GLM_3XTF32: X split as well (every logit fp32-exact); B2_FLAG_GLM_TF32: single-pass TF32;
  * B2_FLAG_GLM_MMA_SYNC: the round-1 mma.sync kernel; B2_FLAG_GLM_FP32: the fp32 SIMT kernel.
  * workspace: b2_glm_workspace() bytes, zero-initialised ONCE by the caller (its first 256 bytes

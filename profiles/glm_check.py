@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pyro_b200 import _native as N  # noqa: E402
 
-VARIANTS = {"tc_default": 0, "tc_wsplit": N.B2_FLAG_GLM_TF32_GRAD, "tc_3xtf32": N.B2_FLAG_GLM_3XTF32, "tc_tf32": N.B2_FLAG_GLM_TF32, "mma_sync": N.B2_FLAG_GLM_MMA_SYNC,
+VARIANTS = {"tc_default": 0, "tc_bf16grad": N.B2_FLAG_GLM_BF16_GRAD, "tc_3xtf32": N.B2_FLAG_GLM_3XTF32, "tc_tf32": N.B2_FLAG_GLM_TF32, "mma_sync": N.B2_FLAG_GLM_MMA_SYNC,
             "fp32_simt": N.B2_FLAG_GLM_FP32}
 
 
@@ -114,7 +114,7 @@ def main():
     if "--trace" in sys.argv:
         buf = torch.zeros(64, 16, dtype=torch.int64, device=dev)
         os.environ["B2_GLM_TC_TRACE"] = str(buf.data_ptr())
-        for name in ("tc_default", "tc_wsplit"):
+        for name in ("tc_default", "tc_bf16grad"):
             buf.zero_()
             call, _ = run(X, y, W, b, VARIANTS[name])
             call()

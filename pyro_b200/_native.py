@@ -23,7 +23,7 @@ B2_FLAG_SITE_LARGE = 4
 B2_FLAG_GLM_TF32 = 8
 B2_FLAG_GLM_MMA_SYNC = 16
 B2_FLAG_GLM_3XTF32 = 32
-B2_FLAG_GLM_TF32_GRAD = 64
+B2_FLAG_GLM_BF16_GRAD = 64
 FORCE_LARGE_SITE_KERNELS = False   # tests: score small fixtures with the multi-CTA kernels too
 B2_ERR_UNSUPPORTED_REDUCTION = -6
 

@@ -224,7 +224,7 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   // below 8 Ki rows the single-pass TF32 gradient contraction has not averaged its operand rounding
   // (2^-12 relative per term) below the fp32 tolerance yet: those sizes take the exact fp32 SIMT kernel
   // unless a tensor-core variant is asked for explicitly
-  const bool forced_tc = flags & (B2_FLAG_GLM_TF32 | B2_FLAG_GLM_3XTF32 | B2_FLAG_GLM_MMA_SYNC | B2_FLAG_GLM_TF32_GRAD);
+  const bool forced_tc = flags & (B2_FLAG_GLM_TF32 | B2_FLAG_GLM_3XTF32 | B2_FLAG_GLM_MMA_SYNC | B2_FLAG_GLM_BF16_GRAD);
   const bool use_tensor = (D == 32) && !(flags & B2_FLAG_GLM_FP32) && (N >= 8192 || forced_tc);
   const bool use_tc = use_tensor && !(flags & B2_FLAG_GLM_MMA_SYNC) &&
                       reinterpret_cast<uintptr_t>(y) % 16 == 0 && N < ((int64_t)1 << 31);
@@ -235,11 +235,10 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   if (use_tc) {
     // default: W split; below 64 Ki rows the incoherent X rounding has not averaged out yet -> full 3xTF32
-    // from 256 Ki rows: BF16 gradient contraction (operand rounding 2^-9 has averaged out) unless
-    // B2_FLAG_GLM_TF32_GRAD keeps it in TF32
+    // B2_FLAG_GLM_BF16_GRAD (opt-in): BF16 gradient contraction on MN-major operands (MODE 3)
     const int mode = (flags & B2_FLAG_GLM_TF32) ? 0
-                     : (((flags & B2_FLAG_GLM_3XTF32) || N < 65536) ? 2
-                        : ((N >= 262144 && !(flags & B2_FLAG_GLM_TF32_GRAD)) ? 3 : 1));
+                     : ((flags & B2_FLAG_GLM_BF16_GRAD) ? 3
+                        : (((flags & B2_FLAG_GLM_3XTF32) || N < 65536) ? 2 : 1));
     const int rc = launch_glm_tc(X, y, W, b, N, P, partials, gx, mode, s);
     if (rc != 0) return rc;
   } else if (use_mma) {

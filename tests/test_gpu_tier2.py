@@ -275,6 +275,7 @@ def test_unchanged_logistic_model_d32_matches_oracle_trajectory():
 
 
 @pytest.mark.parametrize("flag_name,tol_sum,tol_g", [("default", 2e-5, 2e-4), ("B2_FLAG_GLM_3XTF32", 2e-5, 2e-4),
+                                                     ("B2_FLAG_GLM_BF16_GRAD", 2e-5, 2e-4),
                                                      ("B2_FLAG_GLM_TF32", 5e-4, 2e-3)])
 def test_glm_kernel_full_size_against_oracle(flag_name, tol_sum, tol_g):
     """BASELINE size (N = 1e6, D = 32, P = 64): per-particle sums, dW and db of the tcgen05 kernel against
