@@ -256,10 +256,12 @@ class SVI:
             import os
             import torch.distributed as dist
             single = None
-            if os.environ.get("B2_NCCL_IN_GRAPH", "1") == "1" and dist.get_backend() == "nccl":
-                # ONE graph for the whole step: NCCL collectives are capturable, so the all-reduce of the
-                # [loss, grads] payload sits between the backward and the optimiser inside the graph and a
-                # replay is a single launch (no host round trip between two graphs).
+            if os.environ.get("B2_NCCL_IN_GRAPH", "0") == "1" and dist.get_backend() == "nccl":
+                # OPT-IN (B2_NCCL_IN_GRAPH=1): ONE graph for the whole step -- NCCL collectives are capturable,
+                # so the all-reduce of the [loss, grads] payload sits between the backward and the optimiser
+                # inside the graph and a replay is a single launch.  Off by default: the one 2-GPU run of
+                # round 2 with it enabled hung (a capture invalidated on one rank only leaves the ranks with
+                # different collective schedules), and there was no GPU budget left to debug it.
                 try:
                     g1 = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g1):
