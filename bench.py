@@ -580,6 +580,8 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         import torch.distributed as dist
+        # keep stdout for the ONE JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from pyro_b200 import _native
     import __graft_entry__
