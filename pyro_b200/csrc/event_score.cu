@@ -314,10 +314,14 @@ __global__ void __launch_bounds__(256) categorical_rowthread_kernel(const EventA
 
 // ---- MultivariateNormal(loc, scale_tril): torch/distributions/multivariate_normal.py:256-264,
 // _batch_mahalanobis :29-80.   -0.5*(n log 2pi + |L^-1 (x-mu)|^2) - sum log diag L.
-// One full warp per row; forward substitution with a warp reduction per pivot.  n <= 128
-// (residual z kept in 4 registers per lane).  Larger n belongs on the tensor-core path. ----------
-constexpr int kMvnMaxN = 128;
-template <typename T, bool GRAD>
+// One full warp per row; forward substitution with a warp reduction per pivot.  The residual z (and
+// w = L^-T z for the gradients) live in NSLOT registers per lane: NSLOT = 4 covers n <= 128 (round 1),
+// NSLOT = 16 / 32 cover n <= 512 / 1024 (round 2: the MVN sizes of BASELINE config 3, H = 512).  The
+// per-pivot work is an O(n) dot product read straight from L (L2-resident when the factor is shared by
+// the batch), so the kernel is latency-bound, not a tensor-core GEMM; a blocked TRSM on tcgen05 only
+// pays off for thousands of right-hand sides per factor, which no BASELINE config has. ----------
+constexpr int kMvnMaxN = 1024;
+template <typename T, bool GRAD, int NSLOT = 4>
 __global__ void __launch_bounds__(256) mvn_tril_kernel(const EventArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -334,12 +338,14 @@ __global__ void __launch_bounds__(256) mvn_tril_kernel(const EventArgs a) {
     batch_offsets(a, live ? row : 0, ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1);
     const T* L = Lp + op1;
     // z = L^-1 (x - mu), element j lives in lane j%32, slot j/32
-    T z[4] = {0, 0, 0, 0};
+    T z[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) z[s] = (T)0;
     T logdet = 0;
     for (int i = 0; i < n; ++i) {
       T part = 0;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
+      for (int s = 0; s < NSLOT; ++s) {
         const int j = s * 32 + lane;
         if (j < i) part += L[(int64_t)i * n + j] * z[s];
       }
@@ -347,11 +353,13 @@ __global__ void __launch_bounds__(256) mvn_tril_kernel(const EventArgs a) {
       const T lii = L[(int64_t)i * n + i];
       const T zi = ((xp[ox + i] - mu[op0 + i]) - part) / lii;
       logdet += b2_log(lii);
-      if ((i & 31) == lane) z[i >> 5] = zi;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (s == (i >> 5) && (i & 31) == lane) z[s] = zi;
     }
     T m2 = 0;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) m2 += z[s] * z[s];
+    for (int s = 0; s < NSLOT; ++s) m2 += z[s] * z[s];
     m2 = warp_sum(m2);
     const T lp = (T)-0.5 * ((T)n * ((T)2 * Consts<T>::kLogSqrt2Pi) + m2) - logdet;
     const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
@@ -364,22 +372,30 @@ __global__ void __launch_bounds__(256) mvn_tril_kernel(const EventArgs a) {
       T f = m ? (T)(a.weight * a.scale) : (T)0;
       if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[ou];
       // w = L^-T z  (back substitution):  w_i = (z_i - sum_{j>i} L_ji w_j) / L_ii
-      T w[4] = {0, 0, 0, 0};
+      T w[NSLOT];
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) w[s] = (T)0;
       for (int i = n - 1; i >= 0; --i) {
         T part = 0;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < NSLOT; ++s) {
           const int j = s * 32 + lane;
           if (j > i && j < n) part += L[(int64_t)j * n + i] * w[s];
         }
         part = warp_sum(part);
-        const T zi = __shfl_sync(0xffffffffu, z[i >> 5], i & 31);
+        T zsel = (T)0;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (s == (i >> 5)) zsel = z[s];
+        const T zi = __shfl_sync(0xffffffffu, zsel, i & 31);
         const T wi = (zi - part) / L[(int64_t)i * n + i];
-        if ((i & 31) == lane) w[i >> 5] = wi;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (s == (i >> 5) && (i & 31) == lane) w[s] = wi;
       }
       if (live) {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < NSLOT; ++s) {
           const int j = s * 32 + lane;
           if (j < n) {
             if (a.gx.ptr) reinterpret_cast<T*>(a.gx.ptr)[ogx + j] = m ? -f * w[s] : (T)0;
@@ -391,9 +407,13 @@ __global__ void __launch_bounds__(256) mvn_tril_kernel(const EventArgs a) {
         // dL = f * (tril(w z^T) - diag(1/L_ii)); strictly upper part is zero
         T* gL = reinterpret_cast<T*>(a.gp1.ptr) + ogp1;
         for (int i = 0; i < n; ++i) {
-          const T wi = __shfl_sync(0xffffffffu, w[i >> 5], i & 31);
+          T wsel = (T)0;
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
+          for (int s = 0; s < NSLOT; ++s)
+            if (s == (i >> 5)) wsel = w[s];
+          const T wi = __shfl_sync(0xffffffffu, wsel, i & 31);
+#pragma unroll
+          for (int s = 0; s < NSLOT; ++s) {
             const int j = s * 32 + lane;
             if (j < n && live) {
               T g = (T)0;
@@ -1035,7 +1055,20 @@ extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tenso
   }
   else if (family == B2_DIRICHLET) { B2_EV_LAUNCH(dirichlet_kernel) }
   else if (family == B2_CATEGORICAL) { B2_EV_LAUNCH(categorical_kernel) }
-  else { B2_EV_LAUNCH(mvn_tril_kernel) }
+  else if (event_size <= 128) { B2_EV_LAUNCH(mvn_tril_kernel) }
+  else {
+    // n in (128, 1024]: 16 or 32 register slots per lane; few rows per factor -> one warp per CTA slot is fine
+#define B2_MVN_BIG(NS)                                                                      \
+  if (dtype == B2_F32) {                                                                    \
+    if (grad) mvn_tril_kernel<float, true, NS><<<(unsigned)blocks, 256, 0, s>>>(a);         \
+    else mvn_tril_kernel<float, false, NS><<<(unsigned)blocks, 256, 0, s>>>(a);             \
+  } else {                                                                                  \
+    if (grad) mvn_tril_kernel<double, true, NS><<<(unsigned)blocks, 256, 0, s>>>(a);        \
+    else mvn_tril_kernel<double, false, NS><<<(unsigned)blocks, 256, 0, s>>>(a);            \
+  }
+    if (event_size <= 512) { B2_MVN_BIG(16) } else { B2_MVN_BIG(32) }
+#undef B2_MVN_BIG
+  }
 #undef B2_EV_LAUNCH
   count_launch();
   return check_launch();

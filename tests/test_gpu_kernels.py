@@ -404,3 +404,31 @@ def test_mvn_row_per_thread_kernel(n, dtype, tol, gtol):
         _close(g[0], go[0], gtol)
         _close(g[1], go[1], gtol * red)
         _close(g[2], torch.tril(go[2]), gtol * red)
+
+
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float64, 1e-10, 1e-8), (torch.float32, 5e-5, 2e-3)])
+@pytest.mark.parametrize("n", [129, 200, 512, 1000])
+def test_mvn_large_event_warp_kernel(n, dtype, tol, gtol):
+    """MultivariateNormal(scale_tril) beyond n = 128 (round 2: up to 1024; config 3 has H = 512): the
+    warp-per-row substitution kernel with 16 / 32 register slots per lane, against the oracle (fp64 on the
+    CPU) -- log_prob and all three gradients, factor shared by the batch and one factor per row."""
+    if EMULATE:
+        pytest.skip("kernel test")
+    torch.manual_seed(n)
+    rows = 6
+    A = torch.randn(rows, n, n, dtype=torch.float64)
+    L = torch.linalg.cholesky(A @ A.transpose(-1, -2) / n + torch.eye(n, dtype=torch.float64)).to(DEV, dtype)
+    mu = torch.randn(rows, n, dtype=torch.float64).to(DEV, dtype)
+    x = torch.randn(rows, n, dtype=torch.float64).to(DEV, dtype)
+    for mu_, L_ in ((mu, L), (mu[0], L[0])):
+        mr, Lr, xr = (t.clone().requires_grad_(True) for t in (mu_, L_, x))
+        lp = dist.MultivariateNormal(mr, scale_tril=Lr).log_prob(xr)
+        mo, Lo, xo = (t.double().cpu().requires_grad_(True) for t in (mu_, L_, x))
+        ref = odists.mvn_tril(xo, mo, Lo)
+        _close(lp, ref.detach(), tol)
+        w = torch.randn(rows, dtype=torch.float64)
+        g = torch.autograd.grad((lp * w.to(DEV, dtype)).sum(), [xr, mr, Lr])
+        go = torch.autograd.grad((ref * w).sum(), [xo, mo, Lo])
+        _close(g[0], go[0], gtol)
+        _close(g[1], go[1], gtol * (1 if mu_.dim() == 2 else rows ** 0.5))
+        _close(g[2], torch.tril(go[2]), gtol * (1 if mu_.dim() == 2 else rows ** 0.5))
