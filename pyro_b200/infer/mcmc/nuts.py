@@ -290,9 +290,10 @@ class NUTS(HMC):
                          adapt_mass_matrix=adapt_mass_matrix, full_mass=full_mass,
                          transforms=transforms, max_plate_nesting=max_plate_nesting,
                          target_accept_prob=target_accept_prob, init_strategy=init_strategy)
-        if not use_multinomial_sampling:
-            raise NotImplementedError("slice-sampling NUTS is not built; the reference default "
-                                      "(multinomial) is")
+        # slice-sampling variant (pyro/infer/mcmc/nuts.py:218-229,470-475): leaf weight 1[dE <= e] with one
+        # Exponential(1) slice variable per transition instead of exp(-dE); runs on the generic lockstep
+        # tree (the whole-transition / fused-leaf kernels implement the multinomial default)
+        self.use_multinomial_sampling = bool(use_multinomial_sampling)
         self._max_tree_depth = max_tree_depth
         self._native_small = native_small
         self._fused_leaf = fused_leaf    # model-class leaf kernel (b2_nuts_leaf_hier) when available
@@ -301,8 +302,8 @@ class NUTS(HMC):
     def setup(self, warmup_steps, num_chains, *args, **kwargs):
         super().setup(warmup_steps, num_chains, *args, **kwargs)
         self._use_native = (self._native_small and isinstance(self.potential, NativePotential)
-                            and self.D <= N.NUTS_SMALL_MAX_D)
-        self._use_fused_hier = (not self._use_native and self._fused_leaf
+                            and self.D <= N.NUTS_SMALL_MAX_D and self.use_multinomial_sampling)
+        self._use_fused_hier = (not self._use_native and self._fused_leaf and self.use_multinomial_sampling
                                 and isinstance(self.potential, HierNormalPotential))
         self._gsc = None
         if self._use_native or self._use_fused_hier:
@@ -529,6 +530,8 @@ class NUTS(HMC):
         sck = torch.empty(maxd + 1, C, D, dtype=dtype, device=dev)
         depth_reached = torch.zeros(C, dtype=torch.int32, device=dev)
 
+        # slice variable of this transition: log_slice = -energy0 - Exponential(1)
+        e_slice = None if self.use_multinomial_sampling else -torch.log1p(-self._rand(C))
         for depth in range(maxd):
             if depth > 0 and bool(done.all()):
                 break
@@ -553,11 +556,16 @@ class NUTS(HMC):
                 energy = U_new + ke
                 energy = torch.where(torch.isnan(energy), torch.full_like(energy, float("inf")), energy)
                 delta = energy - energy0
-                div_now = active & (delta > _MAX_SLICED_ENERGY)
                 acc_p = (-delta).exp().clamp(max=1.0)
                 sum_accept = sum_accept + torch.where(active, acc_p, torch.zeros_like(acc_p))
                 num_prop = num_prop + active.to(dtype)
-                w_leaf = -delta
+                if self.use_multinomial_sampling:
+                    div_now = active & (delta > _MAX_SLICED_ENERGY)
+                    w_leaf = -delta
+                else:
+                    sliced = delta - e_slice                       # energy_new + log_slice
+                    div_now = active & (sliced > _MAX_SLICED_ENERGY)
+                    w_leaf = torch.where(sliced <= 0, torch.zeros_like(delta), neg_inf)
                 if leaf == 0:
                     nw = w_leaf
                     take = active

@@ -368,3 +368,8 @@ def test_full_mass_nuts_correlated_posterior_gpu():
     """``NUTS(full_mass=True)`` (dense mass matrix via whitened coordinates) on the device."""
     from test_host_logic_cpu import _full_mass_case
     _full_mass_case(DEV)
+
+
+def test_slice_sampling_nuts_posterior_gpu():
+    from test_host_logic_cpu import _slice_nuts_case
+    _slice_nuts_case(DEV)

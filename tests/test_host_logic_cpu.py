@@ -500,3 +500,27 @@ def _full_mass_case(dev):
 
 def test_full_mass_nuts_correlated_posterior(emu):
     _full_mass_case("cpu")
+
+
+def _slice_nuts_case(dev):
+    """``NUTS(use_multinomial_sampling=False)`` (slice-sampling tree weights, pyro/infer/mcmc/nuts.py:218-229):
+    same posterior as the oracle's recursive multinomial NUTS on the 3-d logistic regression."""
+    from oracle import mcmc as omcmc
+    from pyro_b200.infer import MCMC, NUTS
+    from pyro_b200.infer.mcmc import LogisticPotential
+    torch.set_default_dtype(torch.float64)
+    g = load_npz("mcmc.npz")
+    X, y = torch.as_tensor(g["lr.X"]).to(dev), torch.as_tensor(g["lr.y"]).to(dev)
+    k = NUTS(potential_fn=LogisticPotential(X, y, 1.0), use_multinomial_sampling=False)
+    mc = MCMC(k, num_samples=150, warmup_steps=100, num_chains=8, seed=5)
+    mc.run()
+    assert not k._use_native and not k._use_fused_hier
+    s = mc.get_samples()["beta"].cpu()
+    chain = omcmc.NUTSChain(omcmc.logistic_potential(X.cpu(), y.cpu(), 1.0), 3, seed=2)
+    ref, _ = chain.run(torch.zeros(3, dtype=torch.float64), 150, 600)
+    assert torch.allclose(s.mean(0), ref.mean(0), atol=0.12)
+    assert torch.allclose(s.std(0), ref.std(0), atol=0.08)
+
+
+def test_slice_sampling_nuts_posterior(emu):
+    _slice_nuts_case("cpu")
