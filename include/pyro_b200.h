@@ -185,6 +185,45 @@ int b2_normal_rsample(const b2_tensor* loc, const b2_tensor* scale, int ndim, co
                       void* eps, void* out_sum, void* rng_state, void* stream);
 
 /*
+ * The "latent sites" block of an SVI step (pyro_b200/csrc/latent.cu): a reparameterised Normal guide site
+ * z ~ Normal(loc, scale) -- scale possibly given as log(scale), the unconstrained storage of a positive
+ * parameter (pyro/params/param_store.py:125-156) -- together with a Normal prior on the same z whose
+ * parameters need no gradient.  Replaces, per site and step, the reference's exp / randn / addcmul
+ * (torch/distributions/normal.py:82-85), both log_prob + sum chains (pyro/poutine/trace_struct.py:264-278) and
+ * their autograd backward, including the accumulation of the two gradients that reach z.
+ * A job is one site (<= B2_RSAMPLE_MAX_N elements); one CTA per job, so the sites of a step share a launch.
+ *   b2_latent_normal_draw      z, eps [shape] contiguous out; out0 = 0-d SUM log Normal(z | loc, scale);
+ *                              noise from Philox(seed, stream = job << 32 | element, launch counter)
+ *   b2_latent_normal_prior     out0 = 0-d SUM log Normal(z | prior_loc, prior_scale), value only
+ *   b2_latent_normal_backward  g = gz + prior_weight * d log p(z)/dz;  out0 = d/dloc = g,
+ *                              out1 = d/dscale = g*eps - c/scale  (or d/dlog_scale = g*eps*scale - c), each summed
+ *                              over the dims where the operand's stride is 0 (its stored shape, contiguous)
+ * loc_stride .. prior_scale_stride: element strides of the broadcast views over shape (0 = broadcast).
+ */
+#define B2_LATENT_MAX_JOBS 8
+#define B2_LATENT_LOG_SCALE 1   /* `scale` holds log(scale) */
+typedef struct {
+  int32_t dtype, ndim, flags, pad_;
+  int64_t shape[B2_MAX_DIMS];
+  int64_t loc_stride[B2_MAX_DIMS], scale_stride[B2_MAX_DIMS];
+  int64_t prior_loc_stride[B2_MAX_DIMS], prior_scale_stride[B2_MAX_DIMS];
+  const void* loc;
+  const void* scale;
+  const void* prior_loc;   /* may be NULL (draw, backward without prior) */
+  const void* prior_scale;
+  void* z;
+  void* eps;
+  const void* gz;          /* backward only; NULL = zero */
+  void* out0;
+  void* out1;
+  double c;                /* backward: coefficient of SUM log q in the loss */
+  double prior_weight;     /* backward: coefficient of SUM log p in the loss */
+} b2_latent_job;
+int b2_latent_normal_draw(const b2_latent_job* jobs, int n_jobs, void* rng_state, void* stream);
+int b2_latent_normal_prior(const b2_latent_job* jobs, int n_jobs, void* stream);
+int b2_latent_normal_backward(const b2_latent_job* jobs, int n_jobs, void* stream);
+
+/*
  * b2_reduce_to -- sum a strided full-shape tensor down to an output whose zero strides mark the
  * reduced dims (the "sum_to_size" the fused kernels do not cover in-kernel).
  */

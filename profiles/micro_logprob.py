@@ -5,6 +5,7 @@ ALGORITHMIC bytes (operands once at stored shape; + gradient outputs when reques
 fraction of the measured HBM copy peak."""
 import json
 import os
+import re
 import sys
 
 import torch
@@ -17,13 +18,15 @@ import pyro_b200 as pyro  # noqa: E402
 
 RESULTS = {}
 VERBOSE = True
+ONLY = None
 
 
-def run(verbose=True):
+def run(verbose=True, only=None):
     """Run the table; returns {row name: {ms, GBps, frac, algorithmic_bytes}} (bench.py puts it under
-    ``variants.micro`` so the driver re-measures it every round)."""
-    global VERBOSE
+    ``variants.micro`` so the driver re-measures it every round).  ``only``: regular expression selecting rows."""
+    global VERBOSE, ONLY
     VERBOSE = verbose
+    ONLY = re.compile(only) if only else None
     RESULTS.clear()
     _run()
     return dict(RESULTS)
@@ -39,6 +42,8 @@ def _run():
 
 
     def timed(name, fn, nbytes, reps=5):
+        if ONLY is not None and not ONLY.search(name):
+            return
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
@@ -111,4 +116,4 @@ def _run():
 
 
 if __name__ == "__main__":
-    run(True)
+    run(True, only=sys.argv[1] if len(sys.argv) > 1 else None)

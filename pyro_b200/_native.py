@@ -41,6 +41,24 @@ MODEL_HIER_NORMAL, MODEL_LOGISTIC = 0, 1
 NUTS_SMALL_MAX_D = 64
 
 
+LATENT_MAX_JOBS = 8
+LATENT_LOG_SCALE = 1
+LATENT_BLOCK = True       # Normal guide sites + Normal priors go through the latent-sites kernels (latent.cu)
+LAZY_PARAM = True         # positive-constrained parameters are handed out as deferred exp(u) (_lazyparam.py)
+
+
+class b2_latent_job(ctypes.Structure):
+    _fields_ = [("dtype", ctypes.c_int32), ("ndim", ctypes.c_int32), ("flags", ctypes.c_int32),
+                ("pad_", ctypes.c_int32),
+                ("shape", ctypes.c_int64 * 8),
+                ("loc_stride", ctypes.c_int64 * 8), ("scale_stride", ctypes.c_int64 * 8),
+                ("prior_loc_stride", ctypes.c_int64 * 8), ("prior_scale_stride", ctypes.c_int64 * 8),
+                ("loc", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("prior_loc", ctypes.c_void_p),
+                ("prior_scale", ctypes.c_void_p), ("z", ctypes.c_void_p), ("eps", ctypes.c_void_p),
+                ("gz", ctypes.c_void_p), ("out0", ctypes.c_void_p), ("out1", ctypes.c_void_p),
+                ("c", ctypes.c_double), ("prior_weight", ctypes.c_double)]
+
+
 class b2_tensor(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("ndim", ctypes.c_int32),
                 ("shape", ctypes.c_int64 * B2_MAX_DIMS), ("stride", ctypes.c_int64 * B2_MAX_DIMS)]
@@ -83,6 +101,9 @@ SIGNATURES = {
                               _vp, _tp, _tp, _vp, _sz, _vp]),
     "b2_reduce_to": (_i32, [_tp, _tp, _vp, _sz, _vp]),
     "b2_normal_rsample": (_i32, [_tp, _tp, _i32, ctypes.POINTER(ctypes.c_int64), _vp, _vp, _vp, _vp, _vp]),
+    "b2_latent_normal_draw": (_i32, [_vp, _i32, _vp, _vp]),
+    "b2_latent_normal_prior": (_i32, [_vp, _i32, _vp]),
+    "b2_latent_normal_backward": (_i32, [_vp, _i32, _vp]),
     "b2_elbo_combine": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "b2_glm_bernoulli_logits": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32,
                                        _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -162,6 +183,9 @@ def desc(t, shape=None):
         d.dtype = 0
         d.ndim = len(shape) if shape is not None else 0
         return d
+    if type(t) is not torch.Tensor and hasattr(t, "dense"):
+        # a storage-less lazy tensor: the caller must materialise it BEFORE the autograd boundary
+        raise RuntimeError("pyro_b200: a lazy tensor (%s) reached the native boundary" % type(t).__name__)
     if shape is not None and tuple(t.shape) != tuple(shape):
         t = t.expand(shape)
     nd = t.dim()

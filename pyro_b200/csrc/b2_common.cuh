@@ -40,6 +40,18 @@ struct Pack {
   T v[VecOf<T>::N];
 };
 
+// N-element vector type of T (N * sizeof(T) <= 16)
+template <typename T, int N>
+struct VecN;
+template <>
+struct VecN<float, 4> { using type = float4; };
+template <>
+struct VecN<float, 2> { using type = float2; };
+template <>
+struct VecN<double, 2> { using type = double2; };
+template <>
+struct VecN<double, 1> { using type = double; };
+
 // streaming load (read-once data): evict-first in L1/L2
 template <typename T>
 __device__ __forceinline__ Pack<T> ld_stream(const T* p) {

@@ -7,6 +7,8 @@
 // afterwards by b2_reduce_to (deterministic two-stage tree, no float atomics).
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "b2_common.cuh"
 #include "b2_math.cuh"
 
@@ -34,6 +36,8 @@ struct EventArgs {
   unsigned int* ticket;
   int g_log2;  // lanes per row = 1 << g_log2
 };
+
+constexpr int kEvIdx32 = 1 << 29;  // EventArgs::flags: one merged batch dim, every operand offset fits 32 bits
 
 template <typename T>
 __device__ __forceinline__ T group_sum(T v, int G) {
@@ -431,6 +435,162 @@ __global__ void __launch_bounds__(256) mvn_tril_kernel(const EventArgs a) {
   grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
 }
 
+// ---- MVN, n <= 32: a group of G lanes (G = 2, 4, 8 or 32 >= n) owns a batch row ----------------------------
+// Lane j holds ROW j of the factor (Lr[k] = L[j][k]), so forward substitution is a chain of broadcasts:
+//   pivot i:  z_i = r_i / L_ii is final on lane i -> one shuffle -> every lane j > i does r_j -= L[j][i] z_i
+// i.e. ~35 cycles per pivot (shuffle + FMA) instead of the five dependent shuffle/add steps of a group
+// reduction per pivot, which is what a column-owning lane needs (mvn_warp32_kernel of round 1: ~6 us per 32x32
+// row, 16 warps resident -> 19 % of the HBM peak; the thread-per-row kernel for n <= 8 walked L with 4-byte
+// loads 4*n*n bytes apart across a warp and ran fully unrolled to 8 whatever n was: 26 % at n = 8).  Rows are read
+// coalesced: G <= 8 as 16-byte (8-byte for G = 2) chunks of consecutive lanes, G = 32 as 32 row-major 128-byte
+// lines staged through a padded shared-memory tile and read back transposed.  The gradient pass needs the
+// columns as well (w = L^-T z is a broadcast chain for COLUMN owners); they come from the same tile / from L1.
+template <typename T, int G>
+struct MvnGroupCfg {
+  static constexpr int kThreads = (G == 32 && sizeof(T) == 8) ? 128 : 256;   // static shared memory <= 48 KB
+  static constexpr int kTile = (G == 32) ? (kThreads / 32) * 32 * 33 : 1;
+};
+
+// FULL: n == G (no per-pivot bounds tests, constant address offsets).  IDX32: one merged batch dim whose offsets
+// fit 32 bits (one IMAD per operand instead of a 64-bit multiply chain: with G = 2 a warp iteration is 16 rows
+// of 36 bytes and the offset arithmetic alone was a third of its instructions).
+template <typename T, bool GRAD, int G, bool FULL>
+__global__ void __launch_bounds__(MvnGroupCfg<T, G>::kThreads) mvn_group_kernel(const EventArgs a) {
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
+  const int n = FULL ? G : a.K;
+  const T* xp = reinterpret_cast<const T*>(a.x.ptr);
+  const T* mup = reinterpret_cast<const T*>(a.p0.ptr);
+  const T* Lp = reinterpret_cast<const T*>(a.p1.ptr);
+  const int64_t nrows_pad = ((a.nbatch + ngroups - 1) / ngroups) * ngroups;
+  const bool in = FULL || lane < n;
+  const bool idx32 = (a.flags & kEvIdx32) != 0;
+  const T scale = (T)a.scale, f0 = (T)(a.weight * a.scale);
+  __shared__ T tile[MvnGroupCfg<T, G>::kTile];
+  T* tw = tile + ((G == 32) ? (threadIdx.x >> 5) * 32 * 33 : 0);
+  // dense rows whose length is the group width are read in 16-byte (8-byte) chunks
+  constexpr int V = (G >= 4) ? ((sizeof(T) == 4) ? 4 : 2) : ((sizeof(T) == 4) ? 2 : 1);
+  const bool vec_rows = FULL && (G <= 8) && (reinterpret_cast<uintptr_t>(Lp) % 16 == 0) && (a.ndim <= 1) &&
+                        (a.p1.st[0] % 4 == 0);
+  T acc = (T)0;
+  for (int64_t row = gid; row < nrows_pad; row += ngroups) {
+    const bool live = row < a.nbatch;
+    int64_t ox, op0, op1, om = 0, ou = 0, olp = 0, ogx = 0, ogp0 = 0, ogp1 = 0;
+    if (idx32) {
+      const int r32 = live ? (int)row : 0;
+      ox = r32 * (int)a.x.st[0];
+      op0 = r32 * (int)a.p0.st[0];
+      op1 = r32 * (int)a.p1.st[0];
+      if (a.mask.ptr) om = r32 * (int)a.mask.st[0];
+      if (a.lp.ptr) olp = r32 * (int)a.lp.st[0];
+      if (GRAD) {
+        if (a.up.ptr) ou = r32 * (int)a.up.st[0];
+        ogx = r32 * (int)a.gx.st[0];
+        ogp0 = r32 * (int)a.gp0.st[0];
+        ogp1 = r32 * (int)a.gp1.st[0];
+      }
+    } else {
+      batch_offsets(a, live ? row : 0, ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1);
+    }
+    const T* L = Lp + op1;
+    // Lr[k] = L[lane][k], Lc[r] = L[r][lane]; entries above the diagonal and outside n are never used (forward
+    // substitution touches Lr[i] on lanes > i, back substitution Lc[j] on lanes < j), so nothing is masked here
+    T Lr[G], Lc[GRAD ? G : 1];
+    T dg = (T)1;
+    if constexpr (G == 32) {
+#pragma unroll
+      for (int r = 0; r < G; ++r)
+        tw[r * 33 + lane] = (FULL || (r < n && in)) ? __ldcs(L + (FULL ? r * G : r * n) + lane) : (T)0;
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < G; ++k) Lr[k] = tw[lane * 33 + k];
+      dg = tw[lane * 33 + lane];
+      if (GRAD) {
+#pragma unroll
+        for (int r = 0; r < G; ++r) Lc[GRAD ? r : 0] = tw[r * 33 + lane];
+      }
+      __syncwarp();
+    } else {
+      if (vec_rows) {
+        using VT = typename VecN<T, V>::type;
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) {
+          const VT v = __ldcs(reinterpret_cast<const VT*>(L + lane * G) + c);
+          const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+          for (int j = 0; j < V; ++j) Lr[c * V + j] = e[j];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < G; ++k) Lr[k] = (in && (FULL || k < n)) ? L[lane * n + k] : (T)0;
+      }
+      if (GRAD) {
+#pragma unroll
+        for (int r = 0; r < G; ++r) Lc[GRAD ? r : 0] = (in && (FULL || r < n)) ? L[r * n + lane] : (T)0;
+      }
+#pragma unroll
+      for (int k = 0; k < G; ++k) dg = (k == lane) ? Lr[k] : dg;
+    }
+    if (!FULL) dg = in ? dg : (T)1;
+    const T idg = (sizeof(T) == 4) ? fast_rcp(dg) : (T)1 / dg;
+    T r = in ? xp[ox + lane] - mup[op0 + lane] : (T)0;
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      if (FULL || i < n) {  // uniform
+        const T zi = __shfl_sync(0xffffffffu, r * idg, i, G);
+        r = (lane > i) ? r - Lr[i] * zi : r;
+      }
+    }
+    const T z = r * idg;
+    const T m2 = group_sum(in ? z * z : (T)0, G);
+    const T logdet = group_sum(in ? ((sizeof(T) == 4) ? fast_log(dg) : b2_log(dg)) : (T)0, G);
+    const T lp = (T)-0.5 * ((T)n * ((T)2 * Consts<T>::kLogSqrt2Pi) + m2) - logdet;
+    const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
+    const T slp = (m && live) ? lp * scale : (T)0;
+    if (lane == 0 && live) {
+      acc += slp;
+      if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[olp] = slp;
+    }
+    if (GRAD) {
+      T f = m ? f0 : (T)0;
+      if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[ou];
+      T sacc = (T)0, w = (T)0;
+#pragma unroll
+      for (int j = G - 1; j >= 0; --j) {
+        if (FULL || j < n) {
+          if (lane == j) w = (z - sacc) * idg;
+          const T wj = __shfl_sync(0xffffffffu, w, j, G);
+          if (lane < j) sacc += Lc[GRAD ? j : 0] * wj;  // Lc[j] on lane i is L[j][i]
+        }
+      }
+      if (live && in) {
+        if (a.gx.ptr) reinterpret_cast<T*>(a.gx.ptr)[ogx + lane] = m ? -f * w : (T)0;
+        if (a.gp0.ptr) reinterpret_cast<T*>(a.gp0.ptr)[ogp0 + lane] = m ? f * w : (T)0;
+      }
+      if (a.gp1.ptr) {
+        // dL[i][j] = f (w_i z_j - [i == j] / L_ii) for j <= i, 0 above the diagonal; lane j writes column j
+        T* gL = reinterpret_cast<T*>(a.gp1.ptr) + ogp1;
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          if (FULL || i < n) {
+            const T wi = __shfl_sync(0xffffffffu, w, i, G);
+            if (live && in) {
+              T g = (T)0;
+              if (lane < i) g = wi * z;
+              else if (lane == i) g = wi * z - idg;
+              gL[i * n + lane] = m ? f * g : (T)0;
+            }
+          }
+        }
+      }
+    }
+  }
+  __shared__ double smem[32];
+  double red[1] = {(double)acc};
+  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
+}
+
 // ---- generic strided sum-to ---------------------------------------------------------------------
 struct ReduceArgs {
   int nk, nr;                     // kept / reduced dims
@@ -534,13 +694,20 @@ __global__ void reduce_to_finish_kernel(const ReduceArgs a) {
 }
 
 
-// ---- larger event sizes (K a multiple of 4, rows 16-byte aligned): 16-byte loads, two rows per group in
-// flight.  G = min(32, K/4) lanes own a row, each lane walks float4 / double2 chunks; one iteration
-// of a group handles rows (row, row + ngroups) so two independent chains of loads / special functions /
-// shuffles overlap.  The scalar group kernels measured 9-13% of the HBM peak at K = 64.
+// ---- larger event sizes (K a multiple of the vector width, rows 16-byte aligned) ---------------------------
+// G = min(32, K/V/4) lanes own a row and each lane takes kChunks = 4 16-byte chunks per step, for two rows
+// (row, row + ngroups) at once: 8 independent 16-byte loads in flight per thread, and the per-row overhead --
+// the group reductions, the row's own special functions, offsets, the mask -- is spread over >= 16 elements per
+// lane.  History: scalar sub-warp groups measured 9-13 % of the HBM peak at K = 64 (round 1); one chunk per lane
+// (G = K/V lanes) 33-36 %: ncu showed that version ISSUE-bound, not memory-bound (issue slots 75-81 % busy at 51
+// (Categorical) / 91 (Dirichlet) instructions per element, most of them per-row work amortised over only 4
+// elements per lane) -- requesting the next rows early changed nothing (profiles/micro_logprob_r2.md).
+constexpr int kChunks = 4;
+
 template <typename T, bool GRAD>
 __global__ void __launch_bounds__(256) dirichlet_vec_kernel(const EventArgs a) {
   constexpr int V = VecOf<T>::N;
+  constexpr int UR = 1;  // one row per group in flight: 8 chunks (conc + value) already hold 32 registers
   const int G = 1 << a.g_log2;
   const int lane = threadIdx.x & (G - 1);
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> a.g_log2;
@@ -548,58 +715,73 @@ __global__ void __launch_bounds__(256) dirichlet_vec_kernel(const EventArgs a) {
   const T* xp = reinterpret_cast<const T*>(a.x.ptr);
   const T* cp = reinterpret_cast<const T*>(a.p0.ptr);
   const int KV = a.K / V;
-  const int64_t nrows_pad = ((a.nbatch + 2 * ngroups - 1) / (2 * ngroups)) * (2 * ngroups);
+  const int64_t nrows_pad = ((a.nbatch + UR * ngroups - 1) / (UR * ngroups)) * (UR * ngroups);
+  const T scale = (T)a.scale, f0 = (T)(a.weight * a.scale);
   T acc = (T)0;
-  for (int64_t row0 = gid; row0 < nrows_pad; row0 += 2 * ngroups) {
-    T s_xlogy[2] = {0, 0}, s_conc[2] = {0, 0}, s_lg[2] = {0, 0};
-    bool live[2];
-    int64_t rows[2];
+  for (int64_t row0 = gid; row0 < nrows_pad; row0 += UR * ngroups) {
+    T s_xlogy[UR], s_conc[UR], s_lg[UR];
+    bool live[UR];
+    int64_t rows[UR];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UR; ++u) {
       rows[u] = row0 + u * ngroups;
       live[u] = rows[u] < a.nbatch;
       if (!live[u]) rows[u] = 0;
+      s_xlogy[u] = s_conc[u] = s_lg[u] = (T)0;
     }
-    for (int kv = lane; kv < KV; kv += G) {
-      Pack<T> cv[2], xv[2];
+    for (int kv0 = lane; kv0 < KV; kv0 += kChunks * G) {
+      Pack<T> cv[UR][kChunks], xv[UR][kChunks];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        cv[u] = ld_stream(cp + rows[u] * a.p0.st[0] + kv * V);
-        xv[u] = ld_stream(xp + rows[u] * a.x.st[0] + kv * V);
+      for (int u = 0; u < UR; ++u) {
+        const T* cr = cp + rows[u] * a.p0.st[0];
+        const T* xr = xp + rows[u] * a.x.st[0];
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int kv = kv0 + c * G;
+          if (kv < KV) {
+            cv[u][c] = ld_stream(cr + kv * V);
+            xv[u][c] = ld_stream(xr + kv * V);
+          }
+        }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < UR; ++u) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const T c = cv[u].v[j];
-          s_xlogy[u] += xlogy_fast(c - (T)1, xv[u].v[j]);
-          s_conc[u] += c;
-          T lgc, unused;
-          lgamma_digamma<T, false>(c, lgc, unused);
-          s_lg[u] += lgc;
+        for (int c = 0; c < kChunks; ++c) {
+          if (kv0 + c * G < KV) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const T cc = cv[u][c].v[j];
+              s_xlogy[u] += xlogy_fast(cc - (T)1, xv[u][c].v[j]);
+              s_conc[u] += cc;
+              T lgc, unused;
+              lgamma_digamma<T, false>(cc, lgc, unused);
+              s_lg[u] += lgc;
+            }
+          }
         }
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UR; ++u) {
       s_xlogy[u] = group_sum(s_xlogy[u], G);
       s_conc[u] = group_sum(s_conc[u], G);
       s_lg[u] = group_sum(s_lg[u], G);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UR; ++u) {
       const int64_t row = rows[u];
       T lgsum, psum;
       lgamma_digamma<T, GRAD>(s_conc[u], lgsum, psum);
       const T lp = s_xlogy[u] + lgsum - s_lg[u];
       const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[row * a.mask.st[0]] != 0 : true;
-      const T slp = (m && live[u]) ? lp * (T)a.scale : (T)0;
+      const T slp = (m && live[u]) ? lp * scale : (T)0;
       if (lane == 0 && live[u]) {
         acc += slp;
         if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[row * a.lp.st[0]] = slp;
       }
       if (GRAD && live[u]) {
-        T f = m ? (T)(a.weight * a.scale) : (T)0;
+        T f = m ? f0 : (T)0;
         if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[row * a.up.st[0]];
         for (int kv = lane; kv < KV; kv += G) {
           const Pack<T> cv = ld_keep(cp + row * a.p0.st[0] + kv * V);
@@ -627,7 +809,7 @@ __global__ void __launch_bounds__(256) dirichlet_vec_kernel(const EventArgs a) {
 template <typename T, bool GRAD>
 __global__ void __launch_bounds__(256) categorical_vec_kernel(const EventArgs a) {
   constexpr int V = VecOf<T>::N;
-  constexpr int UR = 2;  // rows in flight per lane group (4 measured slower: 57% -> 41% at K = 1024)
+  constexpr int UR = 2;  // rows in flight per lane group
   const int G = 1 << a.g_log2;
   const int lane = threadIdx.x & (G - 1);
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> a.g_log2;
@@ -636,6 +818,7 @@ __global__ void __launch_bounds__(256) categorical_vec_kernel(const EventArgs a)
   const T* lgp = reinterpret_cast<const T*>(a.p0.ptr);
   const int KV = a.K / V;
   const int64_t nrows_pad = ((a.nbatch + UR * ngroups - 1) / (UR * ngroups)) * (UR * ngroups);
+  const T scale = (T)a.scale, f0 = (T)(a.weight * a.scale);
   T acc = (T)0;
   for (int64_t row0 = gid; row0 < nrows_pad; row0 += UR * ngroups) {
     bool live[UR];
@@ -650,21 +833,39 @@ __global__ void __launch_bounds__(256) categorical_vec_kernel(const EventArgs a)
       se[u] = (T)0;
       vidx[u] = vp[rows[u] * a.x.st[0]];  // issued first: overlaps the logits stream
     }
-    // online logsumexp: one pass over the logits (running max + rescaled sum), then a group merge
-    for (int kv = lane; kv < KV; kv += G) {
-      Pack<T> lv[UR];
-#pragma unroll
-      for (int u = 0; u < UR; ++u) lv[u] = ld_keep(lgp + rows[u] * a.p0.st[0] + kv * V);
+    // online logsumexp, one step = up to kChunks chunks per lane per row: max of the step first, ONE
+    // rescale of the running sum, then the exponentials
+    for (int kv0 = lane; kv0 < KV; kv0 += kChunks * G) {
+      Pack<T> lv[UR][kChunks];
 #pragma unroll
       for (int u = 0; u < UR; ++u) {
-        T cm = lv[u].v[0];
+        const T* lr = lgp + rows[u] * a.p0.st[0];
 #pragma unroll
-        for (int j = 1; j < V; ++j) cm = b2_max(cm, lv[u].v[j]);
+        for (int c = 0; c < kChunks; ++c) {
+          const int kv = kv0 + c * G;
+          if (kv < KV) lv[u][c] = ld_keep(lr + kv * V);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        T cm = -b2_inf<T>();
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          if (kv0 + c * G < KV) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) cm = b2_max(cm, lv[u][c].v[j]);
+          }
+        }
         const T nm = b2_max(mx[u], cm);
-        T s = (mx[u] == -b2_inf<T>()) ? (T)0 : se[u] * fast_exp(mx[u] - nm);
+        T sacc = (mx[u] == -b2_inf<T>()) ? (T)0 : se[u] * fast_exp(mx[u] - nm);
 #pragma unroll
-        for (int j = 0; j < V; ++j) s += fast_exp(lv[u].v[j] - nm);
-        se[u] = s;
+        for (int c = 0; c < kChunks; ++c) {
+          if (kv0 + c * G < KV) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) sacc += fast_exp(lv[u][c].v[j] - nm);
+          }
+        }
+        se[u] = sacc;
         mx[u] = nm;
       }
     }
@@ -684,13 +885,13 @@ __global__ void __launch_bounds__(256) categorical_vec_kernel(const EventArgs a)
       const bool inb = v >= 0 && v < a.K;
       const T lp = inb ? lg[inb ? v : 0] - lse : b2_nan<T>();
       const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[row * a.mask.st[0]] != 0 : true;
-      const T slp = (m && live[u]) ? lp * (T)a.scale : (T)0;
+      const T slp = (m && live[u]) ? lp * scale : (T)0;
       if (lane == 0 && live[u]) {
         acc += slp;
         if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[row * a.lp.st[0]] = slp;
       }
       if (GRAD && live[u] && a.gp0.ptr) {
-        T f = m ? (T)(a.weight * a.scale) : (T)0;
+        T f = m ? f0 : (T)0;
         if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[row * a.up.st[0]];
         for (int kv = lane; kv < KV; kv += G) {
           const Pack<T> lv = ld_keep(lg + kv * V);
@@ -791,97 +992,6 @@ __global__ void __launch_bounds__(256) mvn_rowthread_kernel(const EventArgs a) {
   grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
 }
 
-
-// ---- MVN, 8 < n <= 32: one warp per row, the factor in registers ---------------------------------------
-// Lane j preloads COLUMN j of the row's scale_tril with n coalesced loads issued back to back
-// (Lc[r] = L[r][j]; identity outside n), so the triangular solves never wait on memory:
-//   forward  z = L^-1 (x - mu): pivot i needs <L[i][:i], z[:i]> = warp_sum(Lc[i] * z) over lanes < i;
-//            lane i then finishes z_i locally (it holds L_ii and its own residual);
-//   backward w = L^-T z: lane i accumulates s_i = sum_{j>i} L[j][i] w_j from ITS OWN column, one
-//            broadcast of w_j per pivot;
-//   dL[i][j] = f (w_i z_j - [i==j]/L_ii), written by column owners (coalesced rows).
-// The generic kernel above reloads L from memory inside the dependent pivot loop (7% of HBM at n=32).
-template <typename T, bool GRAD>
-__global__ void __launch_bounds__(256) mvn_warp32_kernel(const EventArgs a) {
-  constexpr int N = 32;
-  const int lane = threadIdx.x & 31;
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int n = a.K;
-  const T* xp = reinterpret_cast<const T*>(a.x.ptr);
-  const T* mup = reinterpret_cast<const T*>(a.p0.ptr);
-  const T* Lp = reinterpret_cast<const T*>(a.p1.ptr);
-  const int64_t nrows_pad = ((a.nbatch + nwarps - 1) / nwarps) * nwarps;
-  const bool in = lane < n;
-  T acc = (T)0;
-  for (int64_t row = wid; row < nrows_pad; row += nwarps) {
-    const bool live = row < a.nbatch;
-    int64_t ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1;
-    batch_offsets(a, live ? row : 0, ox, op0, op1, om, ou, olp, ogx, ogp0, ogp1);
-    const T* L = Lp + op1;
-    T Lc[N];
-#pragma unroll
-    for (int r = 0; r < N; ++r) Lc[r] = (r < n && in && lane <= r) ? L[(int64_t)r * n + lane] : ((r == lane) ? (T)1 : (T)0);
-    const T b = in ? xp[ox + lane] - mup[op0 + lane] : (T)0;
-    // diagonal of this lane's column index
-    T dg = (T)1;
-#pragma unroll
-    for (int r = 0; r < N; ++r) dg = (r == lane) ? Lc[r] : dg;
-    const T idg = (T)1 / dg;
-    T z = (T)0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      if (i < n) {  // uniform
-        const T part = warp_sum((lane < i) ? Lc[i] * z : (T)0);
-        if (lane == i) z = (b - part) * idg;
-      }
-    }
-    const T m2 = warp_sum(in ? z * z : (T)0);
-    const T logdet = warp_sum(in ? ((sizeof(T) == 4) ? fast_log(dg) : b2_log(dg)) : (T)0);
-    const T lp = (T)-0.5 * ((T)n * ((T)2 * Consts<T>::kLogSqrt2Pi) + m2) - logdet;
-    const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
-    const T slp = (m && live) ? lp * (T)a.scale : (T)0;
-    if (lane == 0 && live) {
-      acc += slp;
-      if (a.lp.ptr) reinterpret_cast<T*>(a.lp.ptr)[olp] = slp;
-    }
-    if (GRAD) {
-      T f = m ? (T)(a.weight * a.scale) : (T)0;
-      if (a.up.ptr) f *= reinterpret_cast<const T*>(a.up.ptr)[ou];
-      T s = (T)0, w = (T)0;
-#pragma unroll
-      for (int j = N - 1; j >= 0; --j) {
-        if (j < n) {
-          if (lane == j) w = (z - s) * idg;
-          const T wj = __shfl_sync(0xffffffffu, w, j);
-          if (lane < j) s += Lc[j] * wj;  // Lc[j] on lane i is L[j][i]
-        }
-      }
-      if (live && in) {
-        if (a.gx.ptr) reinterpret_cast<T*>(a.gx.ptr)[ogx + lane] = m ? -f * w : (T)0;
-        if (a.gp0.ptr) reinterpret_cast<T*>(a.gp0.ptr)[ogp0 + lane] = m ? f * w : (T)0;
-      }
-      if (a.gp1.ptr) {
-        T* gL = reinterpret_cast<T*>(a.gp1.ptr) + ogp1;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          if (i < n) {
-            const T wi = __shfl_sync(0xffffffffu, w, i);
-            if (live && in) {
-              T g = (T)0;
-              if (lane < i) g = wi * z;
-              else if (lane == i) g = wi * z - idg;
-              gL[(int64_t)i * n + lane] = m ? f * g : (T)0;
-            }
-          }
-        }
-      }
-    }
-  }
-  __shared__ double smem[32];
-  double red[1] = {(double)acc};
-  grid_finish<1>(red, a.partials, a.ticket, smem, [&](int, double tot) { finish_sum<T>(a, tot); });
-}
 
 }  // namespace b2
 
@@ -1006,31 +1116,58 @@ extern "C" int b2_event_score(int family, const b2_tensor* value, const b2_tenso
     vec_rows_ok = vec_rows_ok && al(a.p0.ptr, a.p0.st[0]) && al(a.gp0.ptr, a.gp0.st[0]);
     if (family == B2_DIRICHLET) vec_rows_ok = vec_rows_ok && al(a.x.ptr, a.x.st[0]) && al(a.gx.ptr, a.gx.st[0]);
   }
-  if (family == B2_MVN_TRIL && cd <= 1 && event_size <= 8 && nb >= 1024) {
+  if (family == B2_MVN_TRIL && cd <= 1 && event_size <= 4 && nb >= 1024) {
+    // tiny events: one thread per row (measured at n = 2: 43 % of the HBM peak against 37 % for lane groups)
     blocks = (nb + 255) / 256;
     if (blocks > cap * 2) blocks = cap * 2;
     if (dtype == B2_F32) {
-      if (grad) mvn_rowthread_kernel<float, true, 8><<<(unsigned)blocks, 256, 0, s>>>(a);
-      else mvn_rowthread_kernel<float, false, 8><<<(unsigned)blocks, 256, 0, s>>>(a);
+      if (grad) mvn_rowthread_kernel<float, true, 4><<<(unsigned)blocks, 256, 0, s>>>(a);
+      else mvn_rowthread_kernel<float, false, 4><<<(unsigned)blocks, 256, 0, s>>>(a);
     } else {
-      if (grad) mvn_rowthread_kernel<double, true, 8><<<(unsigned)blocks, 256, 0, s>>>(a);
-      else mvn_rowthread_kernel<double, false, 8><<<(unsigned)blocks, 256, 0, s>>>(a);
+      if (grad) mvn_rowthread_kernel<double, true, 4><<<(unsigned)blocks, 256, 0, s>>>(a);
+      else mvn_rowthread_kernel<double, false, 4><<<(unsigned)blocks, 256, 0, s>>>(a);
     }
   }
   else if (family == B2_MVN_TRIL && event_size <= 32) {
-    blocks = (nb + 7) / 8;
-    if (blocks > cap) blocks = cap;
+    const int G = event_size <= 2 ? 2 : (event_size <= 4 ? 4 : (event_size <= 8 ? 8 : 32));
+    const int threads = (G == 32 && dtype != B2_F32) ? 128 : 256;
+    blocks = (nb * G + threads - 1) / threads;
+    if (blocks > cap * 2) blocks = cap * 2;
     if (blocks < 1) blocks = 1;
-    B2_EV_LAUNCH(mvn_warp32_kernel)
+    const bool full = event_size == G;
+    {
+      int64_t mx = 0;
+      for (int o = 0; o < 9; ++o)
+        for (int i = 0; i < cd; ++i) { const int64_t v = ost[o][i] < 0 ? -ost[o][i] : ost[o][i]; if (v > mx) mx = v; }
+      if (cd <= 1 && (double)nb * (double)(mx > 0 ? mx : 1) + 2.0 * event_size * event_size < 2147483647.0)
+        a.flags |= kEvIdx32;
+    }
+#define B2_MVN_GROUP2(TT, GR, GG)                                                                   \
+    if (full) mvn_group_kernel<TT, GR, GG, true><<<(unsigned)blocks, threads, 0, s>>>(a);           \
+    else mvn_group_kernel<TT, GR, GG, false><<<(unsigned)blocks, threads, 0, s>>>(a);
+#define B2_MVN_GROUP(GG)                                                                          \
+    if (dtype == B2_F32) {                                                                          \
+      if (grad) { B2_MVN_GROUP2(float, true, GG) } else { B2_MVN_GROUP2(float, false, GG) }         \
+    } else {                                                                                        \
+      if (grad) { B2_MVN_GROUP2(double, true, GG) } else { B2_MVN_GROUP2(double, false, GG) }       \
+    }
+    if (G == 2) { B2_MVN_GROUP(2) }
+    else if (G == 4) { B2_MVN_GROUP(4) }
+    else if (G == 8) { B2_MVN_GROUP(8) }
+    else { B2_MVN_GROUP(32) }
+#undef B2_MVN_GROUP2
+#undef B2_MVN_GROUP
   }
   else if (family != B2_MVN_TRIL && cd <= 1 && !rowthread && vec_rows_ok) {
-    // lanes per row: K/V chunks, at most a warp
+    // lanes per row: the largest power of two <= K/V/4 (each lane takes 4 chunks per step), at most a warp
+    // (measured: doubling the lanes costs Categorical K = 64 53 -> 37 %, halving them gains Dirichlet K = 64
+    // 60 -> 64 % but costs Categorical 53 -> 51 %; profiles/micro_logprob_r2.md)
     int lgv = 0;
     const int V = (dtype == B2_F32) ? 4 : 2;
-    while (lgv < 5 && (1 << lgv) < event_size / V) ++lgv;
+    while (lgv < 5 && (2 << lgv) <= event_size / V / 4) ++lgv;
     a.g_log2 = lgv;
     const int64_t rpb = 256 >> lgv;
-    const int64_t ur = 2;  // rows in flight per lane group (both kernels)
+    const int64_t ur = (family == B2_DIRICHLET) ? 1 : 2;  // rows in flight per lane group
     blocks = (nb + ur * rpb - 1) / (ur * rpb);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;

@@ -96,6 +96,8 @@ extern "C" int b2_site_score(int family, const b2_tensor* value, const b2_tensor
   a.n = n;
   a.scale = scale;
   a.weight = weight;
+  a.scale32 = (float)scale;
+  a.f032 = (float)(weight * scale);
   a.sum_coeff = sum_coeff;
   a.flags = flags;
   a.out_sum = out_sum;

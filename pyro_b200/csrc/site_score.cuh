@@ -10,6 +10,7 @@
 //                       no integer division in the loop.  This is the HBM-roofline kernel.
 //   site_gen_kernel  -- any strides up to kMaxD dims; one element per thread iteration.
 #pragma once
+#include <stdlib.h>
 #include "b2_common.cuh"
 #include "b2_math.cuh"
 
@@ -38,6 +39,8 @@ struct SiteArgs {
   OutOpnd gx;
   OutOpnd gp[B2_MAX_PARAMS];
   double scale, weight, sum_coeff;
+  float scale32, f032;  // (float)scale and (float)(weight*scale): fp32 kernels read these straight from the
+                        // constant bank (the compiler re-converted the doubles PER ELEMENT: F2F.F32.F64)
   int flags;
   void* out_sum;
   double* partials;
@@ -54,6 +57,15 @@ constexpr int64_t kSmallN = B2_SITE_SMALL_N;  // sites up to this many elements 
 constexpr int kSmallThreads = 1024;
 static_assert((1 + B2_MAX_PARAMS) * kSmallN * sizeof(double) <= sizeof(double) * kMaxRed * kMaxPartialBlocks,
               "mode-3 slabs must fit in the partials region of the reduce workspace");
+
+template <typename T>
+__device__ __forceinline__ T site_scale(const SiteArgs& a) {
+  return sizeof(T) == 4 ? (T)a.scale32 : (T)a.scale;
+}
+template <typename T>
+__device__ __forceinline__ T site_f0(const SiteArgs& a) {
+  return sizeof(T) == 4 ? (T)a.f032 : (T)(a.weight * a.scale);
+}
 
 template <typename T>
 __device__ __forceinline__ void finish_outputs(const SiteArgs& a, int k, double tot) {
@@ -101,6 +113,7 @@ struct VecBody {
   T* gpr[NP];
   T xs, ps[NP], us;
   bool u_vec, m_vec;
+  bool want_dx;  // somebody reads the value gradient (a latent site); observed sites skip its extra SFU work
   // operand registers (invariant ones persist across rows)
   Pack<T> xv[NVEC], pv[NVEC][NP];
   // value-only term of a row-invariant value (b2_math.cuh ValueAux): once per column, not per row
@@ -145,6 +158,24 @@ struct VecBody {
         }
       }
     }
+    // one-scalar-per-row operands are spread into the operand registers ONCE per row here; selecting
+    // `p_vec ? vector : scalar` per element re-derived the predicate from the constant bank every time
+    // (LDC + 2 ISETP + FSEL per operand per element: ~12 of Gamma's 75 instructions per element)
+    if (HASV && !x_vec) {
+#pragma unroll
+      for (int u = 0; u < NVEC; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) xv[u].v[j] = xs;
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      if (!p_vec[k]) {
+#pragma unroll
+        for (int u = 0; u < NVEC; ++u)
+#pragma unroll
+          for (int j = 0; j < V; ++j) pv[u][k].v[j] = ps[k];
+      }
+    }
 #pragma unroll
     for (int u = 0; u < NVEC; ++u) {
       const int64_t c = (cv + u * cstep) * V;
@@ -153,9 +184,10 @@ struct VecBody {
       for (int j = 0; j < V; ++j) {
         T pl[NP];
 #pragma unroll
-        for (int k = 0; k < NP; ++k) pl[k] = p_vec[k] ? pv[u][k].v[j] : ps[k];
-        const T xe = HASV ? (x_vec ? xv[u].v[j] : xs) : (T)0;
+        for (int k = 0; k < NP; ++k) pl[k] = pv[u][k].v[j];
+        const T xe = HASV ? xv[u].v[j] : (T)0;
         ElemOut<T> o;
+        o.want_dx = want_dx;
         if constexpr (VA::kHas) {
           if (x_vec && x_inv) Eval<FAM, T, GRAD>::run_aux(xe, xa[u][j], pl, o);
           else Eval<FAM, T, GRAD>::run(xe, pl, o);
@@ -234,8 +266,9 @@ struct VecBody {
       p_vec[k] = a.p[k].st[1] == 1;
       p_inv[k] = a.p[k].st[0] == 0 && a.R > 1;
     }
-    scale = (T)a.scale;
-    f0 = (T)(a.weight * a.scale);
+    scale = site_scale<T>(a);
+    f0 = site_f0<T>(a);
+    want_dx = a.gx.mode != 0;
     ur = nullptr;
     mr = nullptr;
     us = (T)1;
@@ -244,24 +277,26 @@ struct VecBody {
   }
 };
 
-// Vectors in flight per operand per thread.  Forward-only fp32 kernels are pure streams: 4 vectors
-// (measured 87% of the HBM copy peak for Normal).  Kernels that also write gradients carry more
-// live registers; 2 vectors keep them at 3 resident CTAs per SM.
-// (Round 2 tried 4 vectors in flight for the one-parameter gradient kernels as well: 128 registers, 2 CTAs
-// per SM, and no gain -- Bernoulli 67.9 -> 69.8 %, HalfCauchy 71.2 -> 69.5 %, Exponential 65.7 -> 64.3 % of
-// the HBM peak -- so the policy stays as it was.)
-template <int NP, typename T, bool GRAD>
+// Vectors in flight per operand per thread.  Forward-only fp32 kernels of the cheap families are pure streams: 4
+// vectors (measured 85 % of the HBM copy peak for Normal).  Kernels that also write gradients carry more live
+// registers, and the lgamma families (Gamma, Beta, Poisson) are bound by instruction issue, not by loads in
+// flight: 2 vectors (measured, forward-only: Gamma 64.3 -> 69.5 %, Beta 41.5 -> 45.6 %, Poisson 52.5 -> 55.3 % of
+// the HBM peak against 4 vectors; profiles/micro_logprob_r2.md).
+// (Round 2 also tried 4 vectors in flight for the one-parameter gradient kernels: 128 registers, 2 CTAs per SM,
+// and no gain -- Bernoulli 67.9 -> 69.8 %, HalfCauchy 71.2 -> 69.5 %, Exponential 65.7 -> 64.3 %.)
+template <int FAM, typename T, bool GRAD>
 struct VecUnroll {
-  static constexpr int U = (sizeof(T) == 4 && !GRAD) ? 4 : 2;
+  static constexpr bool kHeavy = (FAM == kGamma || FAM == kBeta || FAM == kPoisson);
+  static constexpr int U = (sizeof(T) == 4 && !GRAD && !kHeavy) ? 4 : 2;
   static constexpr int kMinBlocks = (sizeof(T) == 8 && GRAD) ? 2 : 3;
 };
 
 // Loop nest: column chunks outermost (U vectors per thread, then a one-vector tail), rows inside.
 template <int FAM, typename T, bool GRAD, bool MASKUP>
-__global__ void __launch_bounds__(256, VecUnroll<FamilyTraits<FAM>::kNumParams, T, GRAD>::kMinBlocks) site_vec_kernel(const SiteArgs a) {
+__global__ void __launch_bounds__(256, VecUnroll<FAM, T, GRAD>::kMinBlocks) site_vec_kernel(const SiteArgs a) {
+  constexpr int U = VecUnroll<FAM, T, GRAD>::U;
   constexpr int NP = FamilyTraits<FAM>::kNumParams;
   constexpr int V = VecOf<T>::N;
-  constexpr int U = VecUnroll<NP, T, GRAD>::U;
   constexpr int NRED = GRAD ? 2 + NP : 1;
 
   const int TX = 1 << a.tx_log2;
@@ -303,8 +338,8 @@ __global__ void __launch_bounds__(256) site_gen_kernel(const SiteArgs a) {
   constexpr int NP = FamilyTraits<FAM>::kNumParams;
   constexpr bool HASV = FamilyTraits<FAM>::kHasValue;
   constexpr int NRED = GRAD ? 2 + NP : 1;
-  const T f0 = (T)(a.weight * a.scale);
-  const T scale = (T)a.scale;
+  const T f0 = site_f0<T>(a);
+  const T scale = site_scale<T>(a);
   T acc[NRED];
 #pragma unroll
   for (int k = 0; k < NRED; ++k) acc[k] = (T)0;
@@ -337,6 +372,7 @@ __global__ void __launch_bounds__(256) site_gen_kernel(const SiteArgs a) {
     const T xv = HASV ? reinterpret_cast<const T*>(a.x.ptr)[ox] : (T)0;
     const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
     ElemOut<T> o;
+    o.want_dx = a.gx.mode != 0;
     Eval<FAM, T, GRAD>::run(xv, pl, o);
     const T slp = m ? o.lp * scale : (T)0;
     acc[0] += slp;
@@ -422,8 +458,8 @@ __global__ void __launch_bounds__(kSmallThreads) site_small_kernel(const SiteArg
   constexpr int NP = FamilyTraits<FAM>::kNumParams;
   constexpr bool HASV = FamilyTraits<FAM>::kHasValue;
   constexpr int NRED = GRAD ? 2 + NP : 1;
-  const T f0 = (T)(a.weight * a.scale);
-  const T scale = (T)a.scale;
+  const T f0 = site_f0<T>(a);
+  const T scale = site_scale<T>(a);
   T acc[NRED];
 #pragma unroll
   for (int k = 0; k < NRED; ++k) acc[k] = (T)0;
@@ -458,6 +494,7 @@ __global__ void __launch_bounds__(kSmallThreads) site_small_kernel(const SiteArg
     const T xv = (HASV && a.x.ptr) ? reinterpret_cast<const T*>(a.x.ptr)[ox] : (T)0;
     const bool m = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr)[om] != 0 : true;
     ElemOut<T> o;
+    o.want_dx = a.gx.mode != 0;
     Eval<FAM, T, GRAD>::run(xv, pl, o);
     const T slp = m ? o.lp * scale : (T)0;
     acc[0] += slp;
@@ -511,7 +548,7 @@ int launch_site(const SiteArgs& a, int kind, cudaStream_t stream) {
     site_small_kernel<FAM, T, GRAD><<<1, threads, 0, stream>>>(a);
   } else if (kind == kSiteVec) {
     constexpr int V = VecOf<T>::N;
-    constexpr int U = VecUnroll<FamilyTraits<FAM>::kNumParams, T, GRAD>::U;
+    constexpr int U = VecUnroll<FAM, T, GRAD>::U;
     const int64_t CV = a.C / V;
     const int TX = 1 << a.tx_log2, TY = 256 / TX;
     // enough CTAs for ~4 waves of resident blocks; each thread then owns >= U vectors per row

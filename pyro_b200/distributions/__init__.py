@@ -22,6 +22,7 @@ import torch
 from torch.distributions import constraints
 
 from .. import _native as N
+from .._lazyparam import LazyExpParam, densify
 from . import _ops
 
 
@@ -276,6 +277,11 @@ class Normal(_Elementwise):
 
     def __init__(self, loc, scale, validate_args=None):
         super().__init__(loc, scale)
+        # a positive parameter handed out as deferred exp(u) (pyro_b200/_lazyparam.py): the draw kernel takes
+        # u = log(scale) as stored and returns d/du; every other use materialises exp(u)
+        sc = self._params[1]
+        self._log_scale = sc.log_value if isinstance(sc, LazyExpParam) and sc.dtype == self._params[0].dtype \
+            else None
 
     def rsample(self, sample_shape=torch.Size()):
         """``loc + eps*scale`` (torch/distributions/normal.py:82-85).  On the GPU the draw and its
@@ -287,22 +293,30 @@ class Normal(_Elementwise):
         n = 1
         for d in shape:
             n *= int(d)
-        if (N.FUSED_DRAW and N.PHILOX_DRAW and self.loc.is_cuda and 0 < n <= N.RSAMPLE_MAX_N and len(shape) <= 6
-                and self.loc.dtype == self.scale.dtype):
+        loc = densify(self.loc)
+        if (N.FUSED_DRAW and N.PHILOX_DRAW and loc.is_cuda and 0 < n <= N.RSAMPLE_MAX_N and len(shape) <= 6
+                and loc.dtype == self.scale.dtype):
             # noise generated inside the draw kernel (Philox): no randn launch, graph-replay safe
             coeff = _Coeff()
-            z, lq = _NormalRsampleFn.apply(coeff, self.loc, self.scale, None, torch.Size(shape))
+            if self._log_scale is not None and N.LATENT_BLOCK:
+                z, lq = _NormalRsampleFn.apply(coeff, loc, self._log_scale, None, torch.Size(shape), True)
+            else:
+                z, lq = _NormalRsampleFn.apply(coeff, loc, densify(self.scale), None, torch.Size(shape), False)
             z._b2_rsample = _RsampleTag(self.loc, self.scale, lq, coeff)
             return z
-        eps = torch.randn(shape, dtype=self.loc.dtype, device=self.loc.device)
+        eps = torch.randn(shape, dtype=loc.dtype, device=loc.device)
         return self.rsample_with_noise(eps)
 
     def rsample_with_noise(self, eps):
         """The draw for given standard-normal noise ``eps`` (shape = sample_shape + batch_shape)."""
+        loc = densify(self.loc)
         if not N.FUSED_DRAW or (not eps.is_cuda and not N.EMULATE_RSAMPLE):
-            return torch.addcmul(self.loc, eps, self.scale)   # plain draw; scored later by b2_site_score
+            return torch.addcmul(loc, eps, densify(self.scale))   # plain draw; scored later by b2_site_score
         coeff = _Coeff()
-        z, lq = _NormalRsampleFn.apply(coeff, self.loc, self.scale, eps, None)
+        if self._log_scale is not None and N.LATENT_BLOCK:
+            z, lq = _NormalRsampleFn.apply(coeff, loc, self._log_scale, eps, None, True)
+        else:
+            z, lq = _NormalRsampleFn.apply(coeff, loc, densify(self.scale), eps, None, False)
         z._b2_rsample = _RsampleTag(self.loc, self.scale, lq, coeff)
         return z
 
@@ -312,10 +326,11 @@ class _Coeff:
     it).  Kept apart from the tag: the autograd node holds THIS object only -- holding the tag (which
     holds the node's own output) would be a reference cycle through the C++ graph that Python's GC
     cannot break, keeping every step's graph alive."""
-    __slots__ = ("value", "__weakref__")
+    __slots__ = ("value", "prior", "__weakref__")
 
     def __init__(self):
         self.value = 0.0
+        self.prior = None     # (prior_loc, prior_scale, weight of sum log p(z) in the loss): see claim_rsample_prior
 
 
 class _RsampleTag:
@@ -328,29 +343,76 @@ class _RsampleTag:
 
 
 class _NormalRsampleFn(torch.autograd.Function):
+    """``(z, sum log q(z))`` of a Normal site.  ``scale`` is the scale, or with ``log_scale`` the unconstrained
+    storage u = log(scale) of a positive parameter (the gradient then comes back w.r.t. u)."""
+
     @staticmethod
-    def forward(ctx, coeff, loc, scale, eps, shape):
+    def forward(ctx, coeff, loc, scale, eps, shape, log_scale=False):
         if eps is None:
-            z, lq, eps = _ops.normal_rsample_philox(loc, scale, shape)
+            if N.LATENT_BLOCK:
+                z, lq, eps = _ops.latent_draw(loc, scale, log_scale, shape)
+            else:
+                z, lq, eps = _ops.normal_rsample_philox(loc, scale.exp() if log_scale else scale, shape)
         else:
-            z, lq = _ops.normal_rsample_score(loc, scale, eps)
+            z, lq = _ops.normal_rsample_score(loc, scale.exp() if log_scale else scale, eps)
         ctx.coeff = coeff
-        ctx.save_for_backward(eps, loc, scale)
+        ctx.log_scale = log_scale
+        ctx.save_for_backward(eps, loc, scale, z)
         ctx.set_materialize_grads(False)
         return z, lq
 
     @staticmethod
     @_ops.once_differentiable
     def backward(ctx, gz, glq):
-        eps, loc, scale = ctx.saved_tensors
-        if gz is None:
-            gz = _const(0.0, eps.dtype, eps.device)
+        eps, loc, scale, z = ctx.saved_tensors
         # the sum log q output is only reachable through the tag; its consumer folds its
-        # coefficient into tag.coeff and sends a unit upstream gradient (Trace_ELBO's contract)
+        # coefficient into tag.coeff and sends a unit upstream gradient (Trace_ELBO's contract).  A claimed
+        # prior (claim_rsample_prior) rides on the same contract.
         c = ctx.coeff.value if glq is not None else 0.0
-        gloc, gscale = _ops.normal_rsample_backward(gz, eps, loc, scale, c,
-                                                    ctx.needs_input_grad[1], ctx.needs_input_grad[2])
-        return None, gloc, gscale, None, None
+        prior = ctx.coeff.prior if glq is not None else None
+        if N.LATENT_BLOCK:
+            gloc, gscale = _ops.latent_backward(gz, eps, z, loc, scale, ctx.log_scale, c, prior,
+                                                ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        else:
+            if gz is None:
+                gz = _const(0.0, eps.dtype, eps.device)
+            s = scale.exp() if ctx.log_scale else scale
+            gloc, gscale = _ops.normal_rsample_backward(gz, eps, loc, s, c, ctx.needs_input_grad[1],
+                                                        ctx.needs_input_grad[2])
+            if ctx.log_scale and gscale is not None:
+                gscale = gscale * s
+        return None, gloc, gscale, None, None, None
+
+
+def claim_rsample_prior(fn, value, weight):
+    """A model site ``value ~ fn`` whose value is a fused draw with a claimed score: if ``fn`` is a Normal with
+    gradient-free parameters, register ``weight`` (the coefficient of ``sum log_prob(value)`` in the loss being
+    differentiated) with the draw, whose backward kernel then adds ``weight * d log p/dz`` to the gradient
+    reaching z -- no separate gradient kernel for the prior, no accumulation launch at z.  Returns
+    ``(z, prior_loc, prior_scale)`` for the value-only scoring (``_ops.latent_prior``), or None."""
+    if not N.LATENT_BLOCK:
+        return None
+    tag = getattr(value, "_b2_rsample", None)
+    if tag is None or tag.coeff.value == 0.0 or tag.coeff.prior is not None:
+        return None
+    base = fn
+    while isinstance(base, Independent):
+        base = base.base_dist
+    if type(base) is not Normal:
+        return None
+    ploc, pscale = base._params
+    if isinstance(ploc, LazyExpParam) or isinstance(pscale, LazyExpParam):
+        return None
+    if ploc.requires_grad or pscale.requires_grad or not value.is_cuda and not N.EMULATE_RSAMPLE:
+        return None
+    if ploc.dtype != value.dtype or pscale.dtype != value.dtype or ploc.device != value.device:
+        return None
+    if value.numel() == 0 or value.numel() > N.RSAMPLE_MAX_N or value.dim() > 6:
+        return None
+    if torch.broadcast_shapes(value.shape, base.batch_shape) != value.shape:
+        return None
+    tag.coeff.prior = (ploc, pscale, float(weight))
+    return value, ploc, pscale
 
 
 def claim_rsample_score(fn, value, coeff):

@@ -16,6 +16,7 @@ import torch
 from torch.autograd.function import once_differentiable
 
 from .. import _native as N
+from .._lazyparam import densify
 
 
 def _common_shape(value, params, batch_shape=None):
@@ -267,6 +268,8 @@ class _LogProbFn(torch.autograd.Function):
 
 
 def log_prob_op(family, value, params, batch_shape, event_size=None):
+    params = [densify(p) for p in params]
+    value = densify(value)
     if event_size is None:
         shape = _common_shape(value, params, batch_shape)
         value_is_float = value is not None and value.is_floating_point()
@@ -316,6 +319,8 @@ def fused_site_sum(family, value, params, batch_shape, *, mask=None, scale=1.0, 
                    sum_coeff=1.0, event_size=None, assume_unit_upstream=True):
     """0-d tensor ``sum_coeff * sum(scale*mask*log_prob)`` whose backward delivers
     ``weight * d(sum)/d(operand)`` for every operand requiring grad (assuming upstream == 1)."""
+    params = [densify(p) for p in params]
+    value = densify(value)
     if event_size is None:
         shape = _common_shape(value, params, batch_shape)
         vfloat = value is not None and value.is_floating_point()
@@ -408,6 +413,91 @@ def normal_rsample_backward(gz, eps, loc, scale, c, need_loc, need_scale):
                           need_dparams=[need_loc, need_scale, False],
                           grad_like=[loc, scale, None])
     return gp[0], gp[1]
+
+
+# ---- latent-sites block (csrc/latent.cu) -----------------------------------------------------------
+def _latent_job(shape, dtype, loc=None, scale=None, log_scale=False, prior=None, z=None, eps=None, gz=None,
+                out0=None, out1=None, c=0.0, pw=0.0):
+    j = N.b2_latent_job()
+    j.dtype = N._DTYPES[dtype]
+    j.ndim = len(shape)
+    j.flags = N.LATENT_LOG_SCALE if log_scale else 0
+    for i, s in enumerate(shape):
+        j.shape[i] = int(s)
+
+    def view(t, strides):
+        if t is None:
+            return None
+        v = t.expand(shape) if tuple(t.shape) != tuple(shape) else t
+        st = v.stride()
+        for i in range(len(shape)):
+            strides[i] = st[i] if shape[i] != 1 else 0
+        return v.data_ptr()
+
+    j.loc = view(loc, j.loc_stride)
+    j.scale = view(scale, j.scale_stride)
+    if prior is not None:
+        j.prior_loc = view(prior[0], j.prior_loc_stride)
+        j.prior_scale = view(prior[1], j.prior_scale_stride)
+    for name, t in (("z", z), ("eps", eps), ("gz", gz), ("out0", out0), ("out1", out1)):
+        setattr(j, name, t.data_ptr() if t is not None else None)
+    j.c = float(c)
+    j.prior_weight = float(pw)
+    return j
+
+
+def latent_draw(loc, scale, log_scale, shape):
+    """(z, lq, eps) of ONE Normal site: ``z = loc + eps*s`` with ``s = scale`` or ``exp(scale)`` (``log_scale``),
+    eps from the in-kernel Philox stream, and the 0-d ``sum log Normal(z | loc, s)`` (b2_latent_normal_draw)."""
+    shape = tuple(int(s) for s in shape)
+    dev, dtype = loc.device, loc.dtype
+    z = torch.empty(shape, dtype=dtype, device=dev)
+    eps = torch.empty(shape, dtype=dtype, device=dev)
+    lq = torch.empty((), dtype=dtype, device=dev)
+    jobs = (N.b2_latent_job * 1)(_latent_job(shape, dtype, loc=loc, scale=scale, log_scale=log_scale, z=z,
+                                             eps=eps, out0=lq))
+    N.check(N.lib().b2_latent_normal_draw(jobs, 1, rng_state(dev).data_ptr(), N.stream_ptr(dev)),
+            "b2_latent_normal_draw")
+    return z, lq, eps
+
+
+def latent_prior(items):
+    """``[sum log Normal(z_k | ploc_k, pscale_k)]`` for a list of ``(z, ploc, pscale)``: value only, one launch
+    per 8 sites (b2_latent_normal_prior).  Returns a list of 0-d tensors (views of one buffer)."""
+    ref = items[0][0]
+    out = torch.empty(len(items), dtype=ref.dtype, device=ref.device)
+    for base in range(0, len(items), N.LATENT_MAX_JOBS):
+        chunk = items[base:base + N.LATENT_MAX_JOBS]
+        jobs = (N.b2_latent_job * len(chunk))()
+        for k, (z, ploc, pscale) in enumerate(chunk):
+            zc = z if z.is_contiguous() else z.contiguous()
+            jobs[k] = _latent_job(tuple(z.shape), z.dtype, prior=(ploc, pscale), z=zc, out0=out[base + k])
+        N.check(N.lib().b2_latent_normal_prior(jobs, len(chunk), N.stream_ptr(ref.device)),
+                "b2_latent_normal_prior")
+    return [out[k] for k in range(len(items))]
+
+
+def latent_backward(gz, eps, z, loc, scale, log_scale, c, prior, need_loc, need_scale):
+    """Gradients of the loss w.r.t. ``(loc, scale | log scale)`` of a fused draw: ``gz`` = dL/dz from the
+    consumers of z, ``c`` = coefficient of ``sum log q(z)``, ``prior`` = ``(ploc, pscale, weight)`` of a Normal
+    prior whose ``weight * d log p(z)/dz`` joins ``gz`` here; reduced to the stored shapes, one launch."""
+    shape = tuple(eps.shape)
+    if eps.numel() == 0:
+        return (torch.zeros_like(loc) if need_loc else None, torch.zeros_like(scale) if need_scale else None)
+    dev, dtype = eps.device, eps.dtype
+    if gz is not None and (tuple(gz.shape) != shape or not gz.is_contiguous()):
+        gz = gz.expand(shape).contiguous()
+    gloc = torch.empty(loc.shape, dtype=dtype, device=dev) if need_loc else None
+    if not scale.is_contiguous():
+        scale = scale.contiguous()      # the kernel writes d/dscale with the strides it reads scale with
+    gscale = torch.empty(scale.shape, dtype=dtype, device=dev) if need_scale else None
+    pr = (prior[0], prior[1]) if prior is not None else None
+    # loc itself is not read in the backward pass: its slot carries the (contiguous) layout of d/dloc
+    job = _latent_job(shape, dtype, loc=gloc, scale=scale, log_scale=log_scale, prior=pr, z=z, eps=eps, gz=gz,
+                      out0=gloc, out1=gscale, c=c, pw=prior[2] if prior is not None else 0.0)
+    jobs = (N.b2_latent_job * 1)(job)
+    N.check(N.lib().b2_latent_normal_backward(jobs, 1, N.stream_ptr(dev)), "b2_latent_normal_backward")
+    return gloc, gscale
 
 
 def elbo_combine(terms, coeffs):

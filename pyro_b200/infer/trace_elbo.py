@@ -138,12 +138,31 @@ class Trace_ELBO(ELBO):
             if lp.requires_grad:
                 terms.append(w * lp)
 
-        for name, site in model_trace.nodes.items():
-            if site["type"] == "sample":
-                add_site(site, 1.0)
+        # guide sites first: a fused draw whose score has been claimed can also carry its model site's prior
         for name, site in guide_trace.nodes.items():
             if site["type"] == "sample":
                 add_site(site, -1.0)
+        priors, prior_coeffs = [], []
+        for name, site in model_trace.nodes.items():
+            if site["type"] == "sample":
+                job = None
+                if (not site["is_observed"] and (site["mask"] is None or site["mask"] is True)
+                        and not site["args"] and not site["kwargs"]
+                        and not isinstance(site["scale"], torch.Tensor)):
+                    # Normal prior on a fused draw: value-only scoring now (batched below), its d/dz inside
+                    # the draw's backward kernel
+                    from ..distributions import claim_rsample_prior
+                    sc = float(site["scale"])
+                    job = claim_rsample_prior(site["fn"], site["value"], -sc / P)
+                    if job is not None:
+                        priors.append(job)
+                        prior_coeffs.append(sc)
+                if job is None:
+                    add_site(site, 1.0)
+        if priors:
+            from ..distributions import _ops as _o
+            parts.extend(_o.latent_prior(priors))
+            coeffs.extend(prior_coeffs)
         if not parts:
             return torch.zeros(()), terms
         # loss = sum_i (-coeff_i / P) * part_i, assembled on the device in one launch

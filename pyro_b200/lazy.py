@@ -19,6 +19,7 @@ guide value of pyro/poutine/replay_messenger.py:50-61); nothing in the model is 
 """
 import torch
 
+from ._lazyparam import LazyExpParam
 from .distributions import LinearPredictor
 
 _VIEW_FUNCS = {"squeeze", "unsqueeze", "reshape", "view", "transpose", "t", "permute", "expand",
@@ -38,7 +39,7 @@ def _name(func):
 
 
 def _plain(x):
-    if isinstance(x, LinearPredictorTensor):
+    if isinstance(x, (LinearPredictorTensor, LazyExpParam)):
         return x.dense()
     if isinstance(x, SiteValue):
         return x.as_subclass(torch.Tensor)
@@ -49,7 +50,7 @@ def _plain(x):
 
 def _is_data(t):
     """A gradient-free 2-d tensor that is a row-major ``[N, D]`` matrix or the transposed view of one."""
-    if not isinstance(t, torch.Tensor) or isinstance(t, (SiteValue, LinearPredictorTensor)):
+    if not isinstance(t, torch.Tensor) or isinstance(t, (SiteValue, LinearPredictorTensor, LazyExpParam)):
         return False
     if t.requires_grad or t.dim() != 2 or not t.is_floating_point():
         return False

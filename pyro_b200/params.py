@@ -63,6 +63,14 @@ class ParamStoreDict:
         if constraint is constraints.positive:
             # transform_to(positive) = Affine(0, 1) o Exp: the affine part is the identity, skip its
             # two launches (and two more in backward) per parameter per step
+            from . import _native as N
+            if N.LAZY_PARAM and (unconstrained.is_cuda or N.EMULATE_RSAMPLE):
+                # exp deferred: a Normal guide site's draw kernel takes log(scale) as it is stored
+                from ._lazyparam import LazyExpParam
+                constrained = LazyExpParam(unconstrained)
+                constrained.unconstrained = weakref.ref(unconstrained)
+                constrained._pyro_unconstrained_param = unconstrained
+                return constrained
             constrained = unconstrained.exp()
         else:
             constrained = transform_to(constraint)(unconstrained)

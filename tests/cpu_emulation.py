@@ -246,6 +246,24 @@ def _normal_rsample_backward(gz, eps, loc, scale, c, need_loc, need_scale):
     return gloc, gscale
 
 
+def _latent_prior(items):
+    return [odists.ELEMENTWISE[0][0](z, pl, ps).sum().detach() for z, pl, ps in items]
+
+
+def _latent_backward(gz, eps, z, loc, scale, log_scale, c, prior, need_loc, need_scale):
+    # csrc/latent.cu latent_backward_kernel restated: g = gz + pw * dlogp/dz; d/dloc = g;
+    # d/dscale = g*eps - c/s  or  d/dlog_scale = g*eps*s - c
+    s = scale.exp() if log_scale else scale
+    g = torch.zeros_like(eps) if gz is None else gz.expand(eps.shape)
+    if prior is not None:
+        pl, ps, pw = prior
+        g = g + pw * (-(z - pl) / (ps * ps))
+    gloc = g.sum_to_size(loc.shape) if need_loc else None
+    gs = (g * eps * s - c) if log_scale else (g * eps - c / s)
+    gscale = gs.sum_to_size(scale.shape) if need_scale else None
+    return gloc, gscale
+
+
 def _elbo_combine(terms, coeffs):
     return sum(c * t.reshape(()) for c, t in zip(coeffs, terms))
 
@@ -277,6 +295,8 @@ def enabled():
     nuts.NUTS._leaf_hier, nuts.NUTS._tree_merge, nuts.NUTS._rows_copy = _leaf_hier, _tree_merge, _rows_copy
     ops.reduce_to = _reduce_to
     saved_rs = (ops.normal_rsample_score, ops.normal_rsample_backward, N.EMULATE_RSAMPLE)
+    saved_latent = (ops.latent_prior, ops.latent_backward)
+    ops.latent_prior, ops.latent_backward = _latent_prior, _latent_backward
     saved_comb = ops.elbo_combine
     ops.elbo_combine = _elbo_combine
     ops.normal_rsample_score = _normal_rsample_score
@@ -286,6 +306,7 @@ def enabled():
         yield
     finally:
         ops.normal_rsample_score, ops.normal_rsample_backward, N.EMULATE_RSAMPLE = saved_rs
+        ops.latent_prior, ops.latent_backward = saved_latent
         ops.elbo_combine = saved_comb
         pdist._BernoulliLinear._fused_sum = saved_glm
         nuts.NUTS._leaf_vector = saved_leaf

@@ -329,6 +329,75 @@ def test_philox_draw_kernel(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("log_scale", [False, True])
+def test_latent_block_kernels(dtype, log_scale):
+    """csrc/latent.cu through the C ABI: b2_latent_normal_draw (z = loc + eps*s with s = scale or exp(log_scale),
+    the 0-d sum of log q(z) against the oracle, fresh noise per launch and per graph replay, reseeding),
+    b2_latent_normal_prior (value-only prior sums of several sites in one launch) and
+    b2_latent_normal_backward (gradient reaching z + prior's d log p/dz + the score's own total derivative,
+    reduced to the stored shapes of loc / scale / log_scale) against autograd on the same expression."""
+    if EMULATE:
+        pytest.skip("kernel test")
+    import pyro_b200 as pyro
+    from oracle import dists as od
+    pyro.set_rng_seed(5)
+    tol = 3e-6 if dtype == torch.float32 else 1e-13
+    loc = torch.randn(7, 1, 33, device=DEV, dtype=dtype)
+    sc = torch.rand(33, device=DEV, dtype=dtype) + 0.5
+    store = sc.log() if log_scale else sc            # what the kernel reads
+    s = store.exp() if log_scale else store
+    shape = (5, 7, 4, 33)
+    z, lq, eps = _ops.latent_draw(loc, store, log_scale, shape)
+    assert torch.allclose(z, loc + eps * s, rtol=tol, atol=tol)
+    ref = od.normal(z.double().cpu(), loc.double().cpu().expand(shape), s.double().cpu().expand(shape)).sum()
+    assert abs(float(lq) - float(ref)) <= (2e-5 if dtype == torch.float32 else 1e-10) * abs(float(ref))
+    _, _, eps2 = _ops.latent_draw(loc, store, log_scale, shape)
+    assert not torch.equal(eps, eps2)
+    big = _ops.latent_draw(torch.zeros((), device=DEV, dtype=dtype), torch.ones((), device=DEV, dtype=dtype),
+                           False, (64, 1024))[2].reshape(-1).double().cpu()
+    n = big.numel()
+    assert abs(float(big.mean())) < 5 / n ** 0.5 and abs(float(big.var()) - 1) < 5 * (2 / n) ** 0.5
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        _, _, eg = _ops.latent_draw(loc, store, log_scale, shape)
+    g.replay()
+    a = eg.clone()
+    g.replay()
+    assert not torch.equal(a, eg)
+    pyro.set_rng_seed(5)
+    assert torch.equal(_ops.latent_draw(loc, store, log_scale, shape)[2], eps)
+    # value-only priors of two sites, one launch
+    pl, ps = torch.zeros((), device=DEV, dtype=dtype), torch.rand(4, 1, device=DEV, dtype=dtype) + 0.7
+    z2 = torch.randn(11, device=DEV, dtype=dtype)
+    pl2, ps2 = torch.randn(11, device=DEV, dtype=dtype), torch.full((), 10.0, device=DEV, dtype=dtype)
+    lps = _ops.latent_prior([(z, pl, ps), (z2, pl2, ps2)])
+    r1 = od.normal(z.double().cpu(), pl.double().cpu().expand(shape), ps.double().cpu().expand(shape)).sum()
+    r2 = od.normal(z2.double().cpu(), pl2.double().cpu(), ps2.double().cpu().expand(11)).sum()
+    for got, want in zip(lps, (r1, r2)):
+        assert abs(float(got) - float(want)) <= (2e-5 if dtype == torch.float32 else 1e-10) * abs(float(want))
+    # backward
+    gz = torch.randn(shape, device=DEV, dtype=dtype)
+    c, pw = 0.3, -0.7
+    for prior in (None, (pl, ps, pw)):
+        gl, gs = _ops.latent_backward(gz, eps, z, loc, store, log_scale, c, prior, True, True)
+        lo = loc.double().cpu().requires_grad_(True)
+        so = store.double().cpu().requires_grad_(True)
+        s_o = so.exp() if log_scale else so
+        zo = lo + eps.double().cpu() * s_o
+        L = (gz.double().cpu() * zo).sum() + c * od.normal(zo, lo.expand(shape), s_o.expand(shape)).sum()
+        if prior is not None:
+            L = L + pw * od.normal(zo, pl.double().cpu().expand(shape), ps.double().cpu().expand(shape)).sum()
+        glo, gso = torch.autograd.grad(L, [lo, so])
+        assert gl.shape == loc.shape and gs.shape == store.shape
+        gt = 2e-4 if dtype == torch.float32 else 1e-9
+        _close(gl, glo, gt * 20 ** 0.5)
+        _close(gs, gso, gt * 140 ** 0.5)
+    gl, gs = _ops.latent_backward(None, eps, z, loc, store, log_scale, c, None, True, False)
+    assert gs is None and float(gl.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_elbo_combine(dtype):
     """b2_elbo_combine: weighted sum of 0-d device scalars in index order, one launch."""
     torch.manual_seed(0)

@@ -524,3 +524,80 @@ def _slice_nuts_case(dev):
 
 def test_slice_sampling_nuts_posterior(emu):
     _slice_nuts_case("cpu")
+
+
+def test_lazy_exp_param_semantics(emu):
+    """pyro_b200/_lazyparam.py: metadata without materialising, one autograd-connected exp on first use, and the
+    param store hands it out for positive constraints (pyro/params/param_store.py:125-156 semantics kept:
+    ``.unconstrained()`` and the gradient reaching the stored leaf)."""
+    from torch.distributions import constraints
+    from pyro_b200._lazyparam import LazyExpParam
+    pyro.clear_param_store()
+    s = pyro.param("s", torch.full((3, 2), 0.5), constraint=constraints.positive)
+    assert isinstance(s, LazyExpParam) and s._dense is None
+    assert s.shape == (3, 2) and s.dim() == 2 and s.dtype == torch.get_default_dtype() and s._dense is None
+    u = s.unconstrained()
+    assert u.requires_grad and u.grad_fn is None and torch.allclose(u, torch.full((3, 2), 0.5).log())
+    out = (s * 2.0).sum() + s.log().sum()           # any torch function materialises exp(u), once
+    assert s._dense is not None and torch.allclose(s._dense, torch.full((3, 2), 0.5))
+    d = s._dense
+    _ = s + 1
+    assert s._dense is d
+    out.backward()
+    assert torch.allclose(u.grad, torch.full((3, 2), 2 * 0.5 + 1.0))
+    # a distribution other than the Normal draw path densifies at the autograd boundary
+    pyro.clear_param_store()
+    r = pyro.param("r", torch.tensor([1.5, 2.0]), constraint=constraints.positive)
+    lp = dist.Gamma(r, 1.0).log_prob(torch.tensor([0.3, 0.7])).sum()
+    lp.backward()
+    ro = torch.tensor([1.5, 2.0]).log().requires_grad_(True)
+    torch.distributions.Gamma(ro.exp(), 1.0).log_prob(torch.tensor([0.3, 0.7])).sum().backward()
+    assert torch.allclose(r.unconstrained().grad, ro.grad, atol=1e-6)
+
+
+@pytest.mark.parametrize("subsample", [False, True])
+def test_latent_block_step_equals_sitewise_step(emu, subsample):
+    """Trace_ELBO with the latent-sites block (log-scale draw of a positive parameter, Normal prior folded into
+    the draw's backward, batched value-only prior scoring) gives the loss and gradients of the site-by-site
+    path; the claim is really taken (both priors) and really skipped when the prior is learnable."""
+    from pyro_b200 import _native as N
+    from pyro_b200.infer import Trace_ELBO
+    import pyro_b200.distributions as pd
+    torch.manual_seed(3)
+    X = torch.randn(40, 5)
+    y = (torch.rand(40) < 0.4).to(X.dtype)
+
+    def model(X, y):
+        w = pyro.sample("w", dist.Normal(X.new_zeros(5), X.new_ones(5)).to_event(1))
+        b = pyro.sample("b", dist.Normal(X.new_zeros(()), X.new_full((), 10.0)))
+        with pyro.plate("data", 40, subsample_size=10 if subsample else None) as idx:
+            lg = (X[idx] @ w.squeeze(-2).T).T + b if w.dim() > 1 else X[idx] @ w + b
+            pyro.sample("y", dist.Bernoulli(logits=lg), obs=y[idx])
+
+    res, claimed = [], []
+    orig = pd.claim_rsample_prior
+
+    def spy(fn, value, weight):
+        out = orig(fn, value, weight)
+        claimed.append(out is not None)
+        return out
+
+    for latent in (True, False):
+        N.LATENT_BLOCK = latent
+        N.LAZY_PARAM = latent
+        pd.claim_rsample_prior = spy
+        try:
+            pyro.clear_param_store()
+            torch.manual_seed(7)
+            elbo = Trace_ELBO(num_particles=6, vectorize_particles=True, max_plate_nesting=1)
+            loss = elbo.loss_and_grads(model, models.logistic_guide, X, y)
+            store = pyro.get_param_store()
+            res.append((loss, {k: store._params[k].grad.clone() for k in ("w_loc", "w_scale", "b_loc", "b_scale")}))
+        finally:
+            N.LATENT_BLOCK = True
+            N.LAZY_PARAM = True
+            pd.claim_rsample_prior = orig
+    assert claimed[:2] == [True, True] and not any(claimed[2:])
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[1][0])
+    for k in res[0][1]:
+        assert torch.allclose(res[0][1][k], res[1][1][k], rtol=1e-5, atol=1e-6), k
