@@ -202,6 +202,8 @@ int b2_normal_rsample(const b2_tensor* loc, const b2_tensor* scale, int ndim, co
  */
 #define B2_LATENT_MAX_JOBS 8
 #define B2_LATENT_LOG_SCALE 1   /* `scale` holds log(scale) */
+#define B2_LATENT_ACC_OUT0 2    /* backward: out0 += d/dloc (accumulate into an existing .grad) instead of = */
+#define B2_LATENT_ACC_OUT1 4    /* backward: out1 += d/dscale | d/dlog_scale */
 typedef struct {
   int32_t dtype, ndim, flags, pad_;
   int64_t shape[B2_MAX_DIMS];

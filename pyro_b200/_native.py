@@ -43,7 +43,9 @@ NUTS_SMALL_MAX_D = 64
 
 LATENT_MAX_JOBS = 8
 LATENT_LOG_SCALE = 1
+LATENT_ACC_OUT0, LATENT_ACC_OUT1 = 2, 4
 LATENT_BLOCK = True       # Normal guide sites + Normal priors go through the latent-sites kernels (latent.cu)
+LATENT_ACCUMULATE = True  # the draw's backward kernel adds into existing leaf .grad buffers itself
 LAZY_PARAM = True         # positive-constrained parameters are handed out as deferred exp(u) (_lazyparam.py)
 
 

@@ -87,11 +87,8 @@ __global__ void __launch_bounds__(1024) latent_draw_kernel(const LatentArgs a) {
   double v[1] = {acc};
   block_sum<1>(v, smem);
   if (threadIdx.x == 0) *reinterpret_cast<T*>(j.out0) = (T)v[0];
-  // the launch counter advances once per launch: the last job's CTA does it after every CTA of this launch
-  // has read it -- CTAs read it in their first instructions and a job is at most 64 loop trips, but to be
-  // independent of scheduling the counter is double-buffered: readers use state[1], the writer stores
-  // state[1] + 1 into state[2] and the NEXT launch's host code... (see b2_latent_normal_draw: one-CTA launches
-  // advance it in the kernel, multi-job launches use a follow-up 1-thread kernel)
+  // the launch counter advances once per launch: a one-CTA launch does it here (every thread read it before the
+  // block_sum barriers); a multi-job launch is followed by latent_advance_kernel (b2_latent_normal_draw)
   if (gridDim.x == 1 && threadIdx.x == 0) a.state[1] = ctr + 1ull;
 }
 
@@ -135,7 +132,8 @@ __device__ __forceinline__ void latent_grad_elem(const LatentJob& j, unsigned i,
 
 // out[stored shape] = sum over the broadcast positions; one warp per stored element, fixed order.
 template <typename T, int WHICH>
-__device__ __forceinline__ void latent_reduce(const LatentJob& j, const int* st, void* outp, bool logs) {
+__device__ __forceinline__ void latent_reduce(const LatentJob& j, const int* st, void* outp, bool logs,
+                                              bool acc_out) {
   if (!outp) return;
   unsigned cst[kMaxD], m = 1;
   {
@@ -174,7 +172,7 @@ __device__ __forceinline__ void latent_reduce(const LatentJob& j, const int* st,
       s += (double)(WHICH == 0 ? gl : gs);
     }
     s = warp_sum(s);
-    if (lane == 0) out[off] = (T)s;
+    if (lane == 0) out[off] = acc_out ? (T)((double)out[off] + s) : (T)s;
   }
 }
 
@@ -182,8 +180,8 @@ template <typename T>
 __global__ void __launch_bounds__(1024) latent_backward_kernel(const LatentArgs a) {
   const LatentJob& j = a.job[blockIdx.x];
   const bool logs = (j.flags & B2_LATENT_LOG_SCALE) != 0;
-  latent_reduce<T, 0>(j, j.st_loc, j.out0, logs);
-  latent_reduce<T, 1>(j, j.st_scale, j.out1, logs);
+  latent_reduce<T, 0>(j, j.st_loc, j.out0, logs, (j.flags & B2_LATENT_ACC_OUT0) != 0);
+  latent_reduce<T, 1>(j, j.st_scale, j.out1, logs, (j.flags & B2_LATENT_ACC_OUT1) != 0);
 }
 
 static int fill_job(LatentJob& j, const b2_latent_job& h, int dtype) {

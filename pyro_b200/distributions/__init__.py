@@ -372,7 +372,8 @@ class _NormalRsampleFn(torch.autograd.Function):
         prior = ctx.coeff.prior if glq is not None else None
         if N.LATENT_BLOCK:
             gloc, gscale = _ops.latent_backward(gz, eps, z, loc, scale, ctx.log_scale, c, prior,
-                                                ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+                                                ctx.needs_input_grad[1], ctx.needs_input_grad[2],
+                                                accumulate=N.LATENT_ACCUMULATE)
         else:
             if gz is None:
                 gz = _const(0.0, eps.dtype, eps.device)

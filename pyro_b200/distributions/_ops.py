@@ -477,27 +477,53 @@ def latent_prior(items):
     return [out[k] for k in range(len(items))]
 
 
-def latent_backward(gz, eps, z, loc, scale, log_scale, c, prior, need_loc, need_scale):
+def _grad_slot(t):
+    """A leaf whose ``.grad`` already exists (a replicated step keeps the gradients as views of the all-reduce
+    payload; an eager step keeps the buffers the optimiser zeroed): the backward kernel can add into it and the
+    autograd engine is told there is nothing left to accumulate -- no AccumulateGrad launch per parameter."""
+    g = t.grad if t.is_leaf and t.requires_grad else None
+    if g is not None and g.is_contiguous() and g.shape == t.shape and g.dtype == t.dtype and not g.requires_grad:
+        return g
+    return None
+
+
+def latent_backward(gz, eps, z, loc, scale, log_scale, c, prior, need_loc, need_scale, accumulate=False):
     """Gradients of the loss w.r.t. ``(loc, scale | log scale)`` of a fused draw: ``gz`` = dL/dz from the
     consumers of z, ``c`` = coefficient of ``sum log q(z)``, ``prior`` = ``(ploc, pscale, weight)`` of a Normal
-    prior whose ``weight * d log p(z)/dz`` joins ``gz`` here; reduced to the stored shapes, one launch."""
+    prior whose ``weight * d log p(z)/dz`` joins ``gz`` here; reduced to the stored shapes, one launch.  With
+    ``accumulate``, an operand that is a leaf with an existing ``.grad`` gets its gradient ADDED there by the
+    kernel and None is returned in its place."""
     shape = tuple(eps.shape)
     if eps.numel() == 0:
         return (torch.zeros_like(loc) if need_loc else None, torch.zeros_like(scale) if need_scale else None)
     dev, dtype = eps.device, eps.dtype
     if gz is not None and (tuple(gz.shape) != shape or not gz.is_contiguous()):
         gz = gz.expand(shape).contiguous()
-    gloc = torch.empty(loc.shape, dtype=dtype, device=dev) if need_loc else None
+    flags_acc = 0
+    gloc = gscale = None
+    ret_loc = ret_scale = True
+    if need_loc:
+        slot = _grad_slot(loc) if accumulate else None
+        if slot is not None:
+            gloc, ret_loc, flags_acc = slot, False, flags_acc | N.LATENT_ACC_OUT0
+        else:
+            gloc = torch.empty(loc.shape, dtype=dtype, device=dev)
+    slot = _grad_slot(scale) if (accumulate and need_scale and scale.is_contiguous()) else None
     if not scale.is_contiguous():
         scale = scale.contiguous()      # the kernel writes d/dscale with the strides it reads scale with
-    gscale = torch.empty(scale.shape, dtype=dtype, device=dev) if need_scale else None
+    if need_scale:
+        if slot is not None:
+            gscale, ret_scale, flags_acc = slot, False, flags_acc | N.LATENT_ACC_OUT1
+        else:
+            gscale = torch.empty(scale.shape, dtype=dtype, device=dev)
     pr = (prior[0], prior[1]) if prior is not None else None
     # loc itself is not read in the backward pass: its slot carries the (contiguous) layout of d/dloc
     job = _latent_job(shape, dtype, loc=gloc, scale=scale, log_scale=log_scale, prior=pr, z=z, eps=eps, gz=gz,
                       out0=gloc, out1=gscale, c=c, pw=prior[2] if prior is not None else 0.0)
+    job.flags |= flags_acc
     jobs = (N.b2_latent_job * 1)(job)
     N.check(N.lib().b2_latent_normal_backward(jobs, 1, N.stream_ptr(dev)), "b2_latent_normal_backward")
-    return gloc, gscale
+    return (gloc if ret_loc else None), (gscale if ret_scale else None)
 
 
 def elbo_combine(terms, coeffs):

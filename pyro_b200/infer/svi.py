@@ -259,12 +259,14 @@ class SVI:
             if os.environ.get("B2_NCCL_IN_GRAPH", "0") == "1" and dist.get_backend() == "nccl":
                 # OPT-IN (B2_NCCL_IN_GRAPH=1): ONE graph for the whole step -- NCCL collectives are capturable,
                 # so the all-reduce of the [loss, grads] payload sits between the backward and the optimiser
-                # inside the graph and a replay is a single launch.  Off by default: the one 2-GPU run of
-                # round 2 with it enabled hung (a capture invalidated on one rank only leaves the ranks with
-                # different collective schedules), and there was no GPU budget left to debug it.
+                # inside the graph and a replay is a single launch.  Two precautions (the first 2-GPU run of
+                # round 2 hung without them): the capture is thread-local, so the CUDA calls of NCCL's watchdog
+                # thread cannot invalidate it on one rank only, and the ranks AGREE (eager all-reduce of a flag)
+                # on whether every capture succeeded before any of them replays a graph with a collective in it.
+                ok = 1.0
                 try:
                     g1 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g1):
+                    with torch.cuda.graph(g1, capture_error_mode="thread_local"):
                         loss, params2 = self._grads(tuple(static_args), {}, True)
                         flat[0:1].copy_(loss.detach().reshape(1).to(flat.dtype))
                         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
@@ -273,8 +275,13 @@ class SVI:
                         self.optim(params2)
                     single = (g1, out)
                 except Exception:  # noqa: BLE001 -- fall back to the two-graph form below
+                    ok = 0.0
                     single = None
                     torch.cuda.synchronize(dev)
+                agree = torch.tensor([ok], device=dev)
+                dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+                if float(agree) < 1.0:
+                    single = None
             if single is not None:
                 graph, out = single
                 state.update({"loss": out, "flat": flat, "graph_b": None, "nccl_in_graph": True})

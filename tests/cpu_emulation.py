@@ -250,7 +250,7 @@ def _latent_prior(items):
     return [odists.ELEMENTWISE[0][0](z, pl, ps).sum().detach() for z, pl, ps in items]
 
 
-def _latent_backward(gz, eps, z, loc, scale, log_scale, c, prior, need_loc, need_scale):
+def _latent_backward(gz, eps, z, loc, scale, log_scale, c, prior, need_loc, need_scale, accumulate=False):
     # csrc/latent.cu latent_backward_kernel restated: g = gz + pw * dlogp/dz; d/dloc = g;
     # d/dscale = g*eps - c/s  or  d/dlog_scale = g*eps*s - c
     s = scale.exp() if log_scale else scale
@@ -261,6 +261,16 @@ def _latent_backward(gz, eps, z, loc, scale, log_scale, c, prior, need_loc, need
     gloc = g.sum_to_size(loc.shape) if need_loc else None
     gs = (g * eps * s - c) if log_scale else (g * eps - c / s)
     gscale = gs.sum_to_size(scale.shape) if need_scale else None
+    if accumulate:
+        import pyro_b200.distributions._ops as ops
+        for t, g, which in ((loc, gloc, 0), (scale, gscale, 1)):
+            slot = ops._grad_slot(t) if g is not None else None
+            if slot is not None:
+                slot.add_(g)
+                if which == 0:
+                    gloc = None
+                else:
+                    gscale = None
     return gloc, gscale
 
 

@@ -395,6 +395,14 @@ def test_latent_block_kernels(dtype, log_scale):
         _close(gs, gso, gt * 140 ** 0.5)
     gl, gs = _ops.latent_backward(None, eps, z, loc, store, log_scale, c, None, True, False)
     assert gs is None and float(gl.abs().max()) == 0.0
+    # leaves that already hold a .grad: the kernel adds into it and hands nothing back to autograd
+    gl0, gs0 = _ops.latent_backward(gz, eps, z, loc, store, log_scale, c, (pl, ps, pw), True, True)
+    lleaf, sleaf = loc.clone().requires_grad_(True), store.clone().requires_grad_(True)
+    lleaf.grad, sleaf.grad = torch.ones_like(loc), torch.full_like(store, 2.0)
+    r = _ops.latent_backward(gz, eps, z, lleaf, sleaf, log_scale, c, (pl, ps, pw), True, True, accumulate=True)
+    assert r == (None, None)
+    assert torch.allclose(lleaf.grad, 1.0 + gl0, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(sleaf.grad, 2.0 + gs0, rtol=1e-6, atol=1e-5)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
