@@ -273,6 +273,56 @@ class _RefPyroSVI:
         return self.svi.step(X, y)
 
 
+def _ref_pyro_nuts(y, sigma, warmup=100, samples=100):
+    """eight_schools through UNMODIFIED reference Pyro (baseline/_ref): pyro.infer.MCMC(pyro.infer.NUTS(model)),
+    one chain on the host; leapfrogs counted at pyro.ops.integrator.potential_grad (one call per leapfrog,
+    pyro/ops/integrator.py:45-65).  None when the reference is not importable."""
+    try:
+        from pyro_b200 import bind
+        if not bind.add_reference_to_path():
+            return None
+        import pyro
+        import pyro.distributions as dist
+        import pyro.ops.integrator as integ
+        assert "baseline" in pyro.__file__
+    except Exception:  # noqa: BLE001
+        return None
+
+    def model(y, sigma):
+        eta = pyro.sample("eta", dist.Normal(torch.zeros(8, dtype=y.dtype), torch.ones(8, dtype=y.dtype)))
+        mu = pyro.sample("mu", dist.Normal(torch.zeros(1, dtype=y.dtype), 10 * torch.ones(1, dtype=y.dtype)))
+        tau = pyro.sample("tau", dist.HalfCauchy(25 * torch.ones(1, dtype=y.dtype)))
+        pyro.sample("obs", dist.Normal(mu + tau * eta, sigma), obs=y)
+
+    calls = [0]
+    orig = integ.potential_grad
+
+    def counted(potential_fn, z):
+        calls[0] += 1
+        return orig(potential_fn, z)
+
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    integ.potential_grad = counted
+    try:
+        pyro.set_rng_seed(0)
+        pyro.clear_param_store()
+        mcmc = pyro.infer.MCMC(pyro.infer.NUTS(model), num_samples=samples, warmup_steps=warmup,
+                               disable_progbar=True)
+        t0 = time.perf_counter()
+        mcmc.run(y, sigma)
+        dt = time.perf_counter() - t0
+    except Exception:  # noqa: BLE001
+        return None
+    finally:
+        integ.potential_grad = orig
+        torch.set_num_threads(threads)
+    return {"leapfrog_per_sec": round(calls[0] / dt, 1), "cores": 1, "kind": "reference",
+            "sample": "eight_schools (examples/eight_schools/mcmc.py model), 1 chain, %d warm-up + %d samples, "
+                      "pyro %s pyro.infer.MCMC(NUTS(model)) on the host, fp64, %d potential_grad calls in %.1f s"
+                      % (warmup, samples, pyro.__version__, calls[0], dt)}
+
+
 def cpu_reference(steps, warmup, threads=None, n=N_ROWS):
     """The reference's CPU path for this workload, all host threads: unmodified Pyro when it is vendored
     (kind "reference"), else the oracle port (oracle/svi.py, pinned against reference Pyro's own trajectory
@@ -379,7 +429,11 @@ def nuts_section(dev, quick=False):
                 "per-chain mean/variance of every site; NUTS(model=eight_schools) recognised as the native class; "
                 "%d chains, max_tree_depth 10, %d sampling transitions timed after %d warm-up "
                 "(config 4 asks for 200 + 200: bounded sample)" % (C, S, W)}
-    # CPU baseline: oracle restatement of the reference sampler, config 1, one chain
+    # CPU baseline: unmodified reference Pyro (config 1, one chain), else the oracle restatement of its sampler
+    ref = _ref_pyro_nuts(y.double().cpu(), sigma.double().cpu())
+    if ref is not None:
+        out["cpu_baseline"] = ref
+        return out
     torch.set_num_threads(1)
     U = omcmc.eight_schools_potential(y.double().cpu(), sigma.double().cpu())
     chain = omcmc.NUTSChain(U, 10, seed=0)
