@@ -143,6 +143,32 @@ def build_svi(path, particles, lr=0.01, sharded=False):
                elbo_cls(num_particles=particles, vectorize_particles=True, max_plate_nesting=1))
 
 
+def particle_weak_section(dev, rank, world, flush, a):
+    """SURVEY.md 8(e), the particle axis: every rank scores its OWN 64 particles (different seed) on the full
+    data set, loss and gradients averaged by the one packed all-reduce per step -- weak scaling (64 * world
+    particles per step at the per-rank work of the 1-GPU line)."""
+    import torch.distributed as dist
+    import pyro_b200 as pyro
+    X, y = make_data(dev)
+    torch.manual_seed(1234 + 7919 * rank)
+    pyro.set_rng_seed(1234 + 7919 * rank)
+    svi = build_svi("glm+graph", PARTICLES, sharded=False)
+    steps = max(10, a.steps // 2)
+    dist.barrier()
+    ms, loss = time_steps(svi, (X, y), steps, 5, dev, flush)
+    torch.cuda.synchronize(dev)
+    tot = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
+    dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    tot = float(tot)
+    del svi, X, y
+    torch.cuda.empty_cache()
+    return {"ms_per_step": round(tot / steps, 4), "steps_per_sec": round(steps / (tot * 1e-3), 2),
+            "global_particles": PARTICLES * world,
+            "particle_steps_per_sec": round(PARTICLES * world * steps / (tot * 1e-3), 1),
+            "scaling": "weak: %d particles per rank, full data on every rank, 1 all-reduce of [loss, grads] per step"
+                       % PARTICLES, "final_loss": round(float(loss), 3)}
+
+
 def time_steps(svi, args, steps, warmup, device, flush, sync_each=True):
     """Per-step CUDA-event timing on the current stream; the L2 is flushed (256 MB write) between
     steps, outside the timed interval.  Returns (list of ms per step, last loss)."""
@@ -747,6 +773,12 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = e2e_n / (float(e2e_ms) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
+    weak = None
+    if world > 1 and not a.no_variants:
+        try:
+            weak = particle_weak_section(dev, rank, world, flush, a)
+        except Exception as e:  # pragma: no cover
+            weak = {"error": repr(e)[:300]}
     nuts_mr = None
     if world > 1 and not a.no_nuts:
         try:
@@ -827,6 +859,8 @@ def main():
                 out["nuts"] = nuts_section(dev)
             except Exception as e:  # pragma: no cover
                 out["nuts"] = {"error": repr(e)[:300]}
+    if weak is not None:
+        out["variants"] = {"particle_sharded_weak": weak}
     if nuts_mr is not None:
         out["nuts"] = nuts_mr
     if not a.no_configs:

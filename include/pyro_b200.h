@@ -224,6 +224,15 @@ typedef struct {
 int b2_latent_normal_draw(const b2_latent_job* jobs, int n_jobs, void* rng_state, void* stream);
 int b2_latent_normal_prior(const b2_latent_job* jobs, int n_jobs, void* stream);
 int b2_latent_normal_backward(const b2_latent_job* jobs, int n_jobs, void* stream);
+/* The prior sums of all jobs AND the assembly of the step's loss in one one-CTA launch (replaces
+ * b2_latent_normal_prior + b2_elbo_combine when the sites are small):
+ *   *out = SUM_j job_coeffs[j] * SUM log Normal(z_j | prior_j)  +  SUM_t term_coeffs[t] * *terms[t]
+ * terms: 0-d device scalars of the jobs' dtype (the other per-site sums of the ELBO); jobs[j].out0 (optional)
+ * receives the j-th prior sum.  pyro/infer/trace_elbo.py:82-112,147-152. */
+#define B2_LATENT_MAX_TERMS 24
+int b2_latent_normal_prior_combine(const b2_latent_job* jobs, int n_jobs, const double* job_coeffs,
+                                   const void* const* terms, const double* term_coeffs, int n_terms, void* out,
+                                   void* stream);
 
 /*
  * b2_reduce_to -- sum a strided full-shape tensor down to an output whose zero strides mark the

@@ -42,6 +42,8 @@ NUTS_SMALL_MAX_D = 64
 
 
 LATENT_MAX_JOBS = 8
+LATENT_MAX_TERMS = 24
+LATENT_COMBINE_MAX_N = 32768   # one CTA scores every prior of the step and assembles the loss up to this size
 LATENT_LOG_SCALE = 1
 LATENT_ACC_OUT0, LATENT_ACC_OUT1 = 2, 4
 LATENT_BLOCK = True       # Normal guide sites + Normal priors go through the latent-sites kernels (latent.cu)
@@ -106,6 +108,7 @@ SIGNATURES = {
     "b2_latent_normal_draw": (_i32, [_vp, _i32, _vp, _vp]),
     "b2_latent_normal_prior": (_i32, [_vp, _i32, _vp]),
     "b2_latent_normal_backward": (_i32, [_vp, _i32, _vp]),
+    "b2_latent_normal_prior_combine": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "b2_elbo_combine": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "b2_glm_bernoulli_logits": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32,
                                        _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

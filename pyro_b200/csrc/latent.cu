@@ -112,6 +112,45 @@ __global__ void __launch_bounds__(1024) latent_prior_kernel(const LatentArgs a) 
   if (threadIdx.x == 0) *reinterpret_cast<T*>(j.out0) = (T)v[0];
 }
 
+// Value-only priors of all jobs AND the assembly of the step's loss in one CTA:
+//   *out = sum_j job_coeff[j] * sum log p_j(z_j)  +  sum_t term_coeff[t] * *term[t]
+// (the ELBO's other per-site sums -- the draws' log q, the likelihood -- are 0-d device scalars by now).
+struct LatentCombine {
+  double job_coeff[B2_LATENT_MAX_JOBS];
+  const void* term[B2_LATENT_MAX_TERMS];
+  double term_coeff[B2_LATENT_MAX_TERMS];
+  int n_jobs, n_terms;
+  void* out;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024) latent_prior_combine_kernel(const LatentArgs a, const LatentCombine c) {
+  __shared__ double smem[32];
+  double total = 0.0;
+  for (int k = 0; k < c.n_jobs; ++k) {
+    const LatentJob& j = a.job[k];
+    double acc = 0.0;
+    for (unsigned i = threadIdx.x; i < j.n; i += blockDim.x) {
+      int ol, os, opl, ops;
+      unravel(j, i, ol, os, opl, ops);
+      T p[2] = {reinterpret_cast<const T*>(j.ploc)[opl], reinterpret_cast<const T*>(j.pscale)[ops]};
+      ElemOut<T> o;
+      Eval<kNormal, T, false>::run(reinterpret_cast<const T*>(j.z)[i], p, o);
+      acc += (double)o.lp;
+    }
+    double v[1] = {acc};
+    block_sum<1>(v, smem);
+    if (threadIdx.x == 0) {
+      if (j.out0) *reinterpret_cast<T*>(j.out0) = (T)v[0];
+      total += c.job_coeff[k] * v[0];
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < c.n_terms; ++t) total += c.term_coeff[t] * (double)*reinterpret_cast<const T*>(c.term[t]);
+    *reinterpret_cast<T*>(c.out) = (T)total;
+  }
+}
+
 // Per-element gradients (before the reduction to the stored shapes).
 template <typename T>
 __device__ __forceinline__ void latent_grad_elem(const LatentJob& j, unsigned i, bool logs, T& gloc, T& gscale) {
@@ -275,6 +314,36 @@ extern "C" int b2_latent_normal_prior(const b2_latent_job* jobs, int n_jobs, voi
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == B2_F32) latent_prior_kernel<float><<<n_jobs, threads_for(nmax), 0, s>>>(a);
   else latent_prior_kernel<double><<<n_jobs, threads_for(nmax), 0, s>>>(a);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int b2_latent_normal_prior_combine(const b2_latent_job* jobs, int n_jobs, const double* job_coeffs,
+                                              const void* const* terms, const double* term_coeffs, int n_terms,
+                                              void* out, void* stream) {
+  if (!out || !job_coeffs || (n_terms > 0 && (!terms || !term_coeffs))) return B2_ERR_NULL;
+  if (n_terms < 0 || n_terms > B2_LATENT_MAX_TERMS) return B2_ERR_TOO_LARGE;
+  LatentArgs a;
+  int dtype;
+  unsigned nmax;
+  const int code = fill_args(a, jobs, n_jobs, dtype, nmax);
+  if (code != B2_OK) return code;
+  LatentCombine c;
+  c.n_jobs = n_jobs;
+  c.n_terms = n_terms;
+  c.out = out;
+  for (int k = 0; k < n_jobs; ++k) {
+    if (!a.job[k].ploc || !a.job[k].pscale || !a.job[k].z) return B2_ERR_NULL;
+    c.job_coeff[k] = job_coeffs[k];
+  }
+  for (int t = 0; t < n_terms; ++t) {
+    if (!terms[t]) return B2_ERR_NULL;
+    c.term[t] = terms[t];
+    c.term_coeff[t] = term_coeffs[t];
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == B2_F32) latent_prior_combine_kernel<float><<<1, threads_for(nmax), 0, s>>>(a, c);
+  else latent_prior_combine_kernel<double><<<1, threads_for(nmax), 0, s>>>(a, c);
   count_launch();
   return check_launch();
 }

@@ -477,6 +477,58 @@ def latent_prior(items):
     return [out[k] for k in range(len(items))]
 
 
+def latent_prior_combine(items, item_coeffs, terms, term_coeffs):
+    """0-d ``sum_j item_coeffs[j] * sum log Normal(z_j | prior_j) + sum_t term_coeffs[t] * terms[t]`` in ONE launch
+    (b2_latent_normal_prior_combine), or None when it does not apply (too many / too large sites, mixed dtypes)."""
+    ref = items[0][0]
+    if (len(items) > N.LATENT_MAX_JOBS or len(terms) > N.LATENT_MAX_TERMS
+            or sum(z.numel() for z, _, _ in items) > N.LATENT_COMBINE_MAX_N
+            or any(z.dtype != ref.dtype for z, _, _ in items) or any(t.dtype != ref.dtype for t in terms)):
+        return None
+    out = torch.empty((), dtype=ref.dtype, device=ref.device)
+    jobs = (N.b2_latent_job * len(items))()
+    keep = []
+    for k, (z, ploc, pscale) in enumerate(items):
+        zc = z if z.is_contiguous() else z.contiguous()
+        keep.append(zc)
+        jobs[k] = _latent_job(tuple(z.shape), z.dtype, prior=(ploc, pscale), z=zc)
+    jc = (ctypes.c_double * len(items))(*[float(c) for c in item_coeffs])
+    n = len(terms)
+    ptrs = (ctypes.c_void_p * max(1, n))(*[t.data_ptr() for t in terms])
+    tc = (ctypes.c_double * max(1, n))(*[float(c) for c in term_coeffs])
+    N.check(N.lib().b2_latent_normal_prior_combine(jobs, len(items), jc, ptrs, tc, n, out.data_ptr(),
+                                                   N.stream_ptr(ref.device)), "b2_latent_normal_prior_combine")
+    return out
+
+
+# Deferred draw-backwards: inside `deferred_latent_backward()` (Trace_ELBO wraps its autograd.backward call in it)
+# the backward of a fused draw whose gradients all go straight into existing leaf `.grad` buffers only registers
+# its job; the registered jobs of the pass run as ONE launch when the context closes.  (A draw that has to hand a
+# gradient tensor back to the autograd engine launches at once: the engine may add to that tensor right away.)
+_DEFERRED = None
+
+
+class deferred_latent_backward:
+    def __enter__(self):
+        global _DEFERRED
+        self._prev = _DEFERRED
+        _DEFERRED = []
+        return self
+
+    def __exit__(self, *exc):
+        global _DEFERRED
+        pending, _DEFERRED = _DEFERRED, self._prev
+        for base in range(0, len(pending), N.LATENT_MAX_JOBS):
+            chunk = pending[base:base + N.LATENT_MAX_JOBS]
+            jobs = (N.b2_latent_job * len(chunk))(*[j for j, _, _ in chunk])
+            N.check(N.lib().b2_latent_normal_backward(jobs, len(chunk), N.stream_ptr(chunk[0][2])),
+                    "b2_latent_normal_backward")
+        return False
+
+
+SLOT_LEAVES = set()   # id() of the leaves whose gradient went straight into their .grad (read by SVI's capture)
+
+
 def _grad_slot(t):
     """A leaf whose ``.grad`` already exists (a replicated step keeps the gradients as views of the all-reduce
     payload; an eager step keeps the buffers the optimiser zeroed): the backward kernel can add into it and the
@@ -506,9 +558,12 @@ def latent_backward(gz, eps, z, loc, scale, log_scale, c, prior, need_loc, need_
         slot = _grad_slot(loc) if accumulate else None
         if slot is not None:
             gloc, ret_loc, flags_acc = slot, False, flags_acc | N.LATENT_ACC_OUT0
+            SLOT_LEAVES.add(id(loc))
         else:
             gloc = torch.empty(loc.shape, dtype=dtype, device=dev)
     slot = _grad_slot(scale) if (accumulate and need_scale and scale.is_contiguous()) else None
+    if slot is not None:
+        SLOT_LEAVES.add(id(scale))
     if not scale.is_contiguous():
         scale = scale.contiguous()      # the kernel writes d/dscale with the strides it reads scale with
     if need_scale:
@@ -521,6 +576,12 @@ def latent_backward(gz, eps, z, loc, scale, log_scale, c, prior, need_loc, need_
     job = _latent_job(shape, dtype, loc=gloc, scale=scale, log_scale=log_scale, prior=pr, z=z, eps=eps, gz=gz,
                       out0=gloc, out1=gscale, c=c, pw=prior[2] if prior is not None else 0.0)
     job.flags |= flags_acc
+    if _DEFERRED is not None and (not need_loc or not ret_loc) and (not need_scale or not ret_scale):
+        # every wanted gradient is ADDED into an existing .grad by the kernel (order-independent on the stream)
+        # and nothing is handed back to the engine, so the launch can wait for the other draws of this backward
+        # pass; the job's pointers stay valid through the tensors kept alongside it
+        _DEFERRED.append((job, (gz, eps, z, scale, gloc, gscale, pr), dev))
+        return (gloc if ret_loc else None), (gscale if ret_scale else None)
     jobs = (N.b2_latent_job * 1)(job)
     N.check(N.lib().b2_latent_normal_backward(jobs, 1, N.stream_ptr(dev)), "b2_latent_normal_backward")
     return (gloc if ret_loc else None), (gscale if ret_scale else None)

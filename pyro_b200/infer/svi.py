@@ -211,8 +211,11 @@ class SVI:
         # the real step of this call, on a side stream so that every lazily created buffer exists
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        from ..distributions import _ops as _dops
+        _dops.SLOT_LEAVES.clear()
         with torch.cuda.stream(side):
             eager_loss = self._eager_step(tuple(static_args), {}, want_tensor=True)
+        slot_leaves = set(_dops.SLOT_LEAVES)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         if isinstance(eager_loss, torch.Tensor):
@@ -227,8 +230,11 @@ class SVI:
                     # no stored gradients during the captured backward: autograd hands each parameter
                     # its fresh gradient tensor (no accumulate launch per parameter); the optimiser's
                     # pointer table is re-pointed below
+                    # (parameters whose gradient a kernel adds straight into .grad -- the latent-sites backward --
+                    # keep their buffer: the optimiser zeroed it, nothing is accumulated by the engine)
                     for p in self._last_params:
-                        p.grad = None
+                        if id(p) not in slot_leaves:
+                            p.grad = None
                 loss = self._eager_step(tuple(static_args), {}, want_tensor=True)
                 loss = loss.reshape(()) if isinstance(loss, torch.Tensor) else torch.as_tensor(loss, device=dev)
             if flush is not None:

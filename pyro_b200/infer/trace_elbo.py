@@ -159,14 +159,17 @@ class Trace_ELBO(ELBO):
                         prior_coeffs.append(sc)
                 if job is None:
                     add_site(site, 1.0)
+        from ..distributions import _ops
         if priors:
-            from ..distributions import _ops as _o
-            parts.extend(_o.latent_prior(priors))
+            # the priors' value-only sums and the assembly of the loss in one launch when the sites are small
+            loss = _ops.latent_prior_combine(priors, [-c / P for c in prior_coeffs], parts, [-c / P for c in coeffs])
+            if loss is not None:
+                return loss, terms
+            parts.extend(_ops.latent_prior(priors))
             coeffs.extend(prior_coeffs)
         if not parts:
             return torch.zeros(()), terms
         # loss = sum_i (-coeff_i / P) * part_i, assembled on the device in one launch
-        from ..distributions import _ops
         parts = [e.to(parts[0].dtype) if e.dtype != parts[0].dtype else e for e in parts]
         loss = _ops.elbo_combine(parts, [-c / P for c in coeffs])
         return loss, terms
@@ -184,7 +187,9 @@ class Trace_ELBO(ELBO):
                 # every term's upstream gradient is exactly 1 (contract of the fused nodes);
                 # pass one cached ones-scalar instead of letting autograd fill a new one per term
                 ones = [_one_like(t) for t in terms]
-                torch.autograd.backward(terms, ones, retain_graph=self.retain_graph)
+                from ..distributions import _ops as _o
+                with _o.deferred_latent_backward():
+                    torch.autograd.backward(terms, ones, retain_graph=self.retain_graph)
             return loss_particle
         if not allow_general:
             return None

@@ -250,6 +250,19 @@ def _latent_prior(items):
     return [odists.ELEMENTWISE[0][0](z, pl, ps).sum().detach() for z, pl, ps in items]
 
 
+def _latent_prior_combine(items, item_coeffs, terms, term_coeffs):
+    tot = sum(c * odists.ELEMENTWISE[0][0](z, pl, ps).sum().detach() for c, (z, pl, ps) in zip(item_coeffs, items))
+    return tot + sum(c * t.reshape(()) for c, t in zip(term_coeffs, terms))
+
+
+class _no_defer:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 def _latent_backward(gz, eps, z, loc, scale, log_scale, c, prior, need_loc, need_scale, accumulate=False):
     # csrc/latent.cu latent_backward_kernel restated: g = gz + pw * dlogp/dz; d/dloc = g;
     # d/dscale = g*eps - c/s  or  d/dlog_scale = g*eps*s - c
@@ -305,8 +318,9 @@ def enabled():
     nuts.NUTS._leaf_hier, nuts.NUTS._tree_merge, nuts.NUTS._rows_copy = _leaf_hier, _tree_merge, _rows_copy
     ops.reduce_to = _reduce_to
     saved_rs = (ops.normal_rsample_score, ops.normal_rsample_backward, N.EMULATE_RSAMPLE)
-    saved_latent = (ops.latent_prior, ops.latent_backward)
+    saved_latent = (ops.latent_prior, ops.latent_backward, ops.latent_prior_combine, ops.deferred_latent_backward)
     ops.latent_prior, ops.latent_backward = _latent_prior, _latent_backward
+    ops.latent_prior_combine, ops.deferred_latent_backward = _latent_prior_combine, _no_defer
     saved_comb = ops.elbo_combine
     ops.elbo_combine = _elbo_combine
     ops.normal_rsample_score = _normal_rsample_score
@@ -316,7 +330,8 @@ def enabled():
         yield
     finally:
         ops.normal_rsample_score, ops.normal_rsample_backward, N.EMULATE_RSAMPLE = saved_rs
-        ops.latent_prior, ops.latent_backward = saved_latent
+        (ops.latent_prior, ops.latent_backward, ops.latent_prior_combine,
+         ops.deferred_latent_backward) = saved_latent
         ops.elbo_combine = saved_comb
         pdist._BernoulliLinear._fused_sum = saved_glm
         nuts.NUTS._leaf_vector = saved_leaf
