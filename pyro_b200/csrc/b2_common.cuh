@@ -1,6 +1,7 @@
 // b2_common.cuh -- shared device helpers: vector loads, block reductions with a deterministic
 // cross-CTA finish, launch bookkeeping.
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -15,6 +16,44 @@ constexpr int kMaxPartialBlocks = 8192;
 
 extern int64_t g_launch_count;  // defined in api.cu
 inline void count_launch(int n = 1) { g_launch_count += n; }
+
+// ---- programmatic dependent launch -------------------------------------------------------------------
+// The small kernels of an SVI step run one after the other from a cold L2 (the step streams 132 MB through it),
+// so each of them spends most of its few microseconds on launch latency and on fetching its own code.  A kernel
+// launched with the programmatic-stream-serialization attribute may start while its predecessor in the stream is
+// still running, provided the predecessor allowed it (griddepcontrol.launch_dependents); it then blocks in
+// griddepcontrol.wait until the predecessor has COMPLETED and its memory is visible.  Both instructions sit at the
+// very top of the kernels below, so only launch + code fetch overlap, never a data access.  Captured into a CUDA
+// graph the dependency becomes a programmatic edge.  B2_PDL=0 in the environment launches the plain way.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_enter() {
+#if __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B2_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 inline int check_launch() {
   cudaError_t e = cudaGetLastError();

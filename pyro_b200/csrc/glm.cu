@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(256) glm_finish_kernel(const float* __restrict
                                                          double sum_coeff, int flags,
                                                          float* __restrict__ out_total,
                                                          unsigned int* __restrict__ ticket) {
+  pdl_enter();
   const int total = P * (D + 2);
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -253,8 +254,8 @@ extern "C" int b2_glm_bernoulli_logits(const float* X, const float* y, const flo
   }
   float* sum_p = out_sum_p ? out_sum_p : partials + (size_t)gx * P * (D + 2);
   const int total = P * (D + 2);
-  glm_finish_kernel<<<(total + 7) / 8, 256, 0, s>>>(
-      partials, gx, P, D, scale, weight, sum_p, out_dW, out_db, sum_coeff, flags, out_total, ticket);
+  launch_pdl(glm_finish_kernel, dim3((total + 7) / 8), dim3(256), 0, s,
+             partials, gx, P, D, scale, weight, sum_p, out_dW, out_db, sum_coeff, flags, out_total, ticket);
   const int nl = 2;
   count_launch(nl);
   return check_launch();

@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 glm_bernoulli_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                         const float* __restrict__ W, const float* __restrict__ bvec, int64_t N, int P,
                         float* __restrict__ partials, long long* __restrict__ trace) {
+  pdl_enter();   // lets glm_finish_kernel be resident (blocked in its griddepcontrol.wait) before this kernel ends
   using L = Layout<MODE>;
   // optional event trace of CTA (0, 0): trace[it * 16 + k] = SM clock of event k of tile it (first 64 tiles)
   const bool tr = (trace != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
@@ -803,13 +804,13 @@ int launch_glm_tc(const float* X, const float* y, const float* W, const float* b
   const char* tr_env = getenv("B2_GLM_TC_TRACE");
   long long* trace = tr_env ? reinterpret_cast<long long*>(strtoull(tr_env, nullptr, 10)) : nullptr;
   if (mode == 3)
-    glm_bernoulli_tc_kernel<3><<<grid, kThreads, Layout<3>::kSmemBytes, s>>>(mx, my, W, b, N, P, partials, trace);
+    launch_pdl(glm_bernoulli_tc_kernel<3>, grid, dim3(kThreads), (size_t)Layout<3>::kSmemBytes, s, mx, my, W, b, N, P, partials, trace);
   else if (mode == 2)
-    glm_bernoulli_tc_kernel<2><<<grid, kThreads, Layout<2>::kSmemBytes, s>>>(mx, my, W, b, N, P, partials, trace);
+    launch_pdl(glm_bernoulli_tc_kernel<2>, grid, dim3(kThreads), (size_t)Layout<2>::kSmemBytes, s, mx, my, W, b, N, P, partials, trace);
   else if (mode == 1)
-    glm_bernoulli_tc_kernel<1><<<grid, kThreads, Layout<1>::kSmemBytes, s>>>(mx, my, W, b, N, P, partials, trace);
+    launch_pdl(glm_bernoulli_tc_kernel<1>, grid, dim3(kThreads), (size_t)Layout<1>::kSmemBytes, s, mx, my, W, b, N, P, partials, trace);
   else
-    glm_bernoulli_tc_kernel<0><<<grid, kThreads, Layout<0>::kSmemBytes, s>>>(mx, my, W, b, N, P, partials, trace);
+    launch_pdl(glm_bernoulli_tc_kernel<0>, grid, dim3(kThreads), (size_t)Layout<0>::kSmemBytes, s, mx, my, W, b, N, P, partials, trace);
   return 0;
 }
 

@@ -62,6 +62,7 @@ __device__ __forceinline__ void unravel(const LatentJob& j, unsigned i, int& ol,
 
 template <typename T>
 __global__ void __launch_bounds__(1024) latent_draw_kernel(const LatentArgs a) {
+  pdl_enter();
   const LatentJob& j = a.job[blockIdx.x];
   const unsigned long long seed = a.state[0], ctr = a.state[1];
   const bool logs = (j.flags & B2_LATENT_LOG_SCALE) != 0;
@@ -125,6 +126,7 @@ struct LatentCombine {
 
 template <typename T>
 __global__ void __launch_bounds__(1024) latent_prior_combine_kernel(const LatentArgs a, const LatentCombine c) {
+  pdl_enter();
   __shared__ double smem[32];
   double total = 0.0;
   for (int k = 0; k < c.n_jobs; ++k) {
@@ -217,6 +219,7 @@ __device__ __forceinline__ void latent_reduce(const LatentJob& j, const int* st,
 
 template <typename T>
 __global__ void __launch_bounds__(1024) latent_backward_kernel(const LatentArgs a) {
+  pdl_enter();
   const LatentJob& j = a.job[blockIdx.x];
   const bool logs = (j.flags & B2_LATENT_LOG_SCALE) != 0;
   latent_reduce<T, 0>(j, j.st_loc, j.out0, logs, (j.flags & B2_LATENT_ACC_OUT0) != 0);
@@ -290,8 +293,8 @@ extern "C" int b2_latent_normal_draw(const b2_latent_job* jobs, int n_jobs, void
     if (!a.job[k].loc || !a.job[k].scale || !a.job[k].z || !a.job[k].eps || !a.job[k].out0) return B2_ERR_NULL;
   a.state = reinterpret_cast<unsigned long long*>(rng_state);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == B2_F32) latent_draw_kernel<float><<<n_jobs, threads_for(nmax), 0, s>>>(a);
-  else latent_draw_kernel<double><<<n_jobs, threads_for(nmax), 0, s>>>(a);
+  if (dtype == B2_F32) launch_pdl(latent_draw_kernel<float>, dim3(n_jobs), dim3(threads_for(nmax)), 0, s, a);
+  else launch_pdl(latent_draw_kernel<double>, dim3(n_jobs), dim3(threads_for(nmax)), 0, s, a);
   count_launch();
   int rc = check_launch();
   if (rc == B2_OK && n_jobs > 1) {
@@ -342,8 +345,8 @@ extern "C" int b2_latent_normal_prior_combine(const b2_latent_job* jobs, int n_j
     c.term_coeff[t] = term_coeffs[t];
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == B2_F32) latent_prior_combine_kernel<float><<<1, threads_for(nmax), 0, s>>>(a, c);
-  else latent_prior_combine_kernel<double><<<1, threads_for(nmax), 0, s>>>(a, c);
+  if (dtype == B2_F32) launch_pdl(latent_prior_combine_kernel<float>, dim3(1), dim3(threads_for(nmax)), 0, s, a, c);
+  else launch_pdl(latent_prior_combine_kernel<double>, dim3(1), dim3(threads_for(nmax)), 0, s, a, c);
   count_launch();
   return check_launch();
 }
@@ -360,8 +363,8 @@ extern "C" int b2_latent_normal_backward(const b2_latent_job* jobs, int n_jobs, 
     if (a.job[k].ploc && !a.job[k].z) return B2_ERR_NULL;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == B2_F32) latent_backward_kernel<float><<<n_jobs, threads_for(nmax), 0, s>>>(a);
-  else latent_backward_kernel<double><<<n_jobs, threads_for(nmax), 0, s>>>(a);
+  if (dtype == B2_F32) launch_pdl(latent_backward_kernel<float>, dim3(n_jobs), dim3(threads_for(nmax)), 0, s, a);
+  else launch_pdl(latent_backward_kernel<double>, dim3(n_jobs), dim3(threads_for(nmax)), 0, s, a);
   count_launch();
   return check_launch();
 }

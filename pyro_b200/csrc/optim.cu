@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) clipped_adam_kernel(void* const* __restri
                                                            double* __restrict__ lrs,
                                                            int32_t* __restrict__ steps,
                                                            int zero_grad) {
+  pdl_enter();
   const int ti = blockIdx.y;
   const int64_t n = numel[ti];
   double* h = hyper + (size_t)ti * kAdamHyperStride;
@@ -165,9 +166,9 @@ extern "C" int b2_clipped_adam(int n, void* const* p, void* const* g, void* cons
     // every tensor fits one CTA's grid-stride loop: one launch does advance + update
     dim3 grid(1, (unsigned)n, 1);
     if (dtype == B2_F32)
-      clipped_adam_kernel<float, true><<<grid, 256, 0, s>>>(p, g, m, v, numel, hyper, lrs, steps, zero_grad);
+      launch_pdl(clipped_adam_kernel<float, true>, grid, dim3(256), 0, s, p, g, m, v, numel, hyper, lrs, steps, zero_grad);
     else
-      clipped_adam_kernel<double, true><<<grid, 256, 0, s>>>(p, g, m, v, numel, hyper, lrs, steps, zero_grad);
+      launch_pdl(clipped_adam_kernel<double, true>, grid, dim3(256), 0, s, p, g, m, v, numel, hyper, lrs, steps, zero_grad);
     count_launch(1);
     return check_launch();
   }
