@@ -14,7 +14,11 @@ import torch
 from torch.utils._pytree import tree_map
 
 _META = {"size", "dim", "ndimension", "numel", "nelement", "__len__", "is_floating_point", "is_complex",
-         "element_size", "get_device", "__get__", "__repr__", "__str__", "__format__"}
+         "element_size", "get_device", "__repr__", "__str__", "__format__"}
+# attributes (property getters arrive as ``__get__`` of their descriptor) answered from the metadata alone
+_META_ATTRS = {"shape", "dtype", "device", "ndim", "layout", "is_cuda", "is_cpu", "is_sparse", "is_quantized",
+               "is_meta", "is_leaf", "requires_grad", "grad_fn", "names", "is_mkldnn", "is_xpu", "is_nested",
+               "itemsize", "nbytes", "output_nr", "_version"}
 
 
 class LazyExpParam(torch.Tensor):
@@ -49,7 +53,8 @@ class LazyExpParam(torch.Tensor):
     def __torch_function__(cls, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
         name = getattr(func, "__name__", None)
-        if name in _META:
+        if name in _META or (name == "__get__" and
+                             getattr(getattr(func, "__self__", None), "__name__", "") in _META_ATTRS):
             with torch._C.DisableTorchFunctionSubclass():
                 return func(*args, **kwargs)
         return func(*tree_map(densify, args), **tree_map(densify, kwargs))
