@@ -185,7 +185,16 @@ class GaussianHMM(Distribution):
         ll = ll - 0.5 * ((vs * vs).sum() + rem * const) - rem * Ls.diagonal().log().sum()
         return ll
 
-    def _filter(self, value, T):
+    def filter(self, value):
+        """Posterior over the FINAL hidden state given a sequence of observations, as a ``MultivariateNormal``
+        usable as ``initial_dist`` of a continuation (pyro/distributions/hmm.py:604-633: there the time axis is
+        eliminated by the tensordot scan and the precision form is converted back; here the filtered mean and
+        covariance of the last Kalman step are the answer directly)."""
+        T = value.shape[-2]
+        _, m, P = self._filter(value, T, return_state=True)
+        return MultivariateNormal(m.squeeze(-2), covariance_matrix=P)
+
+    def _filter(self, value, T, return_state=False):
         O = self.obs_dim
         m = self._m0.unsqueeze(-2)            # [..., 1, H] row vector
         P = self._P0
@@ -213,6 +222,8 @@ class GaussianHMM(Distribution):
             m = m + v @ Kt
             P = P - PH @ Kt
             P = 0.5 * (P + P.transpose(-1, -2))
+        if return_state:
+            return ll, m, P
         return ll
 
     def rsample(self, sample_shape=torch.Size()):

@@ -5,6 +5,8 @@ from /root/reference + the opt_einsum stand-in; run in the build container):
 
   renyi.npz    RenyiELBO (alpha = 0.5 and 2.0, 4 vectorised particles) loss and parameter gradients on a
                Normal regression with injected guide noise (pyro/infer/renyi_elbo.py)
+  hmm_filter.npz  GaussianHMM.filter (pyro/distributions/hmm.py:604-633): posterior mean / covariance of the final
+               hidden state, time-invariant and time-varying parameters
 """
 import os
 import sys
@@ -64,5 +66,29 @@ def renyi():
     print({k: (v if np.ndim(v) == 0 else np.asarray(v).shape) for k, v in out.items()})
 
 
+def hmm_filter():
+    torch.manual_seed(11)
+    out = {}
+    for tag, tv in (("inv", False), ("var", True)):
+        Hd, O, T = 3, 2, 7
+        lead = (T,) if tv else ()
+        F = 0.5 * torch.randn(lead + (Hd, Hd))
+        Hm = torch.randn(lead + (Hd, O))
+        i_loc, i_scale = torch.randn(Hd), torch.rand(Hd) + 0.5
+        t_loc, t_scale = torch.randn(lead + (Hd,)), torch.rand(lead + (Hd,)) + 0.3
+        o_loc, o_scale = torch.randn(lead + (O,)), torch.rand(lead + (O,)) + 0.4
+        x = torch.randn(T, O)
+        hmm = dist.GaussianHMM(dist.Normal(i_loc, i_scale).to_event(1), F, dist.Normal(t_loc, t_scale).to_event(1),
+                               Hm, dist.Normal(o_loc, o_scale).to_event(1), duration=T)
+        post = hmm.filter(x)
+        for k, v in (("F", F), ("H", Hm), ("i_loc", i_loc), ("i_scale", i_scale), ("t_loc", t_loc),
+                     ("t_scale", t_scale), ("o_loc", o_loc), ("o_scale", o_scale), ("x", x),
+                     ("mean", post.loc), ("cov", post.covariance_matrix), ("logp", hmm.log_prob(x))):
+            out["%s.%s" % (tag, k)] = v.detach().numpy()
+    np.savez(os.path.join(HERE, "hmm_filter.npz"), **out)
+    print({k: np.asarray(v).shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     renyi()
+    hmm_filter()

@@ -104,3 +104,42 @@ def test_kalman_filter_against_first_principles_oracle_on_seeded_inputs():
                          dist.Normal(bv, osc).to_event(1), duration=T)
     ref = ohmm.gaussian_hmm_log_prob(m0, P0, F, bw, Q, Hm, bv, torch.diag_embed(osc ** 2), x)
     assert abs(float(d.log_prob(x)) - float(ref)) <= 1e-9 * abs(float(ref))
+
+
+def _filter_case(tag, device, dtype):
+    g = load_npz("hmm_filter.npz")
+    t = lambda k: torch.as_tensor(g["%s.%s" % (tag, k)]).to(device, dtype)  # noqa: E731
+    d = dist.GaussianHMM(dist.Normal(t("i_loc"), t("i_scale")).to_event(1), t("F"),
+                         dist.Normal(t("t_loc"), t("t_scale")).to_event(1), t("H"),
+                         dist.Normal(t("o_loc"), t("o_scale")).to_event(1), duration=t("x").shape[0])
+    post = d.filter(t("x"))
+    L = post.scale_tril
+    return post.loc.detach().cpu().double(), (L @ L.transpose(-1, -2)).detach().cpu().double(), \
+        d.log_prob(t("x")).detach().cpu().double(), g
+
+
+@pytest.mark.parametrize("tag", ["inv", "var"])
+def test_gaussian_hmm_filter_matches_reference_and_oracle(tag):
+    """``GaussianHMM.filter`` (pyro/distributions/hmm.py:604-633): posterior of the final hidden state against
+    the unmodified reference (tests/golden/hmm_filter.npz) and against the first-principles oracle (joint
+    Gaussian of (z_T, x_1..x_T), conditioned on x); the oracle itself is pinned by the same golden."""
+    from oracle import hmm as ohmm
+    mean, cov, lp, g = _filter_case(tag, "cpu", torch.float64)
+    rm, rc = torch.as_tensor(g[tag + ".mean"]), torch.as_tensor(g[tag + ".cov"])
+    assert torch.allclose(mean, rm, atol=1e-9, rtol=1e-9) and torch.allclose(cov, rc, atol=1e-9, rtol=1e-9)
+    assert abs(float(lp) - float(g[tag + ".logp"])) <= 1e-9 * abs(float(g[tag + ".logp"]))
+    t = lambda k: torch.as_tensor(g["%s.%s" % (tag, k)])  # noqa: E731
+    om, oc = ohmm.gaussian_hmm_filter(t("i_loc"), torch.diag_embed(t("i_scale") ** 2), t("F"), t("t_loc"),
+                                      torch.diag_embed(t("t_scale") ** 2), t("H"), t("o_loc"),
+                                      torch.diag_embed(t("o_scale") ** 2), t("x"))
+    assert torch.allclose(om, rm, atol=1e-9, rtol=1e-9) and torch.allclose(oc, rc, atol=1e-9, rtol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["inv", "var"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-4)])
+def test_gaussian_hmm_filter_matches_reference_gpu(tag, dtype, tol):
+    from conftest import device
+    mean, cov, _, g = _filter_case(tag, device(), dtype)
+    assert torch.allclose(mean, torch.as_tensor(g[tag + ".mean"]), atol=tol, rtol=tol)
+    assert torch.allclose(cov, torch.as_tensor(g[tag + ".cov"]), atol=tol, rtol=tol)
