@@ -65,5 +65,11 @@ class LazyExpParam(torch.Tensor):
 
 
 def densify(x):
-    """``x`` itself, or the materialised ``exp(u)`` of a :class:`LazyExpParam`."""
-    return x.dense() if isinstance(x, LazyExpParam) else x
+    """What a native kernel (an autograd.Function, opaque to ``__torch_function__``) must be handed: the
+    materialised ``exp(u)`` of a :class:`LazyExpParam`; the plain tensor inside a trace-time wrapper that keeps one
+    as ``_t`` (the provenance tags of TraceGraph_ELBO); anything else unchanged."""
+    if isinstance(x, LazyExpParam):
+        return x.dense()
+    if type(x) is not torch.Tensor and isinstance(x, torch.Tensor) and hasattr(x, "_provenance"):
+        return x._t
+    return x

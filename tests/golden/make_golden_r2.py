@@ -5,6 +5,9 @@ from /root/reference + the opt_einsum stand-in; run in the build container):
 
   renyi.npz    RenyiELBO (alpha = 0.5 and 2.0, 4 vectorised particles) loss and parameter gradients on a
                Normal regression with injected guide noise (pyro/infer/renyi_elbo.py)
+  tracegraph.npz  TraceGraph_ELBO (pyro/infer/tracegraph_elbo.py): two consecutive loss_and_grads calls on a model with
+               nested plates, two non-reparameterisable sites (decaying-average baseline / baseline_value), one
+               reparameterised site, injected guide values; losses, parameter gradients, baseline state
   hmm_filter.npz  GaussianHMM.filter (pyro/distributions/hmm.py:604-633): posterior mean / covariance of the final
                hidden state, time-invariant and time-varying parameters
 """
@@ -89,6 +92,66 @@ def hmm_filter():
     print({k: np.asarray(v).shape for k, v in out.items()})
 
 
+def tracegraph():
+    from pyro.infer import TraceGraph_ELBO
+    torch.manual_seed(5)
+    data = torch.randn(4, 3)
+    a_val = torch.tensor([1.0, 0.0, 1.0])
+    b_val = torch.tensor([[0, 2, 1], [1, 1, 0], [2, 0, 2], [0, 1, 1]])
+    eps = torch.randn(3)
+    probs_b = torch.tensor([[0.2, 0.5, 0.3], [0.6, 0.1, 0.3]])
+    qb0 = torch.softmax(torch.randn(4, 3, 3), -1)
+    out = {"data": data.numpy(), "a": a_val.numpy(), "b": b_val.numpy(), "eps": eps.numpy(),
+           "probs_b": probs_b.numpy(), "qb0": qb0.numpy()}
+
+    def model(data):
+        with pyro.plate("outer", 3, dim=-1):
+            a = pyro.sample("a", dist.Bernoulli(torch.tensor(0.35)))
+            z = pyro.sample("z", dist.Normal(2 * a - 1, 1.0))
+            with pyro.plate("inner", 4, dim=-2):
+                b = pyro.sample("b", dist.Categorical(probs_b[a.long()]))
+                pyro.sample("obs", dist.Normal(z + b.to(data.dtype), 1.5), obs=data)
+
+    class Inject(poutine.messenger.Messenger):
+        def _pyro_sample(self, msg):
+            if msg["name"] == "a":
+                msg["value"] = a_val
+            elif msg["name"] == "b":
+                msg["value"] = b_val
+            elif msg["name"] == "z":
+                msg["value"] = msg["fn"].loc + eps * msg["fn"].scale
+
+    def guide(data):
+        qa = pyro.param("qa", torch.tensor([0.4, 0.6, 0.5]), constraint=dist.constraints.unit_interval)
+        qb = pyro.param("qb", qb0, constraint=dist.constraints.simplex)
+        mz = pyro.param("mz", torch.tensor([0.1, -0.3, 0.2]))
+        sz = pyro.param("sz", torch.tensor([0.8, 1.2, 0.6]), constraint=dist.constraints.positive)
+        bv = pyro.param("bv", torch.full((4, 3), -2.0))
+        with Inject(), pyro.plate("outer", 3, dim=-1):
+            a = pyro.sample("a", dist.Bernoulli(qa),
+                            infer={"baseline": {"use_decaying_avg_baseline": True, "baseline_beta": 0.8}})
+            pyro.sample("z", dist.Normal(mz + a, sz))
+            with pyro.plate("inner", 4, dim=-2):
+                pyro.sample("b", dist.Categorical(qb), infer={"baseline": {"baseline_value": bv}})
+
+    pyro.clear_param_store()
+    elbo = TraceGraph_ELBO(max_plate_nesting=2)
+    names = ("qa", "qb", "mz", "sz", "bv")
+    for it in range(2):
+        loss = elbo.loss_and_grads(model, guide, data)
+        store = pyro.get_param_store()
+        out["loss_%d" % it] = loss
+        for n in names:
+            u = store[n].unconstrained()
+            out["grad_%s_%d" % (n, it)] = u.grad.numpy().copy()
+            u.grad = None
+        out["avg_a_%d" % it] = store["__baseline_avg_downstream_cost_a"].detach().numpy().copy()
+    out["value"] = elbo.loss(model, guide, data)
+    np.savez(os.path.join(HERE, "tracegraph.npz"), **out)
+    print({k: (v if np.ndim(v) == 0 else np.asarray(v).shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     renyi()
     hmm_filter()
+    tracegraph()

@@ -105,3 +105,71 @@ def test_predictive_conjugate_gpu():
     if EMULATE:
         pytest.skip("covered by the cpu test")
     _predictive(device())
+
+
+def _tracegraph(dev):
+    """TraceGraph_ELBO against unmodified Pyro (tests/golden/tracegraph.npz): nested plates, a Bernoulli and a
+    Categorical guide site without rsample (decaying-average baseline / learnable baseline_value), a Normal site
+    with rsample between them; guide values injected; two consecutive calls so the running baseline is used."""
+    from pyro_b200.infer import TraceGraph_ELBO
+    g = load_npz("tracegraph.npz")
+    torch.set_default_dtype(torch.float64)
+    t = lambda k: torch.as_tensor(g[k]).to(dev)  # noqa: E731
+    data, a_val, b_val, eps, probs_b, qb0 = t("data"), t("a"), t("b"), t("eps"), t("probs_b"), t("qb0")
+    c = lambda v: torch.tensor(v, device=dev)  # noqa: E731
+
+    def model(data):
+        with pyro.plate("outer", 3, dim=-1):
+            a = pyro.sample("a", dist.Bernoulli(c(0.35)))
+            z = pyro.sample("z", dist.Normal(2 * a - 1, c(1.0)))
+            with pyro.plate("inner", 4, dim=-2):
+                b = pyro.sample("b", dist.Categorical(probs_b[a.long()]))
+                pyro.sample("obs", dist.Normal(z + b.to(data.dtype), c(1.5)), obs=data)
+
+    class Inject(poutine.Messenger):
+        def _pyro_sample(self, msg):
+            if msg["name"] == "a":
+                msg["value"] = a_val
+            elif msg["name"] == "b":
+                msg["value"] = b_val
+            elif msg["name"] == "z":
+                msg["value"] = msg["fn"].loc + eps * msg["fn"].scale
+
+    def guide(data):
+        qa = pyro.param("qa", lambda: c([0.4, 0.6, 0.5]), constraint=constraints.unit_interval)
+        qb = pyro.param("qb", lambda: qb0.clone(), constraint=constraints.simplex)
+        mz = pyro.param("mz", lambda: c([0.1, -0.3, 0.2]))
+        sz = pyro.param("sz", lambda: c([0.8, 1.2, 0.6]), constraint=constraints.positive)
+        bv = pyro.param("bv", lambda: torch.full((4, 3), -2.0, device=dev))
+        with Inject(), pyro.plate("outer", 3, dim=-1):
+            a = pyro.sample("a", dist.Bernoulli(qa),
+                            infer={"baseline": {"use_decaying_avg_baseline": True, "baseline_beta": 0.8}})
+            pyro.sample("z", dist.Normal(mz + a, sz))
+            with pyro.plate("inner", 4, dim=-2):
+                pyro.sample("b", dist.Categorical(qb), infer={"baseline": {"baseline_value": bv}})
+
+    pyro.clear_param_store()
+    elbo = TraceGraph_ELBO(max_plate_nesting=2)
+    store = pyro.get_param_store()
+    for it in range(2):
+        loss = elbo.loss_and_grads(model, guide, data)
+        assert abs(loss - float(g["loss_%d" % it])) <= 1e-9 * abs(float(g["loss_%d" % it]))
+        for n in ("qa", "qb", "mz", "sz", "bv"):
+            u = store._params[n]
+            assert torch.allclose(u.grad.cpu(), torch.as_tensor(g["grad_%s_%d" % (n, it)]), atol=1e-9, rtol=1e-8), (n, it)
+            u.grad = None
+        avg = store._params["__baseline_avg_downstream_cost_a"].detach().cpu()
+        assert torch.allclose(avg, torch.as_tensor(g["avg_a_%d" % it]), atol=1e-10, rtol=1e-10)
+    assert abs(elbo.loss(model, guide, data) - float(g["value"])) <= 1e-9 * abs(float(g["value"]))
+    torch.set_default_dtype(torch.float32)
+
+
+def test_tracegraph_elbo_matches_reference_cpu(emu):
+    _tracegraph("cpu")
+
+
+@pytest.mark.gpu
+def test_tracegraph_elbo_matches_reference_gpu():
+    if EMULATE:
+        pytest.skip("covered by the cpu test")
+    _tracegraph(device())
