@@ -117,66 +117,79 @@ class GaussianHMM(Distribution):
         tol = 1e-13 if value.dtype == torch.float64 else 3e-7
         m = self._m0.unsqueeze(0)             # [1, H] predicted/filtered mean (row vector)
         P = self._P0
-        ll = value.new_zeros(())
+        Ft, Ht = F.transpose(-1, -2), Hm.transpose(-1, -2)
         Pm_prev = None
         t = 0
         converged = False
+        vs_all, diag_all = [], []
+        # The step is launch-bound (H = 512: ~20 small kernels per time step, three times that with the backward
+        # pass), so the recursion is written with fused multiply-adds (addmm), the per-step likelihood terms are
+        # only COLLECTED here and reduced once after the loop, and convergence is tested every 4th step (a test
+        # is 6 launches and a host synchronisation; running up to 3 exact steps more costs less).
         while t < T:
-            m = m @ F + bw
-            Pm = F.transpose(-1, -2) @ P @ F + Q
-            if Pm_prev is not None and t >= 4:
+            m = torch.addmm(bw, m, F)
+            Pm = torch.addmm(Q, Ft @ P, F)
+            if Pm_prev is not None and t >= 4 and t % 4 == 0:
                 with torch.no_grad():
                     rel = float((Pm - Pm_prev).abs().max() / Pm.abs().max().clamp(min=1e-300))
                 if rel <= tol:
                     converged = True
                     break
             PH = Pm @ Hm
-            S = Hm.transpose(-1, -2) @ PH + R
-            v = value[t:t + 1, :] - (m @ Hm + bv)
+            S = torch.addmm(R, Ht, PH)
+            v = value[t:t + 1, :] - torch.addmm(bv, m, Hm)
             Ls = torch.linalg.cholesky(S)
-            vs = torch.linalg.solve_triangular(Ls, v.transpose(-1, -2), upper=False)
-            ll = ll - 0.5 * ((vs * vs).sum() + const) - Ls.diagonal().log().sum()
+            vs_all.append(torch.linalg.solve_triangular(Ls, v.transpose(-1, -2), upper=False))
+            diag_all.append(Ls.diagonal())
             Kt = torch.cholesky_solve(PH.transpose(-1, -2), Ls)
-            m = m + v @ Kt
-            P = Pm - PH @ Kt
+            m = torch.addmm(m, v, Kt)
+            P = torch.addmm(Pm, PH, Kt, alpha=-1.0)
             P = 0.5 * (P + P.transpose(-1, -2))
             Pm_prev = Pm
             t += 1
+        ll = value.new_zeros(())
+        if vs_all:
+            VS = torch.cat(vs_all, dim=1)                                  # [O, t]
+            ll = -0.5 * ((VS * VS).sum() + len(vs_all) * const) - torch.stack(diag_all).log().sum()
         if not converged:
             return ll
         # ---- stationary phase: m holds the predicted mean of step t, Pm the stationary covariance ----
         rem = T - t
         PH = Pm @ Hm
-        S = Hm.transpose(-1, -2) @ PH + R
+        S = torch.addmm(R, Ht, PH)
         Ls = torch.linalg.cholesky(S)
         Kt = torch.cholesky_solve(PH.transpose(-1, -2), Ls)            # [O, H]
         KF = Kt @ F                                                    # [O, H]
         A = F - Hm @ KF                                                # (I - H K) F
         X = value[t:] - bv                                             # [rem, O]
-        U = X @ KF + bw                                                # [rem, H]
+        U = torch.addmm(bw, X, KF)                                     # [rem, H]
         B = max(8, int(math.ceil(math.sqrt(rem))))
         nblk = (rem + B - 1) // B
         pad = nblk * B - rem
         if pad:
             U = torch.cat([U, U.new_zeros(pad, Hd)], dim=0)
         Ub = U.reshape(nblk, B, Hd)
-        # local solutions with zero start, all blocks at once; powers of A alongside
+        # powers A^1 .. A^B by doubling: [A^1..A^k] @ A^k = [A^(k+1)..A^(2k)] -- ceil(log2 B) batched GEMM launches
+        # instead of B sequential ones (same FLOPs)
+        pows = A.unsqueeze(0)
+        while pows.shape[0] < B:
+            k = pows.shape[0]
+            take = min(k, B - k)
+            pows = torch.cat([pows, pows[:take] @ pows[k - 1]], dim=0)
+        AP = torch.cat([torch.eye(Hd, dtype=A.dtype, device=A.device).unsqueeze(0), pows[:B - 1]], dim=0)  # A^0..A^(B-1)
+        AB = pows[B - 1]                                               # A^B
+        # local solutions with zero start, all blocks at once
         w = U.new_zeros(nblk, Hd)
-        ap = torch.eye(Hd, dtype=A.dtype, device=A.device)
-        Ws, APs = [], []
+        Ws = []
         for j in range(B):
             Ws.append(w)
-            APs.append(ap)
-            w = w @ A + Ub[:, j]
-            ap = ap @ A
+            w = torch.addmm(Ub[:, j], w, A)
         W = torch.stack(Ws, dim=1)                                     # [nblk, B, H]
-        AP = torch.stack(APs, dim=0)                                   # [B, H, H], AP[j] = A^j
-        AB = ap                                                        # A^B
         starts = []
         s_b = m                                                        # [1, H]
         for b in range(nblk):
             starts.append(s_b)
-            s_b = s_b @ AB + w[b:b + 1]
+            s_b = torch.addmm(w[b:b + 1], s_b, AB)
         S0 = torch.cat(starts, dim=0)                                  # [nblk, H]
         M = torch.einsum("bh,jhk->bjk", S0, AP) + W                    # predicted means [nblk, B, H]
         M = M.reshape(nblk * B, Hd)[:rem]
