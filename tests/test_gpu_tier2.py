@@ -373,3 +373,42 @@ def test_full_mass_nuts_correlated_posterior_gpu():
 def test_slice_sampling_nuts_posterior_gpu():
     from test_host_logic_cpu import _slice_nuts_case
     _slice_nuts_case(DEV)
+
+
+def test_config4_potential_and_integrator_at_baseline_size():
+    """BASELINE config 4 at its stated size (J = 1 000 000 groups, D = J + 2): the native hierarchical-Normal
+    potential and gradient against the fp64 oracle (oracle/mcmc.py, chain 0 and chain 3 of 4), and two
+    size-independent properties of the C-ABI leapfrog at that size -- time reversibility (n steps forward,
+    momentum flipped, n steps back returns to the start) and an O(eps^2) energy error."""
+    if EMULATE:
+        pytest.skip("needs the device kernels")
+    from pyro_b200.infer.mcmc import HierNormalPotential
+    torch.manual_seed(4)
+    J, C = 1_000_000, 4
+    sig = 5 + 15 * torch.rand(J, device=DEV)
+    yy = 5 + 3 * torch.randn(J, device=DEV) + sig * torch.randn(J, device=DEV)
+    pot = HierNormalPotential(yy, sig)
+    z = torch.cat([torch.randn(C, 2, device=DEV) * 0.1, torch.randn(C, J, device=DEV)], 1).contiguous()
+    U, G = pot.value_and_grad(z)
+    ref_U = omcmc.eight_schools_potential(yy.double().cpu(), sig.double().cpu())
+    for c in (0, 3):
+        g_ref, u_ref = omcmc.potential_grad(ref_U, z[c].double().cpu())
+        assert abs(float(U[c]) - float(u_ref)) <= 2e-6 * abs(float(u_ref))
+        assert float((G[c].double().cpu() - g_ref).abs().max()) <= 1e-3 * max(1.0, float(g_ref.abs().max()))
+    k = HMC(potential_fn=pot, adapt_step_size=False, adapt_mass_matrix=False)
+    k.setup(0, C, initial_params=z.clone())
+    eps = torch.full((C,), 1e-3, device=DEV)
+    minv = torch.ones(C, J + 2, device=DEV)
+    r0 = torch.randn(C, J + 2, device=DEV)
+    zc, rc, gc = z.clone(), r0.clone(), G.clone()
+    e0 = U + 0.5 * (r0 * r0).sum(1)
+    for _ in range(5):
+        zc, rc, gc, Uc, ke = k._leapfrog(zc, rc, gc, eps, minv)
+    e1 = Uc + ke
+    assert float(((e1 - e0).abs() / e0.abs()).max()) < 1e-5            # fp32 sums of 1e6 terms + O(eps^2)
+    rb = (-rc).contiguous()
+    zb, gb = zc, gc
+    for _ in range(5):
+        zb, rb, gb, _, _ = k._leapfrog(zb, rb, gb, eps, minv)
+    assert float((zb - z).abs().max()) < 5e-5
+    assert float((rb + r0).abs().max()) < 5e-4
