@@ -17,6 +17,8 @@
 // One CTA per job (a job = one site, <= B2_RSAMPLE_MAX_N elements, <= 6 dims after host-side coalescing is NOT
 // required: strides are taken as given), blockIdx.x = job, so the sites of a step share launches.  Reductions
 // are in a fixed order (deterministic).
+#include <stdint.h>
+
 #include "b2_common.cuh"
 #include "b2_math.cuh"
 #include "nuts_core.cuh"
@@ -236,6 +238,12 @@ static int fill_job(LatentJob& j, const b2_latent_job& h, int dtype) {
   }
   for (int d = 0; d < h.ndim; ++d) {
     if (h.shape[d] <= 0) return B2_ERR_BAD_SHAPE;
+    // offsets are 32-bit in the kernels (a site has <= 65 536 elements, but an operand may be a strided view)
+    const int64_t lim = INT32_MAX / B2_RSAMPLE_MAX_N;
+    if (h.loc_stride[d] > lim || h.loc_stride[d] < -lim || h.scale_stride[d] > lim || h.scale_stride[d] < -lim ||
+        h.prior_loc_stride[d] > lim || h.prior_loc_stride[d] < -lim || h.prior_scale_stride[d] > lim ||
+        h.prior_scale_stride[d] < -lim)
+      return B2_ERR_TOO_LARGE;
     j.shape[d] = (unsigned)h.shape[d];
     n *= h.shape[d];
     j.st_loc[d] = (int)h.loc_stride[d];

@@ -430,6 +430,11 @@ def _latent_job(shape, dtype, loc=None, scale=None, log_scale=False, prior=None,
             return None
         v = t.expand(shape) if tuple(t.shape) != tuple(shape) else t
         st = v.stride()
+        if any(abs(x) > 32767 for x in st):
+            # the kernels index with 32-bit offsets: a widely strided view is packed first (its memory stays
+            # valid for the launch: the caching allocator reuses it in stream order only)
+            v = t.contiguous().expand(shape)
+            st = v.stride()
         for i in range(len(shape)):
             strides[i] = st[i] if shape[i] != 1 else 0
         return v.data_ptr()
