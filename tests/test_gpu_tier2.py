@@ -379,7 +379,7 @@ def test_config4_potential_and_integrator_at_baseline_size():
     """BASELINE config 4 at its stated size (J = 1 000 000 groups, D = J + 2): the native hierarchical-Normal
     potential and gradient against the fp64 oracle (oracle/mcmc.py, chain 0 and chain 3 of 4), and two
     size-independent properties of the C-ABI leapfrog at that size -- time reversibility (n steps forward,
-    momentum flipped, n steps back returns to the start) and an O(eps^2) energy error."""
+    momentum flipped, n steps back returns to the start) and second-order convergence of the energy error."""
     if EMULATE:
         pytest.skip("needs the device kernels")
     from pyro_b200.infer.mcmc import HierNormalPotential
@@ -397,18 +397,28 @@ def test_config4_potential_and_integrator_at_baseline_size():
         assert float((G[c].double().cpu() - g_ref).abs().max()) <= 1e-3 * max(1.0, float(g_ref.abs().max()))
     k = HMC(potential_fn=pot, adapt_step_size=False, adapt_mass_matrix=False)
     k.setup(0, C, initial_params=z.clone())
-    eps = torch.full((C,), 1e-3, device=DEV)
     minv = torch.ones(C, J + 2, device=DEV)
     r0 = torch.randn(C, J + 2, device=DEV)
-    zc, rc, gc = z.clone(), r0.clone(), G.clone()
     e0 = U + 0.5 * (r0 * r0).sum(1)
-    for _ in range(5):
-        zc, rc, gc, Uc, ke = k._leapfrog(zc, rc, gc, eps, minv)
-    e1 = Uc + ke
-    assert float(((e1 - e0).abs() / e0.abs()).max()) < 1e-5            # fp32 sums of 1e6 terms + O(eps^2)
+
+    def run(step, n):
+        eps = torch.full((C,), step, device=DEV)
+        zc, rc, gc = z.clone(), r0.clone(), G.clone()
+        for _ in range(n):
+            zc, rc, gc, Uc, ke = k._leapfrog(zc, rc, gc, eps, minv)
+        return zc, rc, gc, (Uc + ke - e0), eps
+
+    # second order: the same trajectory length with half the step has ~1/4 of the energy error (errors of a few
+    # hundred / tens on a total energy of 6e6 -- O(eps^2 D) -- well above the fp32 noise of the sums)
+    _, _, _, err_coarse, _ = run(2e-3, 4)
+    zc, rc, gc, err_fine, eps = run(1e-3, 8)
+    assert float((err_fine.abs() / e0.abs()).max()) < 1e-4
+    ratio = (err_coarse / err_fine).cpu()
+    assert bool(((ratio > 3.0) & (ratio < 5.5)).all()), ratio
+    # time reversibility: flip the momentum, integrate back
     rb = (-rc).contiguous()
     zb, gb = zc, gc
-    for _ in range(5):
+    for _ in range(8):
         zb, rb, gb, _, _ = k._leapfrog(zb, rb, gb, eps, minv)
     assert float((zb - z).abs().max()) < 5e-5
     assert float((rb + r0).abs().max()) < 5e-4
