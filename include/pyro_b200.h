@@ -185,6 +185,16 @@ int b2_normal_rsample(const b2_tensor* loc, const b2_tensor* scale, int ndim, co
                       void* eps, void* out_sum, void* rng_state, void* stream);
 
 /*
+ * b2_gamma_rsample -- reparameterised Gamma(concentration, rate) draws (Marsaglia-Tsang on the in-kernel Philox
+ * stream) together with d z / d concentration by implicit reparameterisation: replaces _standard_gamma +
+ * division + clamp (torch/distributions/gamma.py:79-87) and the ATen backward _standard_gamma_grad --
+ * SURVEY.md 8(f) row 1.  conc, rate: broadcast views over `shape`; z, dz_dconc (nullable): contiguous outputs
+ * of prod(shape) elements; rng_state as for b2_normal_rsample.  d z / d rate = -z / rate is left to the caller.
+ */
+int b2_gamma_rsample(const b2_tensor* conc, const b2_tensor* rate, int ndim, const int64_t* shape, void* z,
+                     void* dz_dconc, void* rng_state, void* stream);
+
+/*
  * The "latent sites" block of an SVI step (pyro_b200/csrc/latent.cu): a reparameterised Normal guide site
  * z ~ Normal(loc, scale) -- scale possibly given as log(scale), the unconstrained storage of a positive
  * parameter (pyro/params/param_store.py:125-156) -- together with a Normal prior on the same z whose

@@ -48,6 +48,7 @@ LATENT_LOG_SCALE = 1
 LATENT_ACC_OUT0, LATENT_ACC_OUT1 = 2, 4
 LATENT_BLOCK = True       # Normal guide sites + Normal priors go through the latent-sites kernels (latent.cu)
 LATENT_ACCUMULATE = True  # the draw's backward kernel adds into existing leaf .grad buffers itself
+GAMMA_RSAMPLE = True      # Gamma.rsample draws with the own kernel (b2_gamma_rsample) instead of ATen
 LAZY_PARAM = True         # positive-constrained parameters are handed out as deferred exp(u) (_lazyparam.py)
 
 
@@ -105,6 +106,7 @@ SIGNATURES = {
                               _vp, _tp, _tp, _vp, _sz, _vp]),
     "b2_reduce_to": (_i32, [_tp, _tp, _vp, _sz, _vp]),
     "b2_normal_rsample": (_i32, [_tp, _tp, _i32, ctypes.POINTER(ctypes.c_int64), _vp, _vp, _vp, _vp, _vp]),
+    "b2_gamma_rsample": (_i32, [_tp, _tp, _i32, ctypes.POINTER(ctypes.c_int64), _vp, _vp, _vp, _vp]),
     "b2_latent_normal_draw": (_i32, [_vp, _i32, _vp, _vp]),
     "b2_latent_normal_prior": (_i32, [_vp, _i32, _vp]),
     "b2_latent_normal_backward": (_i32, [_vp, _i32, _vp]),

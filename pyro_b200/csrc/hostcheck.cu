@@ -66,6 +66,25 @@ extern "C" double b2h_digamma(double x) { return digamma<double>(x); }
 extern "C" float b2h_digammaf(float x) { return digamma<float>(x); }
 extern "C" double b2h_trigamma(double x) { return trigamma<double>(x); }
 
+// ---- Gamma sampler + implicit-reparameterisation gradient on the host ---------------------------------
+#include "gamma_sample.cuh"
+extern "C" double b2h_standard_gamma_grad(double a, double x) { return standard_gamma_grad<double>(a, x); }
+extern "C" float b2h_standard_gamma_gradf(float a, float x) { return standard_gamma_grad<float>(a, x); }
+extern "C" void b2h_standard_gamma_sample(uint64_t seed, int64_t n, double a, double* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    Philox r;
+    r.init(seed, (uint64_t)i, 0);
+    out[i] = standard_gamma_sample<double>(a, r);
+  }
+}
+extern "C" void b2h_standard_gamma_samplef(uint64_t seed, int64_t n, float a, float* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    Philox r;
+    r.init(seed, (uint64_t)i, 0);
+    out[i] = standard_gamma_sample<float>(a, r);
+  }
+}
+
 // ---- NUTS core on the host (same code path as nuts_small_kernel, one chain at a time) ----------
 #include "nuts_core.cuh"
 

@@ -519,6 +519,37 @@ class Gamma(_Elementwise):
     def __init__(self, concentration, rate, validate_args=None):
         super().__init__(concentration, rate)
 
+    def rsample(self, sample_shape=torch.Size()):
+        """``_standard_gamma(concentration) / rate`` clamped away from 0 (torch/distributions/gamma.py:79-87).  On
+        the GPU one kernel draws (Marsaglia-Tsang on the in-kernel Philox stream) and evaluates the
+        implicit-reparameterisation derivative d z / d concentration that the backward pass needs
+        (``b2_gamma_rsample``)."""
+        shape = self.shape(sample_shape)
+        conc, rate = densify(self.concentration), densify(self.rate)
+        if (N.GAMMA_RSAMPLE and conc.is_cuda and conc.dtype == rate.dtype and len(shape) <= 6
+                and conc.dtype in (torch.float32, torch.float64) and all(int(d) > 0 for d in shape)):
+            return _GammaRsampleFn.apply(conc, rate, torch.Size(shape))
+        return self._torch().rsample(sample_shape)
+
+
+class _GammaRsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, conc, rate, shape):
+        need = ctx.needs_input_grad[0]
+        z, dz = _ops.gamma_rsample(conc, rate, shape, want_grad=need)
+        ctx.save_for_backward(z, dz, rate)
+        ctx.shapes = (conc.shape, rate.shape)
+        return z
+
+    @staticmethod
+    @_ops.once_differentiable
+    def backward(ctx, gz):
+        z, dz, rate = ctx.saved_tensors
+        cshape, rshape = ctx.shapes
+        gconc = (gz * dz).sum_to_size(cshape) if ctx.needs_input_grad[0] else None
+        grate = (-(gz * z) / rate).sum_to_size(rshape) if ctx.needs_input_grad[1] else None
+        return gconc, grate, None
+
 
 class Beta(_Elementwise):
     family = N.BETA

@@ -415,6 +415,22 @@ def normal_rsample_backward(gz, eps, loc, scale, c, need_loc, need_scale):
     return gp[0], gp[1]
 
 
+def gamma_rsample(conc, rate, shape, want_grad=True):
+    """``(z, dz_dconc)``: reparameterised Gamma(conc, rate) draws of ``shape`` and, with ``want_grad``, the
+    derivative of every draw w.r.t. its concentration -- one launch (b2_gamma_rsample)."""
+    shape = tuple(int(s) for s in shape)
+    dev, dtype = conc.device, conc.dtype
+    N.require_cuda(conc, "Gamma.rsample")
+    z = torch.empty(shape, dtype=dtype, device=dev)
+    dz = torch.empty(shape, dtype=dtype, device=dev) if want_grad else None
+    cd, rd = N.desc(conc, shape), N.desc(rate, shape)
+    shp = (ctypes.c_int64 * max(1, len(shape)))(*shape)
+    N.check(N.lib().b2_gamma_rsample(ctypes.byref(cd), ctypes.byref(rd), len(shape), shp, z.data_ptr(),
+                                     dz.data_ptr() if dz is not None else None, rng_state(dev).data_ptr(),
+                                     N.stream_ptr(dev)), "b2_gamma_rsample")
+    return z, dz
+
+
 # ---- latent-sites block (csrc/latent.cu) -----------------------------------------------------------
 def _latent_job(shape, dtype, loc=None, scale=None, log_scale=False, prior=None, z=None, eps=None, gz=None,
                 out0=None, out1=None, c=0.0, pw=0.0):

@@ -406,6 +406,60 @@ def test_latent_block_kernels(dtype, log_scale):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_gamma_rsample_kernel(dtype):
+    """b2_gamma_rsample through ``Gamma.rsample``: goodness of fit of the draws (Kolmogorov-Smirnov and moments
+    per concentration, in the style of tests/distributions/test_distributions.py:138-164), the
+    implicit-reparameterisation derivative against ATen's ``_standard_gamma_grad`` (the reference's backward of
+    torch/distributions/gamma.py:79-87) on the kernel's own draws, the autograd gradients w.r.t. broadcast
+    concentration / rate, fresh noise per launch and per graph replay, reproducibility after reseeding."""
+    if EMULATE:
+        pytest.skip("kernel test")
+    import pyro_b200 as pyro
+    from scipy import stats
+    pyro.set_rng_seed(3)
+    alphas = torch.tensor([0.15, 0.8, 1.0, 3.5, 40.0], device=DEV, dtype=dtype)
+    rates = torch.tensor([0.5, 2.0, 1.0, 4.0, 10.0], device=DEV, dtype=dtype)
+    n = 40000
+    conc = alphas[:, None].clone().requires_grad_(True)          # [5, 1] broadcast over the draws
+    rate = rates[:, None].clone().requires_grad_(True)
+    z = dist.Gamma(conc, rate).rsample((n,)).squeeze(-1)        # [n, 5]
+    assert z.shape == (n, 5) and bool((z > 0).all())
+    zc = z.detach().double().cpu().numpy()
+    for k, (a, r) in enumerate(zip(alphas.tolist(), rates.tolist())):
+        x = zc[:, k] * r
+        assert stats.kstest(x, "gamma", args=(a,)).pvalue > 1e-3, a
+        assert abs(x.mean() - a) < 5 * (a / n) ** 0.5 and abs(x.var() - a) < 6 * a * (2 / n + 6 / (a * n)) ** 0.5
+    # gradients: d sum(w z) / d conc, d rate with the derivative of every draw from ATen on the same draws
+    w = torch.randn(n, 5, device=DEV, dtype=dtype)
+    gc, gr = torch.autograd.grad((w * z).sum(), [conc, rate])
+    x = (z.detach() * rates).double()
+    ref_dx = torch._standard_gamma_grad(alphas.double().expand(n, 5).contiguous(), x.contiguous())
+    ref_gc = (w.double() * ref_dx / rates.double()).sum(0)
+    ref_gr = (-(w.double() * z.detach().double()) / rates.double()).sum(0)
+    scale_c = (w.double().abs() * ref_dx.abs() / rates.double()).sum(0)
+    assert bool(((gc.squeeze(-1).double() - ref_gc).abs() <= 3e-3 * scale_c).all())   # ATen's own approximation error
+    assert torch.allclose(gr.squeeze(-1).double(), ref_gr, rtol=1e-4 if dtype == torch.float32 else 1e-10)
+    # per-draw derivative against ATen
+    _, dz = _ops.gamma_rsample(alphas.expand(n, 5), rates.expand(n, 5), (n, 5))
+    z2, dz2 = _ops.gamma_rsample(alphas.expand(n, 5), rates.expand(n, 5), (n, 5))
+    ref2 = torch._standard_gamma_grad(alphas.double().expand(n, 5).contiguous(),
+                                      (z2 * rates).double().contiguous()) / rates.double()
+    assert float(((dz2.double() - ref2).abs() / ref2.abs().clamp(min=1e-30)).max()) < 5e-3
+    assert not torch.equal(dz, dz2)
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        zg, _ = _ops.gamma_rsample(alphas, rates, (5,))
+    g.replay()
+    a0 = zg.clone()
+    g.replay()
+    assert not torch.equal(a0, zg)
+    pyro.set_rng_seed(3)
+    again = dist.Gamma(conc, rate).rsample((n,)).squeeze(-1)
+    assert torch.equal(again.detach(), z.detach())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_elbo_combine(dtype):
     """b2_elbo_combine: weighted sum of 0-d device scalars in index order, one launch."""
     torch.manual_seed(0)

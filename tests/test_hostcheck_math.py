@@ -217,3 +217,57 @@ def test_philox_known_answer():
     H.lib().b2h_philox(ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0), 4,
                        out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
     assert [hex(v) for v in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+
+
+def test_standard_gamma_grad_against_finite_differences_and_torch():
+    """csrc/gamma_sample.cuh ``standard_gamma_grad`` (the code b2_gamma_rsample runs, built for the host): the
+    implicit-reparameterisation derivative dx/da against a central finite difference of scipy's inverse
+    incomplete gamma function (fp64, 1e-6), the fp32 evaluation against the fp64 one (3e-4), and ATen's
+    ``_standard_gamma_grad`` -- the reference's backward of ``Gamma.rsample`` (torch/distributions/gamma.py:79-87)
+    -- within the accuracy of ITS approximation (2e-3)."""
+    import ctypes
+    from scipy.special import gammainc, gammaincinv
+    L = H.lib()
+    L.b2h_standard_gamma_grad.restype = ctypes.c_double
+    L.b2h_standard_gamma_grad.argtypes = [ctypes.c_double, ctypes.c_double]
+    L.b2h_standard_gamma_gradf.restype = ctypes.c_float
+    L.b2h_standard_gamma_gradf.argtypes = [ctypes.c_float, ctypes.c_float]
+    rng = np.random.default_rng(0)
+    worst = [0.0, 0.0, 0.0]
+    for a in (0.05, 0.1, 0.3, 0.5, 0.9, 1.0, 1.5, 2.0, 3.0, 5.0, 8.0, 12.0, 20.0, 50.0, 100.0, 300.0, 1000.0):
+        xs = np.concatenate([rng.gamma(a, size=30), [a * 0.1, a, a + 1, a + 1.0001, 3 * a + 3]])
+        for x in xs[xs > 1e-30]:
+            g64 = L.b2h_standard_gamma_grad(a, float(x))
+            g32 = float(L.b2h_standard_gamma_gradf(a, float(x)))
+            p = gammainc(a, x)
+            eps = 1e-6 * max(1.0, a)
+            fd = (gammaincinv(a + eps, p) - gammaincinv(a - eps, p)) / (2 * eps)
+            if np.isfinite(fd) and 1e-12 < p < 1 - 1e-12:
+                worst[0] = max(worst[0], abs(g64 - fd) / abs(fd))
+            worst[1] = max(worst[1], abs(g32 - g64) / abs(g64))
+            t = float(torch._standard_gamma_grad(torch.tensor([a], dtype=torch.float64),
+                                                 torch.tensor([x], dtype=torch.float64)))
+            worst[2] = max(worst[2], abs(t - g64) / abs(g64))
+    assert worst[0] < 1e-6 and worst[1] < 3e-4 and worst[2] < 2e-3, worst
+
+
+def test_standard_gamma_sampler_goodness_of_fit():
+    """Marsaglia-Tsang on the Philox stream (csrc/gamma_sample.cuh, host build): Kolmogorov-Smirnov against the
+    Gamma CDF and the first two moments, shapes below and above 1, fp32 and fp64 (in the style of
+    tests/distributions/test_distributions.py:138-164)."""
+    import ctypes
+    from scipy import stats
+    L = H.lib()
+    n = 40000
+    for a in (0.2, 0.7, 1.0, 2.5, 17.0):
+        out = np.zeros(n, np.float64)
+        L.b2h_standard_gamma_sample(ctypes.c_uint64(7), ctypes.c_int64(n), ctypes.c_double(a),
+                                    out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        outf = np.zeros(n, np.float32)
+        L.b2h_standard_gamma_samplef(ctypes.c_uint64(9), ctypes.c_int64(n), ctypes.c_float(a),
+                                     outf.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        for s in (out, outf.astype(np.float64)):
+            assert (s > 0).all()
+            assert stats.kstest(s, "gamma", args=(a,)).pvalue > 1e-3, a
+            assert abs(s.mean() - a) < 5 * (a / n) ** 0.5
+            assert abs(s.var() - a) < 6 * a * (2 / n + 6 / (a * n)) ** 0.5
