@@ -33,7 +33,7 @@ B2_HD T standard_gamma_grad(T a, T x) {
   if (x < a + one) {
     T Tn = one, S = one, H = (T)0, SH = (T)0;
     for (int n = 1; n < 4000; ++n) {
-      const T inv = one / (a + (T)n);
+      const T inv = fast_rcp(a + (T)n);      // fp32 on the device: MUFU.RCP (1 ulp); an IEEE division is ~10 instructions
       Tn *= x * inv;
       H += inv;
       S += Tn;
@@ -50,10 +50,11 @@ B2_HD T standard_gamma_grad(T a, T x) {
     const T an = -(T)i * ((T)i - a), anp = (T)i;
     b += (T)2;
     const T draw = an * d + b, drawp = anp * d + an * dp - one;
-    const T cn = b + an / c;
-    cp = -one + (anp * c - an * cp) / (c * c);
+    const T ic = fast_rcp(c);
+    const T cn = b + an * ic;
+    cp = -one + (anp * c - an * cp) * (ic * ic);
     c = cn;
-    d = one / draw;
+    d = fast_rcp(draw);
     dp = -drawp * d * d;
     const T de = d * c, dep = dp * c + d * cp;
     hp = hp * de + h * dep;
