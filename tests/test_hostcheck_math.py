@@ -271,3 +271,65 @@ def test_standard_gamma_sampler_goodness_of_fit():
             assert stats.kstest(s, "gamma", args=(a,)).pvalue > 1e-3, a
             assert abs(s.mean() - a) < 5 * (a / n) ** 0.5
             assert abs(s.var() - a) < 6 * a * (2 / n + 6 / (a * n)) ** 0.5
+
+
+def test_beta_shared_evaluation_sweep_fp32():
+    """Round 2's Beta functor evaluates lgamma(c1+c0) - lgamma(c1) - lgamma(c0) and the three digammas together
+    (one reciprocal, one shift logarithm; csrc/b2_math.cuh ``lbeta_terms_f32``): log density and both parameter
+    gradients over five decades of both concentrations -- including the hand-over points of the joint route
+    (1e-6, a sum of 1e9, the shift at 4) -- against the fp64 reference formulas (beta.py:87-91 ->
+    dirichlet.py:90-97), same tolerances as the Gamma sweep."""
+    g = np.concatenate([np.logspace(-2.5, 2.5, 40), [0.5, 1.0, 3.999999, 4.0, 4.000001]])
+    c1, c0 = [v.ravel() for v in np.meshgrid(g, g)]
+    extra1 = np.array([5e-7, 2e-6, 1e-6, 0.3, 6e8, 7e8, 2.0, 1e-3])
+    extra0 = np.array([0.4, 5e-7, 2.0, 9e8, 6e8, 2e8, 3.999999, 1e3])
+    c1, c0 = np.concatenate([c1, extra1]), np.concatenate([c0, extra0])
+    x = np.full_like(c1, 0.37)
+    lp, _, dp = H.eval_family(3, x, [c1, c0], np.float32)
+    a1 = torch.tensor(c1, requires_grad=True)
+    a0 = torch.tensor(c0, requires_grad=True)
+    ref = torch.distributions.Beta(a1, a0).log_prob(torch.tensor(x))
+    g1, g0 = torch.autograd.grad(ref.sum(), [a1, a0])
+    ref, g1, g0 = ref.detach().numpy(), g1.numpy(), g0.numpy()
+    # the density is a difference of terms that reach 1e3 .. 2e10 at these concentrations: the fp32 bound is
+    # relative to the LARGEST term (torch's own fp32 evaluation shows the same cancellation), not to the result
+    from scipy.special import gammaln
+    terms = (np.abs(gammaln(c1 + c0)) + np.abs(gammaln(c1)) + np.abs(gammaln(c0)) +
+             np.abs((c1 - 1) * np.log(0.37)) + np.abs((c0 - 1) * np.log(0.63)))
+    tol = 1e-5 * np.maximum(1, np.abs(ref)) + 3e-7 * terms
+    assert np.all(np.abs(lp - ref) <= tol), float(np.max(np.abs(lp - ref) / tol))
+    ref32 = torch.distributions.Beta(torch.tensor(c1, dtype=torch.float32), torch.tensor(c0, dtype=torch.float32)
+                                     ).log_prob(torch.tensor(x, dtype=torch.float32)).numpy()
+    assert np.max(np.abs(lp - ref) / tol) <= 2 * max(1.0, np.max(np.abs(ref32 - ref) / tol))
+    gt = 2e-4 + 3e-6 * np.log(c1 + c0 + 2)
+    assert np.all(np.abs(dp[0] - g1) <= gt * np.maximum(1, np.abs(g1)))
+    assert np.all(np.abs(dp[1] - g0) <= gt * np.maximum(1, np.abs(g0)))
+
+
+def test_poisson_and_lognormal_fast_paths_fp32():
+    """The fp32 device routes added in round 2 share their algebra with the host build: Poisson (integer counts
+    below / above the 64-entry log-factorial table, non-integer values) and LogNormal / Exponential / HalfNormal
+    (reciprocal + logarithm form) against torch's fp64 formulas."""
+    k = np.concatenate([np.arange(0, 80, dtype=np.float64), [63.0, 64.0, 1000.0, 2.5, 0.3]])
+    rate = np.linspace(0.05, 60.0, k.size)
+    lp, _, dp = H.eval_family(4, k, [rate], np.float32)
+    rt = torch.tensor(rate, requires_grad=True)
+    ref = torch.tensor(k) * rt.log() - rt - torch.lgamma(torch.tensor(k) + 1)
+    (gr,) = torch.autograd.grad(ref.sum(), rt)
+    assert np.all(np.abs(lp - ref.detach().numpy()) <= 1e-5 * np.maximum(1, np.abs(ref.detach().numpy())))
+    assert np.all(np.abs(dp[0] - gr.numpy()) <= 2e-4 * np.maximum(1, np.abs(gr.numpy())))
+    x = np.logspace(-3, 3, 60)
+    loc, sc = np.linspace(-2, 2, 60), np.logspace(-1, 1, 60)
+    for fam, tdist, params in ((8, torch.distributions.LogNormal, [loc, sc]),
+                               (7, torch.distributions.Exponential, [sc]),
+                               (9, torch.distributions.HalfNormal, [sc])):
+        lp, dx, dp = H.eval_family(fam, x, params, np.float32)
+        ps = [torch.tensor(p, requires_grad=True) for p in params]
+        xt = torch.tensor(x, requires_grad=True)
+        ref = tdist(*ps).log_prob(xt)
+        grads = torch.autograd.grad(ref.sum(), [xt] + ps)
+        r = ref.detach().numpy()
+        assert np.all(np.abs(lp - r) <= 1e-5 * np.maximum(1, np.abs(r))), fam
+        assert np.all(np.abs(dx - grads[0].numpy()) <= 2e-4 * np.maximum(1, np.abs(grads[0].numpy()))), fam
+        for got, want in zip(dp, grads[1:]):
+            assert np.all(np.abs(got - want.numpy()) <= 2e-4 * np.maximum(1, np.abs(want.numpy()))), fam
